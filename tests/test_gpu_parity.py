@@ -1,0 +1,312 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, on a B200.
+
+Tolerances: fp64 operator and RK4 results within 1e-12 relative L2 of the oracle
+(BASELINE.json north_star); geometry factors and the lumped mass are bit-exact because
+the GPU precompute follows the oracle's operation order with explicit rounding; fp32
+within 2e-5 relative L2.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+L = 0.1
+TOL64 = 1e-12
+TOL32 = 2e-5
+
+
+def rel_l2(a, b):
+    return np.linalg.norm(np.asarray(a, dtype=np.float64) - b) / np.linalg.norm(b)
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return torch
+
+
+def dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _mesh(wfx, N, P, perturb=0.15, **kw):
+    return wfx.create_box_hex(N, P, (L, L, L), perturb=perturb, **kw)
+
+
+# ---- a1: geometry ---------------------------------------------------------------------------
+@pytest.mark.parametrize("P,perturb", [(2, 0.0), (4, 0.0), (4, 0.15), (3, 0.15), (7, 0.15)])
+def test_geometry_bit_exact(wfx, orc, torch, P, perturb):
+    mesh = _mesh(wfx, 3 if P < 7 else 2, P, perturb)
+    G, detJ = wfx.Geometry(mesh, P).get()
+    Go, detJo = orc.precompute_geometric_data(mesh, P)
+    assert np.array_equal(detJ, detJo)
+    iu = np.triu_indices(3)
+    assert np.array_equal(G[:, :, iu[0], iu[1]], Go[:, :, iu[0], iu[1]])  # stored entries: bit-exact
+    assert np.array_equal(G, np.swapaxes(G, 2, 3))                        # symmetric storage
+    assert rel_l2(G, Go) < 1e-15                                          # mirrored entries: roundoff
+
+
+def test_geometry_clamp_triggers_like_reference(wfx, orc, torch):
+    # tiny cells: legitimate G entries below 1e-8 are zeroed
+    mesh = wfx.create_box_hex(2, 4, (2e-4,) * 3)
+    G, _ = wfx.Geometry(mesh, 4).get()
+    Go, _ = orc.precompute_geometric_data(mesh, 4)
+    assert np.array_equal(G, Go) and (np.diagonal(G, axis1=2, axis2=3) == 0).any()
+
+
+def test_general_point_jacobian_data(wfx, orc, torch):
+    mesh = _mesh(wfx, 3, 2)
+    pts, wts = orc.gauss_legendre(3)
+    P3 = np.array([[a, b, c] for a in pts for b in pts for c in pts])
+    W3 = np.array([a * b * c for a in wts for b in wts for c in wts])
+    got = wfx.compute_jacobian_data(mesh, P3, W3)
+    want = orc.jacobian_data(mesh, P3, W3)
+    for k in ("J", "detJ", "K", "G"):
+        assert np.array_equal(got[k], want[k]), k
+
+
+# ---- a3: mass ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("P,renumber", [(2, None), (4, None), (4, 5), (5, 9)])
+def test_lumped_mass_bit_exact_and_apply(wfx, orc, torch, P, renumber):
+    mesh = _mesh(wfx, 3, P, renumber=renumber)
+    op = wfx.MassOperator(mesh, P)
+    _, detJ = orc.precompute_geometric_data(mesh, P)
+    m = np.zeros(mesh.ndofs)
+    orc.mass_apply(mesh, P, detJ, np.ones(mesh.ndofs), m)  # m = M.1 (LinearGLL.hpp:102-110)
+    assert np.array_equal(op.diagonal(), m)
+    assert np.array_equal(op.inverse_diagonal(), 1.0 / m)
+    x = np.random.default_rng(42).standard_normal(mesh.ndofs)
+    y0 = np.random.default_rng(43).standard_normal(mesh.ndofs)
+    yo = y0.copy()
+    orc.mass_apply(mesh, P, detJ, x, yo)
+    yd = dev(torch, y0)
+    op(dev(torch, x), yd)  # y += M x
+    assert rel_l2(yd.cpu().numpy(), yo) < 1e-15
+    yh = y0.copy()
+    op(x, yh)              # host path
+    assert np.array_equal(yh, yd.cpu().numpy())
+
+
+# ---- a4: stiffness ------------------------------------------------------------------------------
+CASES = [(2, 4, 0.15, None), (2, 9, 0.15, 3), (3, 5, 0.15, None), (4, 4, 0.0, None), (4, 4, 0.15, None),
+         (4, 6, 0.15, 17), (5, 3, 0.15, None), (6, 2, 0.15, 1), (7, 2, 0.15, None)]
+
+
+@pytest.mark.parametrize("mode", ["brick", "cell_colour"])
+@pytest.mark.parametrize("P,N,perturb,renumber", CASES)
+def test_stiffness_matches_dense_reference_kernel(wfx, orc, torch, mode, P, N, perturb, renumber):
+    mesh = _mesh(wfx, N, P, perturb, renumber=renumber)
+    flag = wfx.capi.STIFF_AUTO if mode == "brick" else wfx.capi.STIFF_CELL_COLOUR
+    op = wfx.StiffnessOperator(mesh, P, {"c0": 1500.0}, mode=flag)
+    Go, _ = orc.precompute_geometric_data(mesh, P)
+    rng = np.random.default_rng(42)
+    x, y0 = rng.standard_normal(mesh.ndofs), rng.standard_normal(mesh.ndofs)
+    yo = y0.copy()
+    orc.stiffness_apply(mesh, P, Go, x, yo, dense=True)   # the reference's skernel
+    kx = yo - y0
+    yd = dev(torch, y0)
+    op(dev(torch, x), yd)                                  # y += A x
+    assert rel_l2(yd.cpu().numpy() - y0, kx) < TOL64
+    yd2 = dev(torch, y0)
+    op.apply(dev(torch, x), yd2, beta=0)                   # y = A x, old y never read
+    assert rel_l2(yd2.cpu().numpy(), kx) < TOL64
+    # deterministic: bitwise repeatable
+    yd3 = torch.full_like(yd2, float("nan"))
+    op.apply(dev(torch, x), yd3, beta=0)
+    assert torch.equal(yd2, yd3)
+
+
+def test_stiffness_host_call_shape(wfx, orc, torch):
+    mesh = _mesh(wfx, 4, 4)
+    op = wfx.StiffnessOperator(mesh, 4, {"c0": 1.0})       # params ignored like the reference: c0 = 1500
+    Go, _ = orc.precompute_geometric_data(mesh, 4)
+    x = np.random.default_rng(0).standard_normal(mesh.ndofs)
+    y, yo = np.zeros(mesh.ndofs), np.zeros(mesh.ndofs)
+    op(x, y)
+    orc.stiffness_apply(mesh, 4, Go, x, yo)
+    assert rel_l2(y, yo) < TOL64
+    with pytest.raises(wfx.WfxError):
+        op(x[:-1].copy(), y)
+    with pytest.raises(wfx.WfxError):
+        op(x.astype(np.float32), y)
+
+
+def test_stiffness_fused_mass_inverse(wfx, orc, torch):
+    P = 4
+    mesh = _mesh(wfx, 5, P, renumber=2)
+    geo = wfx.Geometry(mesh, P)
+    op = wfx.StiffnessOperator(mesh, P, geometry=geo)
+    mass = wfx.MassOperator(mesh, P, geometry=geo)
+    Go, _ = orc.precompute_geometric_data(mesh, P)
+    x = np.random.default_rng(3).standard_normal(mesh.ndofs)
+    b = np.zeros(mesh.ndofs)
+    orc.stiffness_apply(mesh, P, Go, x, b)
+    want = b / mass.diagonal()                              # LinearGLL.hpp:188-191
+    y = torch.full((mesh.ndofs,), float("nan"), dtype=torch.float64, device="cuda")
+    op.apply_scaled(dev(torch, x), mass.inverse_diagonal_ptr(), y)
+    assert rel_l2(y.cpu().numpy(), want) < TOL64
+
+
+def test_stiffness_ghost_only_entries_and_errors(wfx, orc, torch):
+    # vector longer than the dofs the cells reference (ghost-only slots): y = A x zeroes them
+    import copy
+    mesh = copy.copy(_mesh(wfx, 3, 2))
+    mesh.ndofs += 7
+    op = wfx.StiffnessOperator(mesh, 2)
+    x = torch.ones(mesh.ndofs, dtype=torch.float64, device="cuda")
+    y = torch.full_like(x, float("nan"))
+    op.apply(x, y, beta=0)
+    assert torch.isfinite(y).all() and (y[-7:] == 0).all()
+    with pytest.raises(wfx.WfxError, match="alias"):
+        op.apply(x, x, beta=0)
+
+
+@pytest.mark.parametrize("P", [2, 4, 6])
+def test_stiffness_fp32(wfx, orc, torch, P):
+    mesh = _mesh(wfx, 4 if P < 6 else 2, P)
+    op = wfx.StiffnessOperator(mesh, P, dtype=np.float32)
+    Go, _ = orc.precompute_geometric_data(mesh, P)
+    x = np.random.default_rng(1).standard_normal(mesh.ndofs)
+    yo = np.zeros(mesh.ndofs)
+    orc.stiffness_apply(mesh, P, Go, x.astype(np.float32).astype(np.float64), yo, dense=False)
+    y = torch.zeros(mesh.ndofs, dtype=torch.float32, device="cuda")
+    op(dev(torch, x.astype(np.float32)), y)
+    assert rel_l2(y.cpu().numpy(), yo) < TOL32
+
+
+def test_stiffness_medium_mesh_vs_sumfact_oracle(wfx, orc, torch):
+    P, N = 4, 16
+    mesh = _mesh(wfx, N, P)
+    op = wfx.StiffnessOperator(mesh, P)
+    Go, _ = orc.precompute_geometric_data(mesh, P)
+    x = np.random.default_rng(42).standard_normal(mesh.ndofs)
+    yo = np.zeros(mesh.ndofs)
+    orc.stiffness_apply(mesh, P, Go, x, yo, dense=False, nthreads=orc.max_threads())
+    y = torch.zeros(mesh.ndofs, dtype=torch.float64, device="cuda")
+    op(dev(torch, x), y)
+    assert rel_l2(y.cpu().numpy(), yo) < TOL64
+
+
+def test_config2_full_size_properties(wfx, torch):
+    """BASELINE config 2 (64^3 cells, P4, 16 974 593 dofs): size-independent properties --
+    the two kernels agree, constants are annihilated, K is symmetric, and the energy of a
+    linear field is exact."""
+    P, N = 4, 64
+    mesh = wfx.create_box_hex(N, P, (L, L, L), perturb=0.0)
+    assert mesh.ndofs == 16974593
+    geo = wfx.Geometry(mesh, P)
+    brick = wfx.StiffnessOperator(mesh, P, geometry=geo)
+    simple = wfx.StiffnessOperator(mesh, P, geometry=geo, mode=wfx.capi.STIFF_CELL_COLOUR)
+    g = torch.Generator(device="cuda").manual_seed(42)
+    x1 = torch.randn(mesh.ndofs, dtype=torch.float64, device="cuda", generator=g)
+    x2 = torch.randn(mesh.ndofs, dtype=torch.float64, device="cuda", generator=g)
+    y1, y1s, y2 = torch.empty_like(x1), torch.empty_like(x1), torch.empty_like(x1)
+    brick.apply(x1, y1, beta=0)
+    simple.apply(x1, y1s, beta=0)
+    assert float((y1 - y1s).norm() / y1.norm()) < 1e-14
+    brick.apply(x2, y2, beta=0)
+    a, b = float(x2 @ y1), float(x1 @ y2)
+    assert abs(a - b) < 1e-11 * abs(a)
+    ones = torch.ones_like(x1)
+    brick.apply(ones, y2, beta=0)
+    assert float(y2.abs().max()) < 1e-9 * 1500.0 ** 2 * (L / N)
+    X = torch.from_numpy(wfx.dof_coordinates(mesh)).cuda()
+    av = torch.tensor([1.0, -2.0, 0.5], dtype=torch.float64, device="cuda")
+    xl = X @ av
+    brick.apply(xl, y2, beta=0)
+    want = -1500.0 ** 2 * float(av @ av) * L ** 3
+    assert abs(float(xl @ y2) - want) < 1e-11 * abs(want)
+
+
+# ---- a5: boundary form -------------------------------------------------------------------------
+def test_boundary_operator(wfx, orc, torch):
+    P = 4
+    mesh = _mesh(wfx, 3, P)
+    op = wfx.BoundaryOperator(mesh, P)
+    m1o, m2o = orc.boundary_facet_mass(mesh, P)
+    m1, m2 = op.facet_masses()
+    np.testing.assert_allclose(m1, m1o, rtol=1e-14, atol=0)
+    np.testing.assert_allclose(m2, m2o, rtol=1e-14, atol=0)
+    rng = np.random.default_rng(8)
+    vn, b0 = rng.standard_normal(mesh.ndofs), rng.standard_normal(mesh.ndofs)
+    c0, g = 1500.0, 123.456
+    want = b0 + c0 * c0 * g * m1o - c0 * m2o * vn
+    b = dev(torch, b0)
+    op.apply(c0, g, dev(torch, vn), b)
+    got = b.cpu().numpy()
+    assert rel_l2(got - b0, want - b0) < 1e-14
+    assert np.array_equal(got[(m1o == 0) & (m2o == 0)], b0[(m1o == 0) & (m2o == 0)])
+
+
+# ---- a6/a7: f1 + RK4 (cpu_planar3d in miniature, config 1) ----------------------------------------
+@pytest.mark.parametrize("shape,perturb,steps", [((8, 8, 8), 0.0, 60), ((6, 5, 4), 0.15, 40)])
+def test_rk4_matches_reference_time_stepper(wfx, orc, torch, shape, perturb, steps):
+    P, c0, f0, p0 = 4, 1500.0, 0.5e6, 6e4
+    mesh = wfx.create_box_hex(shape, P, (L * shape[0] / 8, L * shape[1] / 8, L * shape[2] / 8),
+                              perturb=perturb)
+    Go, detJ = orc.precompute_geometric_data(mesh, P)
+    m = np.zeros(mesh.ndofs)
+    orc.mass_apply(mesh, P, detJ, np.ones(mesh.ndofs), m)
+    m1, m2 = orc.boundary_facet_mass(mesh, P)
+    dt = wfx.cfl_timestep(mesh.h_min, c0, P, f0)
+    tf = L / c0 + 8.0 / f0                                   # cpu_planar3d/main.cpp:64
+    uo, vo = np.zeros(mesh.ndofs), np.zeros(mesh.ndofs)
+    so, to = orc.rk4(mesh, P, Go, m, m1, m2, c0, f0, p0, 0.0, tf, dt, uo, vo, max_steps=steps,
+                     sumfact=True, nthreads=orc.max_threads())
+    eqn = wfx.LinearGLLOpt(mesh, None, P, c0, f0, p0)
+    eqn.init()
+    s, t = eqn.rk4(0.0, tf, dt, max_steps=steps)
+    u, v = eqn.get_state()
+    assert (s, t) == (so, to) and s == steps
+    assert np.abs(uo).max() > 0
+    assert rel_l2(u, uo) < TOL64 and rel_l2(v, vo) < TOL64
+
+
+def test_rk4_final_short_step(wfx, orc, torch):
+    # `while (t < tf)` with dt = min(dt, tf - t) (LinearGLL.hpp:241-242): last step shortened
+    P, c0, f0, p0 = 2, 1500.0, 0.5e6, 6e4
+    mesh = wfx.create_box_hex(4, P, (0.01,) * 3)
+    Go, detJ = orc.precompute_geometric_data(mesh, P)
+    m = np.zeros(mesh.ndofs)
+    orc.mass_apply(mesh, P, detJ, np.ones(mesh.ndofs), m)
+    m1, m2 = orc.boundary_facet_mass(mesh, P)
+    dt = wfx.cfl_timestep(mesh.h_min, c0, P, f0)
+    tf = 10.4 * dt
+    uo, vo = np.zeros(mesh.ndofs), np.zeros(mesh.ndofs)
+    so, to = orc.rk4(mesh, P, Go, m, m1, m2, c0, f0, p0, 0.0, tf, dt, uo, vo)
+    eqn = wfx.LinearGLLOpt(mesh, None, P, c0, f0, p0)
+    eqn.init()
+    s, t = eqn.rk4(0.0, tf, dt)
+    u, v = eqn.get_state()
+    assert s == so == 11 and t == to
+    assert rel_l2(u, uo) < TOL64 and rel_l2(v, vo) < TOL64
+
+
+# ---- L1 primitives --------------------------------------------------------------------------------
+def test_gather_and_scatter_add(wfx, torch):
+    import ctypes as C
+    capi = wfx.capi
+    ctx = wfx.Context.get()
+    mesh = _mesh(wfx, 3, 2)
+    idx = np.ascontiguousarray(mesh.dofmap.reshape(-1), dtype=np.int32)
+    # demo/gpu_scatter_local/main.cpp:70-90: gather of iota reproduces the dofmap
+    x = torch.arange(mesh.ndofs, dtype=torch.float64, device="cuda")
+    xe = torch.empty(idx.size, dtype=torch.float64, device="cuda")
+    didx = torch.from_numpy(idx).cuda()
+    capi.call("wfx_gather", ctx.handle, capi.F64, idx.size, C.c_void_p(didx.data_ptr()),
+              C.c_void_p(x.data_ptr()), C.c_void_p(xe.data_ptr()), None)
+    assert np.array_equal(xe.cpu().numpy(), idx.astype(np.float64))
+    # scatter-add without atomics equals the serial loop, bitwise
+    plan = C.c_void_p()
+    capi.call("wfx_scatter_plan_create", ctx.handle, idx.size, capi.i32p(idx), mesh.ndofs, C.byref(plan))
+    vals = np.random.default_rng(0).standard_normal(idx.size)
+    want = np.zeros(mesh.ndofs)
+    for i, j in enumerate(idx):
+        want[j] += vals[i]
+    out = torch.zeros(mesh.ndofs, dtype=torch.float64, device="cuda")
+    capi.call("wfx_scatter_add", plan, capi.F64, C.c_void_p(dev(torch, vals).data_ptr()),
+              C.c_void_p(out.data_ptr()), 1, None)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), want)
+    capi.call("wfx_scatter_plan_destroy", plan)

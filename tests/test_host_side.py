@@ -1,0 +1,142 @@
+"""CPU-side checks of the product: host tables against the oracle, the C-ABI library loads
+and exports every symbol include/wavefx.h declares, mesh generator invariants, and the
+atomic-free scatter plans (built and verified on the host, no GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(wfx):
+    hdr = open(os.path.join(ROOT, "include", "wavefx.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(wfx_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) > 40
+    lib = ctypes.CDLL(wfx.capi.LIB_PATH)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.wfx_version() == 100
+    # every declared symbol is bound in the Python layer too
+    bound = set(wfx.capi._SIG) | {"wfx_last_error", "wfx_version"}
+    assert not [n for n in names if n not in bound]
+
+
+def test_no_gpu_fails_loudly(wfx):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(wfx.WfxError, match="no CPU fallback|no CUDA device"):
+        wfx.Context(0)
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7])
+def test_tables_match_oracle(wfx, orc, P):
+    assert (wfx.capi.compute_permutations(P) == orc.perm(P)).all()
+    p, w = wfx.capi.gll(P)
+    po, wo = orc.gll(P)
+    np.testing.assert_allclose(p, po, rtol=0, atol=2e-16)
+    np.testing.assert_allclose(w, wo, rtol=4e-16, atol=0)
+    D, Do = wfx.capi.deriv_1d(P), orc.deriv_1d(P)
+    np.testing.assert_allclose(D, Do, rtol=1e-14, atol=1e-14)
+    assert ((D == 0) == (Do == 0)).all()
+
+
+def test_reorder_dofmap_contract(wfx, orc):
+    # common/permute.hpp:22-26: out[c*nd+t] = in[c*nd+perm[t]]
+    P = 3
+    mesh = wfx.create_box_hex(2, P, renumber=3)
+    out = wfx.capi.reorder_dofmap(mesh.dofmap, P)
+    perm = wfx.capi.compute_permutations(P)
+    assert (out == mesh.dofmap[:, perm]).all()
+    assert (out == orc.reorder_dofmap(mesh.dofmap, P)).all()
+
+
+def test_tabulate_1d_matches_oracle(wfx, orc):
+    for P, q in [(2, 4), (4, 8), (5, 10)]:
+        for d in (0, 1):
+            np.testing.assert_allclose(wfx.capi.tabulate_1d(P, q, d), orc.tabulate_1d(P, q, d),
+                                       rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("P", [2, 4])
+def test_mesh_generator(wfx, P):
+    N = 3
+    mesh = wfx.create_box_hex(N, P, (0.1, 0.1, 0.1))
+    assert mesh.ndofs == (P * N + 1) ** 3 and mesh.dofmap.shape == (N ** 3, (P + 1) ** 3)
+    # every dof referenced, shared dofs coincide geometrically
+    assert np.array_equal(np.unique(mesh.dofmap), np.arange(mesh.ndofs))
+    X = wfx.dof_coordinates(mesh)
+    pts, _ = wfx.capi.gll(P)
+    perm = wfx.capi.compute_permutations(P)
+    n = P + 1
+    h = 0.1 / N
+    for c in (0, 13, 26):
+        cz, cy, cx = c % N, (c // N) % N, c // (N * N)
+        for t in (0, 7, n ** 3 - 1, n ** 3 // 2):
+            i, j, k = t // (n * n), (t // n) % n, t % n
+            want = np.array([(cx + pts[i]) * h, (cy + pts[j]) * h, (cz + pts[k]) * h])
+            np.testing.assert_allclose(X[mesh.dofmap[c, perm[t]]], want, atol=1e-15)
+    # vertex dofs 0..7 sit on the geometry vertices in the same order
+    np.testing.assert_allclose(X[mesh.dofmap[:, :8]], mesh.x[mesh.xdofs], atol=1e-15)
+    # tags: 1 on x=0 (local facet 2), 2 on x=L (local facet 3)
+    assert set(mesh.facet_local[mesh.facet_tags == 1]) == {2}
+    assert set(mesh.facet_local[mesh.facet_tags == 2]) == {3}
+    assert (mesh.facet_tags == 1).sum() == N * N
+
+
+def _centroids(mesh):
+    return mesh.x[mesh.xdofs].mean(axis=1)
+
+
+@pytest.mark.parametrize("P,N,be,W", [(4, 8, 4, 8), (4, 6, 4, 8), (2, 8, 8, 16), (3, 5, 4, 8),
+                                      (5, 4, 2, 1), (7, 2, 2, 1)])
+def test_brick_plan_structured(wfx, P, N, be, W):
+    mesh = wfx.create_box_hex(N, P, perturb=0.15)
+    s = wfx.capi.debug_plan_stats(P, mesh.dofmap, mesh.ndofs, _centroids(mesh), be, W)
+    nb_axis = -(-N // be)
+    assert s["batches"] == nb_axis ** 3
+    assert s["batch_colours"] == min(8, s["batches"])
+    assert s["cell_colours"] == 8
+    assert s["nloc_max"] == (P * min(be, N) + 1) ** 3
+    assert s["untouched"] == 0
+    if N % be == 0 and be ** 3 // 8 >= W:
+        assert s["padded_slots"] == 0
+
+
+def test_brick_plan_random_numbering_and_no_geometry(wfx):
+    P, N = 4, 4
+    mesh = wfx.create_box_hex(N, P, renumber=11)
+    rng = np.random.default_rng(5)
+    shuffled = mesh.dofmap[rng.permutation(mesh.ncells)]
+    # without centroids the plan batches cells in the given (here random) order: still valid
+    s = wfx.capi.debug_plan_stats(P, shuffled, mesh.ndofs, None, 4, 8)
+    assert s["batches"] >= 1 and s["untouched"] == 0
+    # a tight shared-memory capacity forces batch splitting
+    s2 = wfx.capi.debug_plan_stats(P, mesh.dofmap, mesh.ndofs, _centroids(mesh), 4, 8, nloc_cap=2000)
+    assert s2["nloc_max"] <= 2000 and s2["batches"] > 1
+    # vector entries no cell references (ghost-only slots) are reported
+    s3 = wfx.capi.debug_plan_stats(P, mesh.dofmap, mesh.ndofs + 5, _centroids(mesh), 4, 8)
+    assert s3["untouched"] == 5
+
+
+def test_plan_rejects_bad_dofmap(wfx):
+    mesh = wfx.create_box_hex(2, 2)
+    bad = mesh.dofmap.copy()
+    bad[0, 0] = mesh.ndofs
+    with pytest.raises(wfx.WfxError, match="out of range"):
+        wfx.capi.debug_plan_stats(2, bad, mesh.ndofs, None, 4, 8)
+
+
+def test_cfl_timestep_matches_reference_formula(wfx):
+    # demo/cpu_planar3d/main.cpp:61-66 with mesh::h = sqrt(3) * side (App. A.7)
+    side = 0.1 / 16
+    mesh = wfx.create_box_hex(2, 4, (2 * side,) * 3)
+    assert abs(mesh.h_min - np.sqrt(3) * side) < 1e-15
+    dt = wfx.cfl_timestep(mesh.h_min, 1500.0, 4, 0.5e6)
+    raw = 0.5 * np.sqrt(3) * side / (1500.0 * 16)
+    spp = int(2e-6 / raw + 1)
+    assert dt == 2e-6 / spp and dt <= raw

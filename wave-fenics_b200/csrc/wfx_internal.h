@@ -1,0 +1,139 @@
+// Internal declarations shared by the libwavefx translation units.
+#pragma once
+
+#include "wavefx.h"
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#define WFX_MAXN 12 // max GLL points per direction handled by the host tables
+
+struct wfx_stiffness;
+
+namespace wfx
+{
+void set_error(const char* fmt, ...);
+
+struct Error : std::runtime_error
+{
+  using std::runtime_error::runtime_error;
+};
+
+[[noreturn]] void fail(const char* fmt, ...);
+
+#define WFX_CUDA(call)                                                                           \
+  do                                                                                             \
+  {                                                                                              \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      wfx::fail("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));      \
+  } while (0)
+
+// Body wrapper for every extern "C" entry point: exceptions -> status + message.
+#define WFX_API_BEGIN try {
+#define WFX_API_END                                                                              \
+  return 0;                                                                                      \
+  }                                                                                              \
+  catch (const std::exception& e)                                                                \
+  {                                                                                              \
+    wfx::set_error("%s", e.what());                                                              \
+    return 1;                                                                                    \
+  }                                                                                              \
+  catch (...)                                                                                    \
+  {                                                                                              \
+    wfx::set_error("unknown error");                                                             \
+    return 2;                                                                                    \
+  }
+
+// RAII device buffer (role of cuda::array<T>, common/cuda/array.hpp, without its
+// implicit-copy double free).
+template <typename T>
+struct DevBuf
+{
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  explicit DevBuf(size_t n_) { alloc(n_); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept
+  {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t n_)
+  {
+    release();
+    n = n_;
+    if (n) WFX_CUDA(cudaMalloc((void**)&p, n * sizeof(T)));
+  }
+  void release()
+  {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void upload(const T* h, size_t cnt)
+  {
+    if (cnt > n) alloc(cnt);
+    if (cnt) WFX_CUDA(cudaMemcpy(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  void upload(const std::vector<T>& h) { upload(h.data(), h.size()); }
+  void download(T* h, size_t cnt) const
+  {
+    if (cnt) WFX_CUDA(cudaMemcpy(h, p, cnt * sizeof(T), cudaMemcpyDeviceToHost));
+  }
+};
+
+// host tables (wfx_tables.cpp)
+void gll_points_weights(int P, double* pts, double* wts); // [0,1,interior] ordering
+void deriv_1d(int P, double* D, bool clamp);              // D[q*n+i]
+void tensor_perm(int P, int32_t* perm);                   // tensor index -> DOLFINx dof
+double clamp_m101(double v);                              // xt::isclose clamp to -1/0/1
+
+int stiffness_dtype(const struct ::wfx_stiffness* op); // wfx_stiffness.cu
+
+struct ScopedDevice
+{
+  int prev = -1;
+  explicit ScopedDevice(int dev)
+  {
+    cudaGetDevice(&prev);
+    if (prev != dev) WFX_CUDA(cudaSetDevice(dev));
+  }
+  ~ScopedDevice() { if (prev >= 0) cudaSetDevice(prev); }
+};
+} // namespace wfx
+
+struct wfx_ctx
+{
+  int device = 0;
+  int num_sms = 0;
+  size_t smem_optin = 0;
+};
+
+// Geometric factors on the device (kernel layout).
+//   nq = n^3 points per cell, n = P+1, n2 = n^2.
+//   point index inside a cell is "k-major": r = k*n2 + (i*n + j) for tensor node (i,j,k)
+//   (i <-> x, slowest in the reference's tensor order; k <-> z).
+//   G6  [ncells][6][nq]  components (00,01,02,11,12,22), dtype T
+//   dJw [ncells][nq]     detJ * w, fp64 (setup-only consumers)
+struct wfx_geom
+{
+  wfx_ctx* ctx = nullptr;
+  int P = 0, n = 0, nq = 0, dtype = WFX_F64;
+  int64_t ncells = 0;
+  void* G6 = nullptr;     // T
+  double* dJw = nullptr;  // fp64
+  // cell centroids (host) for the locality-preserving batch plan
+  std::vector<float> centroid; // [ncells][3]
+  ~wfx_geom();
+};

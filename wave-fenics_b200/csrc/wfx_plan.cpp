@@ -1,0 +1,436 @@
+// Host-side construction and verification of the atomic-free scatter plans
+// (see wfx_plan.h).  Pure C++: runs without a GPU, so the plans are unit-tested on CPU.
+#include "wfx_plan.h"
+#include "wfx_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+namespace wfx
+{
+namespace
+{
+inline int lowest_zero_bit(uint64_t m)
+{
+  if (~m == 0) return -1;
+  return __builtin_ctzll(~m);
+}
+} // namespace
+
+void build_cell_colour_plan(int nd, int64_t ncells, int64_t ndofs, const int32_t* tdm,
+                            CellColourPlan& plan)
+{
+  std::vector<uint64_t> dofmask((size_t)ndofs, 0);
+  std::vector<uint8_t> colour((size_t)ncells);
+  int ncol = 0;
+  for (int64_t c = 0; c < ncells; ++c)
+  {
+    const int32_t* d = tdm + c * nd;
+    uint64_t m = 0;
+    for (int t = 0; t < nd; ++t) m |= dofmask[d[t]];
+    const int col = lowest_zero_bit(m);
+    if (col < 0) fail("cell colouring needs more than 64 colours");
+    const uint64_t bit = 1ull << col;
+    for (int t = 0; t < nd; ++t) dofmask[d[t]] |= bit;
+    colour[c] = (uint8_t)col;
+    ncol = std::max(ncol, col + 1);
+  }
+  plan.ncolours = ncol;
+  plan.colour_off.assign(ncol + 1, 0);
+  for (int64_t c = 0; c < ncells; ++c) plan.colour_off[colour[c] + 1]++;
+  for (int k = 0; k < ncol; ++k) plan.colour_off[k + 1] += plan.colour_off[k];
+  plan.cells.resize((size_t)ncells);
+  std::vector<int32_t> pos(plan.colour_off.begin(), plan.colour_off.end() - 1);
+  for (int64_t c = 0; c < ncells; ++c) plan.cells[pos[colour[c]]++] = (int32_t)c;
+}
+
+void verify_cell_colour_plan(const CellColourPlan& plan, int nd, int64_t ncells, int64_t ndofs,
+                             const int32_t* tdm)
+{
+  if ((int64_t)plan.cells.size() != ncells) fail("colour plan: wrong cell count");
+  std::vector<int32_t> stamp((size_t)ndofs, -1);
+  std::vector<uint8_t> seen((size_t)ncells, 0);
+  for (int k = 0; k < plan.ncolours; ++k)
+    for (int32_t p = plan.colour_off[k]; p < plan.colour_off[k + 1]; ++p)
+    {
+      const int32_t c = plan.cells[p];
+      if (c < 0 || c >= ncells || seen[c]) fail("colour plan: cell listed twice or out of range");
+      seen[c] = 1;
+      for (int t = 0; t < nd; ++t)
+      {
+        int32_t& s = stamp[tdm[(int64_t)c * nd + t]];
+        if (s == k) fail("colour plan: two cells of colour %d share a dof", k);
+      }
+      for (int t = 0; t < nd; ++t) stamp[tdm[(int64_t)c * nd + t]] = k;
+    }
+}
+
+void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
+                      const float* centroid, int brick_edge, int W, int nloc_cap,
+                      BrickPlan& plan)
+{
+  const int n = P + 1, nd = n * n * n;
+  if (ndofs > (int64_t)BD_MASK) fail("brick plan: more than 2^30 local dofs");
+  if (nloc_cap > 65535) nloc_cap = 65535;
+  if (nloc_cap < nd) fail("brick plan: shared-memory dof capacity %d below one cell", nloc_cap);
+  if (W < 1) fail("brick plan: W < 1");
+  const int64_t max_cells = (int64_t)brick_edge * brick_edge * brick_edge;
+  plan = BrickPlan();
+  plan.P = P;
+  plan.nd = nd;
+  plan.W = W;
+  plan.ncells = ncells;
+  plan.ndofs = ndofs;
+
+  // ---- 1. spatial keys -------------------------------------------------------
+  std::vector<uint64_t> key((size_t)ncells);
+  std::vector<uint32_t> parity((size_t)ncells, 0);
+  if (centroid && ncells > 0)
+  {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int64_t c = 0; c < ncells; ++c)
+      for (int a = 0; a < 3; ++a)
+      {
+        lo[a] = std::min(lo[a], (double)centroid[3 * c + a]);
+        hi[a] = std::max(hi[a], (double)centroid[3 * c + a]);
+      }
+    // cell spacing of the (assumed roughly uniform) mesh: centroids of a structured
+    // grid span (n_a - 1) h per axis; solve prod (ext_a + h) = ncells h^3 by iteration.
+    double ext[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+    double h = std::cbrt(std::max(ext[0], 1e-300) * std::max(ext[1], 1e-300) * std::max(ext[2], 1e-300)
+                         / (double)ncells);
+    if (!(h > 0)) h = 1.0;
+    for (int it = 0; it < 50; ++it)
+      h = std::cbrt((ext[0] + h) * (ext[1] + h) * (ext[2] + h) / (double)ncells);
+    for (int64_t c = 0; c < ncells; ++c)
+    {
+      uint64_t b[3], loc[3];
+      for (int a = 0; a < 3; ++a)
+      {
+        int64_t ia = (int64_t)std::floor((centroid[3 * c + a] - lo[a]) / h + 0.5);
+        if (ia < 0) ia = 0;
+        if (ia > 0xFFFF) ia = 0xFFFF;
+        b[a] = (uint64_t)(ia / brick_edge);
+        loc[a] = (uint64_t)(ia % brick_edge);
+      }
+      // brick coordinates in the high bits, in-brick position in the low bits
+      key[c] = (b[0] << 44) | (b[1] << 28) | (b[2] << 12) | (loc[0] << 8) | (loc[1] << 4) | loc[2];
+      parity[c] = (uint32_t)((b[0] & 1) | ((b[1] & 1) << 1) | ((b[2] & 1) << 2));
+    }
+  }
+  else
+  {
+    for (int64_t c = 0; c < ncells; ++c) key[c] = ((uint64_t)(c / max_cells)) << 12;
+  }
+  std::vector<int32_t> order((size_t)ncells);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+
+  // ---- 2. batches: runs of equal brick key, capacity-limited --------------------
+  struct Batch
+  {
+    int64_t begin, end; // range in `order`
+    int colour = -1;
+    uint32_t parity = 0;
+    int nloc = 0;
+  };
+  std::vector<Batch> batches;
+  {
+    int64_t s = 0;
+    while (s < ncells)
+    {
+      int64_t e = s + 1;
+      const uint64_t bk = key[order[s]] >> 12;
+      while (e < ncells && (key[order[e]] >> 12) == bk && e - s < max_cells) ++e;
+      Batch b;
+      b.begin = s;
+      b.end = e;
+      b.parity = parity[order[s]];
+      batches.push_back(b);
+      s = e;
+    }
+  }
+  // enforce the shared-memory dof capacity by splitting
+  std::vector<int32_t> g2l((size_t)ndofs, -1);
+  std::vector<int32_t> uniq;
+  auto count_unique = [&](const Batch& b) {
+    uniq.clear();
+    for (int64_t p = b.begin; p < b.end; ++p)
+    {
+      const int32_t* d = tdm + (int64_t)order[p] * nd;
+      for (int t = 0; t < nd; ++t)
+        if (g2l[d[t]] < 0)
+        {
+          g2l[d[t]] = 1;
+          uniq.push_back(d[t]);
+        }
+    }
+    for (int32_t d : uniq) g2l[d] = -1;
+    return (int)uniq.size();
+  };
+  for (size_t i = 0; i < batches.size();)
+  {
+    const int nl = count_unique(batches[i]);
+    if (nl > nloc_cap && batches[i].end - batches[i].begin > 1)
+    {
+      Batch lo = batches[i], hi = batches[i];
+      lo.end = hi.begin = (batches[i].begin + batches[i].end) / 2;
+      batches[i] = lo;
+      batches.insert(batches.begin() + i + 1, hi);
+      continue; // re-examine the lower half
+    }
+    batches[i].nloc = nl;
+    ++i;
+  }
+  const int nb = (int)batches.size();
+  plan.nbatches = nb;
+
+  // ---- 3. batch colouring (greedy; the brick-coordinate parity is tried first, which
+  //         gives the optimal 8 colours on structured meshes) ------------------------
+  std::vector<uint64_t> dofmask((size_t)ndofs, 0);
+  int ncol = 0;
+  for (int i = 0; i < nb; ++i)
+  {
+    uint64_t m = 0;
+    for (int64_t p = batches[i].begin; p < batches[i].end; ++p)
+    {
+      const int32_t* d = tdm + (int64_t)order[p] * nd;
+      for (int t = 0; t < nd; ++t) m |= dofmask[d[t]];
+    }
+    int col = (int)batches[i].parity;
+    if ((m >> col) & 1) col = lowest_zero_bit(m);
+    if (col < 0) fail("batch colouring needs more than 64 colours");
+    const uint64_t bit = 1ull << col;
+    for (int64_t p = batches[i].begin; p < batches[i].end; ++p)
+    {
+      const int32_t* d = tdm + (int64_t)order[p] * nd;
+      for (int t = 0; t < nd; ++t) dofmask[d[t]] |= bit;
+    }
+    batches[i].colour = col;
+    ncol = std::max(ncol, col + 1);
+  }
+  // compact away unused colours, keep order
+  {
+    std::vector<int> used(ncol, 0), remap(ncol, -1);
+    for (auto& b : batches) used[b.colour] = 1;
+    int k = 0;
+    for (int c = 0; c < ncol; ++c)
+      if (used[c]) remap[c] = k++;
+    // dofmask bits are remapped lazily below through first/last per dof
+    std::vector<uint64_t>().swap(dofmask);
+    for (auto& b : batches) b.colour = remap[b.colour];
+    ncol = k;
+  }
+  plan.ncolours = ncol;
+  std::stable_sort(batches.begin(), batches.end(),
+                   [](const Batch& a, const Batch& b) { return a.colour < b.colour; });
+  plan.colour_off.assign(ncol + 1, 0);
+  for (auto& b : batches) plan.colour_off[b.colour + 1]++;
+  for (int c = 0; c < ncol; ++c) plan.colour_off[c + 1] += plan.colour_off[c];
+
+  // first / last colour touching each dof
+  std::vector<int8_t> cmin((size_t)ndofs, 127), cmax((size_t)ndofs, -1);
+  for (auto& b : batches)
+    for (int64_t p = b.begin; p < b.end; ++p)
+    {
+      const int32_t* d = tdm + (int64_t)order[p] * nd;
+      for (int t = 0; t < nd; ++t)
+      {
+        cmin[d[t]] = std::min<int8_t>(cmin[d[t]], (int8_t)b.colour);
+        cmax[d[t]] = std::max<int8_t>(cmax[d[t]], (int8_t)b.colour);
+      }
+    }
+  for (int64_t i = 0; i < ndofs; ++i)
+    if (cmax[i] < 0) plan.untouched.push_back((int32_t)i);
+
+  // ---- 4. per-batch dof lists, rounds and local dofmaps ---------------------------
+  plan.dof_off.assign(nb + 1, 0);
+  plan.round_off.assign(nb + 1, 0);
+  std::vector<uint64_t> lmask;
+  std::vector<int> ccol;
+  for (int i = 0; i < nb; ++i)
+  {
+    const Batch& b = batches[i];
+    const int nc = (int)(b.end - b.begin);
+    // unique dofs, ascending
+    uniq.clear();
+    for (int64_t p = b.begin; p < b.end; ++p)
+    {
+      const int32_t* d = tdm + (int64_t)order[p] * nd;
+      for (int t = 0; t < nd; ++t)
+        if (g2l[d[t]] < 0)
+        {
+          g2l[d[t]] = 1;
+          uniq.push_back(d[t]);
+        }
+    }
+    std::sort(uniq.begin(), uniq.end());
+    const int nloc = (int)uniq.size();
+    if (nloc > 65535) fail("brick plan: batch with %d dofs exceeds 16-bit local index", nloc);
+    plan.nloc_max = std::max(plan.nloc_max, nloc);
+    for (int l = 0; l < nloc; ++l)
+    {
+      const int32_t d = uniq[l];
+      g2l[d] = l;
+      uint32_t e = (uint32_t)d;
+      if (cmin[d] == b.colour) e |= BD_FIRST;
+      if (cmax[d] == b.colour) e |= BD_LAST;
+      if ((e & BD_FIRST) && (e & BD_LAST)) plan.n_private++;
+      plan.bdofs.push_back(e);
+    }
+    plan.dof_off[i + 1] = (int64_t)plan.bdofs.size();
+    // colour the batch's cells so that cells of one round share no local dof
+    lmask.assign(nloc, 0);
+    ccol.assign(nc, 0);
+    int nlc = 0;
+    for (int q = 0; q < nc; ++q)
+    {
+      const int32_t* d = tdm + (int64_t)order[b.begin + q] * nd;
+      uint64_t m = 0;
+      for (int t = 0; t < nd; ++t) m |= lmask[g2l[d[t]]];
+      const int col = lowest_zero_bit(m);
+      if (col < 0) fail("in-batch cell colouring needs more than 64 colours");
+      for (int t = 0; t < nd; ++t) lmask[g2l[d[t]]] |= 1ull << col;
+      ccol[q] = col;
+      nlc = std::max(nlc, col + 1);
+    }
+    int nrounds = 0;
+    for (int col = 0; col < nlc; ++col)
+    {
+      int filled = 0;
+      for (int q = 0; q < nc; ++q)
+      {
+        if (ccol[q] != col) continue;
+        if (filled == 0)
+        {
+          plan.slot_cell.resize(plan.slot_cell.size() + W, -1);
+          plan.ldm.resize(plan.ldm.size() + (size_t)W * nd, 0);
+          ++nrounds;
+        }
+        const size_t slot = plan.slot_cell.size() - W + filled;
+        const int32_t cell = order[b.begin + q];
+        plan.slot_cell[slot] = cell;
+        const int32_t* d = tdm + (int64_t)cell * nd;
+        for (int t = 0; t < nd; ++t) plan.ldm[slot * nd + t] = (uint16_t)g2l[d[t]];
+        filled = (filled + 1) % W;
+      }
+    }
+    plan.round_off[i + 1] = plan.round_off[i] + nrounds;
+    for (int32_t d : uniq) g2l[d] = -1;
+  }
+  plan.nrounds_total = plan.round_off[nb];
+  plan.n_slots_padded = plan.nrounds_total * W - ncells;
+}
+
+void verify_brick_plan(const BrickPlan& plan, const int32_t* tdm)
+{
+  const int nd = plan.nd, W = plan.W, nb = plan.nbatches;
+  const int64_t ncells = plan.ncells, ndofs = plan.ndofs;
+  if ((int)plan.colour_off.size() != plan.ncolours + 1 || plan.colour_off.back() != nb)
+    fail("brick plan: colour offsets inconsistent");
+  std::vector<uint8_t> cell_seen((size_t)ncells, 0);
+  std::vector<int32_t> colour_stamp((size_t)ndofs, -1); // last colour that touched the dof
+  std::vector<uint8_t> nfirst((size_t)ndofs, 0), nlast((size_t)ndofs, 0), touched((size_t)ndofs, 0);
+  std::vector<int32_t> prev_colour((size_t)ndofs, -1);
+  std::vector<int32_t> round_stamp;
+  int64_t cells_total = 0;
+  for (int col = 0; col < plan.ncolours; ++col)
+    for (int b = plan.colour_off[col]; b < plan.colour_off[col + 1]; ++b)
+    {
+      const int64_t d0 = plan.dof_off[b], d1 = plan.dof_off[b + 1];
+      const int nloc = (int)(d1 - d0);
+      if (nloc > plan.nloc_max) fail("brick plan: nloc_max too small");
+      for (int64_t l = d0; l < d1; ++l)
+      {
+        const uint32_t e = plan.bdofs[l];
+        const int32_t d = (int32_t)(e & BD_MASK);
+        if (d < 0 || d >= ndofs) fail("brick plan: dof out of range");
+        if (l > d0 && (plan.bdofs[l - 1] & BD_MASK) >= (uint32_t)d) fail("brick plan: batch dofs not ascending/unique");
+        if (colour_stamp[d] == col) fail("brick plan: two batches of colour %d share dof %d", col, d);
+        colour_stamp[d] = col;
+        const bool first = e & BD_FIRST, last = e & BD_LAST;
+        if (first && touched[d]) fail("brick plan: FIRST flag on an already touched dof");
+        if (!first && !touched[d]) fail("brick plan: dof %d first touched without FIRST flag", d);
+        if (nlast[d]) fail("brick plan: dof %d touched after its LAST batch", d);
+        touched[d] = 1;
+        nfirst[d] += first;
+        nlast[d] += last;
+      }
+      round_stamp.assign(nloc, -1);
+      for (int r = plan.round_off[b]; r < plan.round_off[b + 1]; ++r)
+        for (int s = 0; s < W; ++s)
+        {
+          const int64_t slot = (int64_t)r * W + s;
+          const int32_t cell = plan.slot_cell[slot];
+          if (cell < 0) continue;
+          if (cell >= ncells || cell_seen[cell]) fail("brick plan: cell out of range or listed twice");
+          cell_seen[cell] = 1;
+          ++cells_total;
+          for (int t = 0; t < nd; ++t)
+          {
+            const int l = plan.ldm[slot * nd + t];
+            if (l >= nloc) fail("brick plan: local dof index out of range");
+            if ((int32_t)(plan.bdofs[d0 + l] & BD_MASK) != tdm[(int64_t)cell * nd + t])
+              fail("brick plan: local dofmap does not reproduce the dofmap");
+            if (round_stamp[l] == r) fail("brick plan: two cells of one round share a dof");
+          }
+          for (int t = 0; t < nd; ++t) round_stamp[plan.ldm[slot * nd + t]] = r;
+        }
+    }
+  if (cells_total != ncells) fail("brick plan: %lld of %lld cells covered", (long long)cells_total, (long long)ncells);
+  int64_t nunt = 0;
+  for (int64_t d = 0; d < ndofs; ++d)
+  {
+    if (!touched[d]) { ++nunt; continue; }
+    if (nfirst[d] != 1 || nlast[d] != 1) fail("brick plan: dof %lld has %d FIRST / %d LAST marks", (long long)d, nfirst[d], nlast[d]);
+  }
+  if (nunt != (int64_t)plan.untouched.size()) fail("brick plan: untouched list inconsistent");
+}
+} // namespace wfx
+
+// Debug entry point (not part of the drop-in boundary): builds both plans for a dofmap on
+// the host, verifies every invariant and reports statistics.  Needs no GPU.
+//   stats[0]=cell colours  [1]=batches  [2]=batch colours  [3]=nloc_max  [4]=rounds
+//   [5]=padded slots  [6]=private (first&last) batch dofs  [7]=total batch dofs
+//   [8]=untouched dofs
+extern "C" int wfx_debug_plan_stats(int P, int64_t ncells, int64_t ndofs,
+                                    const int32_t* dofmap_host, const float* centroid_host,
+                                    int brick_edge, int W, int nloc_cap, int64_t* stats)
+{
+  WFX_API_BEGIN
+  using namespace wfx;
+  const int n = P + 1, n2 = n * n, nd = n2 * n;
+  std::vector<int32_t> perm(nd);
+  tensor_perm(P, perm.data());
+  std::vector<int32_t> tdm((size_t)ncells * nd);
+  for (int64_t c = 0; c < ncells; ++c)
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j)
+        for (int k = 0; k < n; ++k)
+        {
+          const int32_t d = dofmap_host[c * nd + perm[(i * n + j) * n + k]];
+          if (d < 0 || d >= ndofs) fail("dofmap entry out of range");
+          tdm[c * nd + k * n2 + i * n + j] = d;
+        }
+  CellColourPlan cp;
+  build_cell_colour_plan(nd, ncells, ndofs, tdm.data(), cp);
+  verify_cell_colour_plan(cp, nd, ncells, ndofs, tdm.data());
+  BrickPlan bp;
+  build_brick_plan(P, ncells, ndofs, tdm.data(), centroid_host, brick_edge, W, nloc_cap, bp);
+  verify_brick_plan(bp, tdm.data());
+  if (stats)
+  {
+    stats[0] = cp.ncolours;
+    stats[1] = bp.nbatches;
+    stats[2] = bp.ncolours;
+    stats[3] = bp.nloc_max;
+    stats[4] = bp.nrounds_total;
+    stats[5] = bp.n_slots_padded;
+    stats[6] = bp.n_private;
+    stats[7] = (int64_t)bp.bdofs.size();
+    stats[8] = (int64_t)bp.untouched.size();
+  }
+  WFX_API_END
+}

@@ -1,0 +1,69 @@
+// Host-side execution plans for the atomic-free stiffness scatter.
+//
+// The reference scatters with atomicAdd (common/cuda/scatter.cu:38-45).  Here the
+// scatter is made race-free by construction at setup time:
+//
+//  CellColourPlan  cells greedily coloured so that no two cells of one colour share a
+//                  dof; one launch per colour, plain read-modify-write on y.
+//  BrickPlan       cells grouped into spatially compact batches ("bricks").  One CTA
+//                  owns one batch: it stages the batch's unique dofs in shared memory,
+//                  processes the batch's cells in conflict-free rounds accumulating in
+//                  shared memory, and writes every batch dof back exactly once.  Batches
+//                  are coloured so that batches of one colour share no dof; colours run
+//                  as consecutive launches.  For every dof the lowest-colour batch that
+//                  touches it is marked FIRST (it may overwrite instead of accumulate)
+//                  and the highest LAST (it may apply the fused diagonal scaling).
+#pragma once
+
+#include <cstdint>
+#include <vector>
+
+namespace wfx
+{
+constexpr uint32_t BD_FIRST = 1u << 30;
+constexpr uint32_t BD_LAST = 1u << 31;
+constexpr uint32_t BD_MASK = (1u << 30) - 1;
+
+struct CellColourPlan
+{
+  int ncolours = 0;
+  std::vector<int32_t> colour_off; // [ncolours+1] into cells
+  std::vector<int32_t> cells;      // cell ids sorted by colour
+};
+
+struct BrickPlan
+{
+  int P = 0, nd = 0, W = 0; // W = cell slots processed concurrently per round
+  int64_t ncells = 0, ndofs = 0;
+  int nbatches = 0, ncolours = 0;
+  int nloc_max = 0;                // largest number of unique dofs in a batch
+  int64_t nrounds_total = 0;
+  // batches are stored sorted by colour
+  std::vector<int32_t> colour_off; // [ncolours+1] into batches
+  std::vector<int64_t> dof_off;    // [nbatches+1] into bdofs
+  std::vector<uint32_t> bdofs;     // global dof | BD_FIRST | BD_LAST, ascending per batch
+  std::vector<int32_t> round_off;  // [nbatches+1] into rounds
+  std::vector<int32_t> slot_cell;  // [nrounds_total*W] cell id or -1
+  std::vector<uint16_t> ldm;       // [nrounds_total*W][nd] batch-local dof, k-major point order
+  std::vector<int32_t> untouched;  // vector entries no cell references
+  // statistics
+  int64_t n_slots_padded = 0;
+  int64_t n_private = 0;           // bdofs entries that are FIRST and LAST
+};
+
+// tdm: tensor-ordered dofmap in the kernels' k-major point order, [ncells][nd]
+void build_cell_colour_plan(int nd, int64_t ncells, int64_t ndofs, const int32_t* tdm,
+                            CellColourPlan& plan);
+
+// centroid: [ncells][3] or nullptr (then cells are batched in the given order).
+// brick_edge: cells per brick edge; max_cells: batch capacity; nloc_cap: capacity of the
+// shared-memory dof arrays.
+void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
+                      const float* centroid, int brick_edge, int W, int nloc_cap,
+                      BrickPlan& plan);
+
+// Checks every invariant the kernels rely on; throws wfx::Error on violation.
+void verify_brick_plan(const BrickPlan& plan, const int32_t* tdm);
+void verify_cell_colour_plan(const CellColourPlan& plan, int nd, int64_t ncells, int64_t ndofs,
+                             const int32_t* tdm);
+} // namespace wfx

@@ -1,0 +1,226 @@
+// Wave model and classical RK4 time integrator on the device.
+// Replaces LinearGLLOpt::{init,f0,f1,rk4} (common/LinearGLL.hpp:131-287).  The reference
+// makes ~17 full-vector passes per stage (copies, axpys, zero, divide) plus three host
+// MPI scatters; here a stage is: stiffness apply (b = -c0^2 K un), boundary term on the
+// facet dofs, one optional halo reduction of b, and ONE fused pointwise kernel that does
+// kv = b/m, both solution updates and the next stage state.
+#include "wfx_internal.h"
+
+#include <cmath>
+
+using namespace wfx;
+
+struct wfx_stiffness;
+struct wfx_mass;
+struct wfx_boundary;
+struct wfx_halo;
+
+struct wfx_wave
+{
+  wfx_ctx* ctx = nullptr;
+  wfx_stiffness* stiff = nullptr;
+  wfx_mass* mass = nullptr;
+  wfx_boundary* bnd = nullptr;
+  wfx_halo* halo = nullptr;
+  int dtype = WFX_F64;
+  int64_t n = 0, size_local = 0;
+  double c0 = 0, f0 = 0, p0 = 0;
+  const void* minv = nullptr;
+  // u_, v_: solution; u0, v0: start of step; un, vn: stage state; b: right-hand side
+  DevBuf<unsigned char> u_, v_, u0, v0, un, vn, b;
+};
+
+namespace
+{
+// Stage update, fused.  STAGE 0 reads the solution as stage state
+// and saves it as u0/v0; STAGE 3 only finishes the solution.
+//   kv = b / m                          (LinearGLL.hpp:188-191; m^-1 precomputed, :179-181)
+//   u_ += b_i dt ku,  v_ += b_i dt kv   (:264-265), ku = vn (f0, :141-144)
+//   un' = u0 + a_{i+1} dt ku, vn' = v0 + a_{i+1} dt kv   (:250-254 of the next stage)
+template <typename T, int STAGE>
+__global__ void __launch_bounds__(256)
+rk_stage_kernel(int64_t n, const T* __restrict__ b, const T* __restrict__ minv, T* __restrict__ u_,
+                T* __restrict__ v_, T* __restrict__ u0, T* __restrict__ v0, T* __restrict__ un,
+                T* __restrict__ vn, T bdt, T adt_next)
+{
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const T kv = b[k] * minv[k];
+  T us = u_[k], vs = v_[k];
+  T ku, ub, vb;
+  if (STAGE == 0)
+  {
+    ku = vs;
+    ub = us;
+    vb = vs;
+    u0[k] = ub;
+    v0[k] = vb;
+  }
+  else
+  {
+    ku = vn[k];
+    if (STAGE < 3)
+    {
+      ub = u0[k];
+      vb = v0[k];
+    }
+  }
+  u_[k] = ku * bdt + us;
+  v_[k] = kv * bdt + vs;
+  if (STAGE < 3)
+  {
+    un[k] = ku * adt_next + ub;
+    vn[k] = kv * adt_next + vb;
+  }
+}
+
+template <typename T>
+void launch_stage(int stage, int64_t n, const void* b, const void* minv, void* u_, void* v_,
+                  void* u0, void* v0, void* un, void* vn, double bdt, double adt_next,
+                  cudaStream_t st)
+{
+  const unsigned grid = (unsigned)((n + 255) / 256);
+#define WFX_STAGE(S)                                                                             \
+  rk_stage_kernel<T, S><<<grid, 256, 0, st>>>(n, (const T*)b, (const T*)minv, (T*)u_, (T*)v_,   \
+                                               (T*)u0, (T*)v0, (T*)un, (T*)vn, (T)bdt, (T)adt_next)
+  switch (stage)
+  {
+  case 0: WFX_STAGE(0); break;
+  case 1: WFX_STAGE(1); break;
+  case 2: WFX_STAGE(2); break;
+  default: WFX_STAGE(3); break;
+  }
+#undef WFX_STAGE
+  WFX_CUDA(cudaGetLastError());
+}
+} // namespace
+
+extern "C" int wfx_wave_create(wfx_ctx* ctx, wfx_stiffness* stiff, wfx_mass* mass,
+                               wfx_boundary* bnd, wfx_halo* halo, int64_t size_local, double c0,
+                               double f0, double p0, wfx_wave** out)
+{
+  WFX_API_BEGIN
+  if (!ctx || !stiff || !mass || !out) fail("NULL argument");
+  ScopedDevice sd(ctx->device);
+  int64_t ndofs = 0;
+  if (wfx_stiffness_info(stiff, nullptr, nullptr, &ndofs, nullptr, nullptr, nullptr, nullptr))
+    fail("%s", wfx_last_error());
+  auto w = std::make_unique<wfx_wave>();
+  w->ctx = ctx;
+  w->stiff = stiff;
+  w->mass = mass;
+  w->bnd = bnd;
+  w->halo = halo;
+  w->n = ndofs;
+  w->size_local = size_local;
+  w->c0 = c0;
+  w->f0 = f0;
+  w->p0 = p0;
+  w->dtype = stiffness_dtype(stiff);
+  if (wfx_mass_inverse_diagonal(mass, &w->minv)) fail("%s", wfx_last_error());
+  const size_t nb = (size_t)ndofs * (w->dtype == WFX_F64 ? 8 : 4);
+  for (auto* v : {&w->u_, &w->v_, &w->u0, &w->v0, &w->un, &w->vn, &w->b})
+  {
+    v->alloc(nb);
+    if (nb) WFX_CUDA(cudaMemset(v->p, 0, nb));
+  }
+  *out = w.release();
+  WFX_API_END
+}
+
+extern "C" int wfx_wave_init(wfx_wave* w)
+{
+  WFX_API_BEGIN
+  if (!w) fail("wave model is NULL");
+  ScopedDevice sd(w->ctx->device);
+  if (w->u_.n)
+  {
+    WFX_CUDA(cudaMemset(w->u_.p, 0, w->u_.n));
+    WFX_CUDA(cudaMemset(w->v_.p, 0, w->v_.n));
+  }
+  WFX_API_END
+}
+
+extern "C" int wfx_wave_set_state(wfx_wave* w, const void* u, const void* v)
+{
+  WFX_API_BEGIN
+  if (!w) fail("wave model is NULL");
+  ScopedDevice sd(w->ctx->device);
+  if (u && w->u_.n) WFX_CUDA(cudaMemcpy(w->u_.p, u, w->u_.n, cudaMemcpyHostToDevice));
+  if (v && w->v_.n) WFX_CUDA(cudaMemcpy(w->v_.p, v, w->v_.n, cudaMemcpyHostToDevice));
+  WFX_API_END
+}
+
+extern "C" int wfx_wave_get_state(wfx_wave* w, void* u, void* v)
+{
+  WFX_API_BEGIN
+  if (!w) fail("wave model is NULL");
+  ScopedDevice sd(w->ctx->device);
+  if (u && w->u_.n) WFX_CUDA(cudaMemcpy(u, w->u_.p, w->u_.n, cudaMemcpyDeviceToHost));
+  if (v && w->v_.n) WFX_CUDA(cudaMemcpy(v, w->v_.p, w->v_.n, cudaMemcpyDeviceToHost));
+  WFX_API_END
+}
+
+extern "C" int wfx_wave_state_ptrs(wfx_wave* w, void** u, void** v)
+{
+  WFX_API_BEGIN
+  if (!w) fail("wave model is NULL");
+  if (u) *u = w->u_.p;
+  if (v) *v = w->v_.p;
+  WFX_API_END
+}
+
+extern "C" int wfx_wave_rk4(wfx_wave* w, double t0, double tf, double dt, int64_t max_steps,
+                            int64_t* steps_out, double* t_end, void* stream)
+{
+  WFX_API_BEGIN
+  if (!w) fail("wave model is NULL");
+  ScopedDevice sd(w->ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const double w0 = 2.0 * M_PI * w->f0, T = 1.0 / w->f0, alpha = 4.0; // LinearGLL.hpp:96-99
+  const double a_runge[5] = {0.0, 0.5, 0.5, 1.0, 0.0};
+  const double b_runge[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};
+  const double c_runge[4] = {0.0, 0.5, 0.5, 1.0};
+  double t = t0;
+  int64_t step = 0;
+  while (t < tf) // :241
+  {
+    if (max_steps > 0 && step >= max_steps) break;
+    dt = std::min(dt, tf - t); // :242
+    for (int i = 0; i < 4; ++i)
+    {
+      const double tn = t + c_runge[i] * dt; // :257
+      // stage state: the solution itself at stage 0 (a_0 = 0), else un/vn
+      const void* un = i == 0 ? w->u_.p : w->un.p;
+      const void* vn = i == 0 ? w->v_.p : w->vn.p;
+      // f1 (:151-192)
+      const double window = tn < T * alpha ? 0.5 * (1.0 - std::cos(w->f0 * M_PI * tn / alpha)) : 1.0;
+      const double g = window * w->p0 * w0 / w->c0 * std::cos(w0 * tn); // :162
+      if (wfx_stiffness_apply(w->stiff, un, w->b.p, 0, st)) fail("%s", wfx_last_error()); // :173-174
+      if (w->bnd && wfx_boundary_apply(w->bnd, w->c0, g, vn, w->b.p, st)) fail("%s", wfx_last_error()); // :175
+      if (w->halo && wfx_halo_update_rev_fwd(w->halo, w->b.p, st)) fail("%s", wfx_last_error()); // :176 (+ :164,167 of the next stage)
+      if (w->dtype == WFX_F64)
+        launch_stage<double>(i, w->n, w->b.p, w->minv, w->u_.p, w->v_.p, w->u0.p, w->v0.p, w->un.p,
+                             w->vn.p, dt * b_runge[i], dt * a_runge[i + 1], st);
+      else
+        launch_stage<float>(i, w->n, w->b.p, w->minv, w->u_.p, w->v_.p, w->u0.p, w->v0.p, w->un.p,
+                            w->vn.p, dt * b_runge[i], dt * a_runge[i + 1], st);
+    }
+    t += dt;
+    step += 1;
+  }
+  if (steps_out) *steps_out = step;
+  if (t_end) *t_end = t;
+  WFX_API_END
+}
+
+extern "C" int wfx_wave_destroy(wfx_wave* w)
+{
+  WFX_API_BEGIN
+  if (w)
+  {
+    ScopedDevice sd(w->ctx->device);
+    delete w;
+  }
+  WFX_API_END
+}
