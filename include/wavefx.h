@@ -132,6 +132,10 @@ int wfx_stiffness_apply_scaled(wfx_stiffness* op, const void* x_dev, const void*
 /* Same call shape as the reference functor on host la::Vector arrays: copies x (and y
  * when beta != 0) to the GPU, applies, copies y back.  Synchronous. */
 int wfx_stiffness_apply_host(wfx_stiffness* op, const void* x_host, void* y_host, int beta);
+/* The headline path end to end with HOST buffers: y = M^-1 (-c0^2 K x), x and y host
+ * arrays (pinned or pageable); H2D copy of x, fused apply, D2H copy of y.  Synchronous. */
+int wfx_stiffness_mass_apply_host(wfx_stiffness* op, wfx_mass* mass, const void* x_host,
+                                  void* y_host);
 /* num_cells / num_dofs / num_quads / flops as on the GPU operator classes
  * (common/cuda/mass.hpp:68-71); bytes = algorithmic bytes per apply. */
 int wfx_stiffness_info(wfx_stiffness* op, int64_t* num_cells, int* num_dofs_per_cell,

@@ -49,7 +49,7 @@ def test_geometry_bit_exact(wfx, orc, torch, P, perturb):
 
 def test_geometry_clamp_triggers_like_reference(wfx, orc, torch):
     # tiny cells: legitimate G entries below 1e-8 are zeroed
-    mesh = wfx.create_box_hex(2, 4, (2e-4,) * 3)
+    mesh = wfx.create_box_hex(2, 4, (1e-4,) * 3)
     G, _ = wfx.Geometry(mesh, 4).get()
     Go, _ = orc.precompute_geometric_data(mesh, 4)
     assert np.array_equal(G, Go) and (np.diagonal(G, axis1=2, axis2=3) == 0).any()

@@ -58,6 +58,7 @@ _SIG = {
     "wfx_stiffness_apply": [_vp, _vp, _vp, C.c_int, _vp],
     "wfx_stiffness_apply_scaled": [_vp, _vp, _vp, _vp, _vp],
     "wfx_stiffness_apply_host": [_vp, _vp, _vp, C.c_int],
+    "wfx_stiffness_mass_apply_host": [_vp, _vp, _vp, _vp],
     "wfx_stiffness_info": [_vp, _c_i64p, C.POINTER(C.c_int), _c_i64p, _c_f64p, _c_f64p,
                            C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "wfx_stiffness_destroy": [_vp],

@@ -583,6 +583,25 @@ extern "C" int wfx_stiffness_apply_host(wfx_stiffness* op, const void* x_host, v
   WFX_API_END
 }
 
+extern "C" int wfx_stiffness_mass_apply_host(wfx_stiffness* op, wfx_mass* mass, const void* x_host,
+                                             void* y_host)
+{
+  WFX_API_BEGIN
+  if (!op || !mass) fail("NULL operator");
+  if (!x_host || !y_host) fail("stiffness: NULL vector");
+  ScopedDevice sd(op->ctx->device);
+  const void* minv = nullptr;
+  if (wfx_mass_inverse_diagonal(mass, &minv)) fail("%s", wfx_last_error());
+  const size_t nb = (size_t)op->ndofs * (op->dtype == WFX_F64 ? 8 : 4);
+  if (op->d_hx.n < nb) op->d_hx.alloc(nb);
+  if (op->d_hy.n < nb) op->d_hy.alloc(nb);
+  WFX_CUDA(cudaMemcpyAsync(op->d_hx.p, x_host, nb, cudaMemcpyHostToDevice, 0));
+  apply_any(op, op->d_hx.p, minv, op->d_hy.p, 0, nullptr);
+  WFX_CUDA(cudaMemcpyAsync(y_host, op->d_hy.p, nb, cudaMemcpyDeviceToHost, 0));
+  WFX_CUDA(cudaStreamSynchronize(0));
+  WFX_API_END
+}
+
 extern "C" int wfx_stiffness_info(wfx_stiffness* op, int64_t* num_cells, int* num_dofs_per_cell,
                                   int64_t* ndofs, double* flops, double* bytes, int* ncolours,
                                   int* nlaunches)
