@@ -61,81 +61,143 @@ struct BlockSync
   __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
 
-// One cell, one thread per (i,j) column.  u[k]: nodal values of the column; yv[k]: result.
-// su/sf0/sf1: this cell's shared tiles [N][N*N] (k-major).  Inactive threads (padding
-// lanes / empty slots) take part in the synchronisation only.
-template <typename T, int N, typename Sync>
-__device__ __forceinline__ void cell_apply(const T (&u)[N], T (&yv)[N], const T* __restrict__ Gc,
-                                           T* __restrict__ su, T* __restrict__ sf0,
-                                           T* __restrict__ sf1, int col, int i, int j,
-                                           const DMat<T, N>& Dm, const T* __restrict__ sD, T coeff,
-                                           bool active, Sync sync)
+// Shared-memory tiles of one cell slot: two [N][N][NP] tiles, rows padded to an even
+// length so that every row is a whole number of 16-byte (fp64) vectors.
+template <int N>
+struct Pad
 {
-  constexpr int N2 = N * N;
+  static constexpr int NP = (N % 2) ? N + 1 : N;
+  static constexpr int TILE = N * N * NP; // elements per tile
+  static constexpr int DSZ = N * NP;      // padded derivative matrix
+};
+
+template <typename T, int NP>
+__device__ __forceinline__ void lds_row(const T* __restrict__ p, T (&r)[NP])
+{
   using V2 = typename Vec2<T>::type;
-  V2 g[N][3];
+#pragma unroll
+  for (int q = 0; q < NP / 2; ++q)
+  {
+    const V2 v = reinterpret_cast<const V2*>(p)[q];
+    r[2 * q] = v.x;
+    r[2 * q + 1] = v.y;
+  }
+}
+
+// G of one cell for this thread's column: [k][pair] 2-vectors, streamed once from HBM.
+template <typename T, int N>
+__device__ __forceinline__ void load_G(const T* __restrict__ Gc, int col,
+                                       typename Vec2<T>::type (&g)[N][3])
+{
+  using V2 = typename Vec2<T>::type;
+  const V2* gp = reinterpret_cast<const V2*>(Gc) + col;
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+#pragma unroll
+    for (int p = 0; p < 3; ++p) g[k][p] = ld_stream(gp + (k * 3 + p) * (N * N));
+}
+
+// Phase 1 of one cell, one thread per (i,j) column: u[k] = nodal values of the column.
+//   w0 = sum_m D[i][m] u(m,j,k), w1 = sum_m D[j][m] u(i,m,k), w2 = sum_m D[k][m] u(i,j,m)
+//   f  = coeff * G w        
+// A holds u as [k][i][j], AT as [k][j][i], so both in-plane contractions read whole rows
+// with vector loads.  sDp = D padded [N][NP].  Inactive threads only synchronise.
+template <typename T, int N, typename Sync>
+__device__ __forceinline__ void cell_phase1(const T (&u)[N], const typename Vec2<T>::type (&g)[N][3],
+                                            T* __restrict__ A, T* __restrict__ AT, int i, int j,
+                                            const DMat<T, N>& Dm, const T* __restrict__ sDp, T coeff,
+                                            bool active, Sync sync, T (&f0)[N], T (&f1)[N], T (&f2)[N])
+{
+  constexpr int NP = Pad<N>::NP;
   if (active)
   {
-    const V2* gp = reinterpret_cast<const V2*>(Gc) + col;
 #pragma unroll
     for (int k = 0; k < N; ++k)
-#pragma unroll
-      for (int p = 0; p < 3; ++p) g[k][p] = ld_stream(gp + (k * 3 + p) * N2);
-#pragma unroll
-    for (int k = 0; k < N; ++k) su[k * N2 + col] = u[k];
+    {
+      A[(k * N + i) * NP + j] = u[k];
+      AT[(k * N + j) * NP + i] = u[k];
+    }
   }
   sync();
-  T f2[N];
   if (active)
   {
-    T Di[N], Dj[N];
-#pragma unroll
-    for (int m = 0; m < N; ++m)
-    {
-      Di[m] = sD[i * N + m];
-      Dj[m] = sD[j * N + m];
-    }
+    T Di[NP], Dj[NP];
+    lds_row<T, NP>(sDp + i * NP, Di);
+    lds_row<T, NP>(sDp + j * NP, Dj);
 #pragma unroll
     for (int k = 0; k < N; ++k)
     {
+      T ri[NP], rj[NP];
+      lds_row<T, NP>(A + (k * N + i) * NP, ri);  // u(i, m, k)
+      lds_row<T, NP>(AT + (k * N + j) * NP, rj); // u(m, j, k)
       T w0 = 0, w1 = 0, w2 = 0;
 #pragma unroll
       for (int m = 0; m < N; ++m)
       {
-        w0 += Di[m] * su[k * N2 + m * N + j];
-        w1 += Dj[m] * su[k * N2 + i * N + m];
+        w0 += Di[m] * rj[m];
+        w1 += Dj[m] * ri[m];
         w2 += Dm.d[k * N + m] * u[m];
       }
       const T g00 = g[k][0].x, g01 = g[k][0].y, g02 = g[k][1].x;
       const T g11 = g[k][1].y, g12 = g[k][2].x, g22 = g[k][2].y;
-      const T f0 = coeff * (g00 * w0 + g01 * w1 + g02 * w2);
-      const T f1 = coeff * (g01 * w0 + g11 * w1 + g12 * w2);
+      f0[k] = coeff * (g00 * w0 + g01 * w1 + g02 * w2);
+      f1[k] = coeff * (g01 * w0 + g11 * w1 + g12 * w2);
       f2[k] = coeff * (g02 * w0 + g12 * w1 + g22 * w2);
-      sf0[k * N2 + col] = f0;
-      sf1[k * N2 + col] = f1;
+    }
+  }
+  sync(); // every read of A / AT is done: the tiles can take f
+}
+
+// Phase 2: y(i,j,k) = sum_m D[m][i] f0(m,j,k) + D[m][j] f1(i,m,k) + D[m][k] f2(i,j,m).
+// f0 goes to AT as [k][j][i], f1 to A as [k][i][j].  sDTp = D^T padded [N][NP].
+template <typename T, int N, typename Sync>
+__device__ __forceinline__ void cell_phase2(const T (&f0)[N], const T (&f1)[N], const T (&f2)[N],
+                                            T* __restrict__ A, T* __restrict__ AT, int i, int j,
+                                            const DMat<T, N>& Dm, const T* __restrict__ sDTp,
+                                            bool active, Sync sync, T (&yv)[N])
+{
+  constexpr int NP = Pad<N>::NP;
+  if (active)
+  {
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+    {
+      AT[(k * N + j) * NP + i] = f0[k];
+      A[(k * N + i) * NP + j] = f1[k];
     }
   }
   sync();
   if (active)
   {
-    T DTi[N], DTj[N];
-#pragma unroll
-    for (int m = 0; m < N; ++m)
-    {
-      DTi[m] = sD[m * N + i];
-      DTj[m] = sD[m * N + j];
-    }
+    T DTi[NP], DTj[NP];
+    lds_row<T, NP>(sDTp + i * NP, DTi);
+    lds_row<T, NP>(sDTp + j * NP, DTj);
 #pragma unroll
     for (int k = 0; k < N; ++k)
     {
+      T r0[NP], r1[NP];
+      lds_row<T, NP>(AT + (k * N + j) * NP, r0); // f0(m, j, k)
+      lds_row<T, NP>(A + (k * N + i) * NP, r1);  // f1(i, m, k)
       T s = 0;
 #pragma unroll
       for (int m = 0; m < N; ++m) s += Dm.d[m * N + k] * f2[m];
 #pragma unroll
-      for (int m = 0; m < N; ++m)
-        s += DTi[m] * sf0[k * N2 + m * N + j] + DTj[m] * sf1[k * N2 + i * N + m];
+      for (int m = 0; m < N; ++m) s += DTi[m] * r0[m] + DTj[m] * r1[m];
       yv[k] = s;
     }
+  }
+}
+
+// D and D^T, rows padded to NP, into shared memory (2 * N * NP elements at sDp)
+template <typename T, int N>
+__device__ __forceinline__ void stage_D(const DMat<T, N>& Dm, T* __restrict__ sDp, int tid, int nthreads)
+{
+  constexpr int NP = Pad<N>::NP;
+  for (int e = tid; e < N * NP; e += nthreads)
+  {
+    const int r = e / NP, c = e % NP;
+    sDp[e] = c < N ? Dm.d[r * N + c] : T(0);
+    sDp[N * NP + e] = c < N ? Dm.d[c * N + r] : T(0);
   }
 }
 
@@ -146,17 +208,19 @@ stiff_cell_kernel(const int32_t* __restrict__ cells, int ncl, const int32_t* __r
                   const T* __restrict__ G6, const T* __restrict__ x, T* __restrict__ y,
                   const DMat<T, N> Dm, T coeff)
 {
-  constexpr int N2 = N * N, ND = N2 * N;
-  __shared__ T s_w[CPB][3][ND];
-  __shared__ T sD[N * N];
-  if (threadIdx.x < N * N) sD[threadIdx.x] = Dm.d[threadIdx.x];
+  constexpr int N2 = N * N, ND = N2 * N, TILE = Pad<N>::TILE;
+  using V2 = typename Vec2<T>::type;
+  __shared__ __align__(16) T s_w[CPB][2][TILE];
+  __shared__ __align__(16) T sD[2 * Pad<N>::DSZ];
+  stage_D<T, N>(Dm, sD, threadIdx.x, SLOT * CPB);
   const int slot = threadIdx.x / SLOT, col = threadIdx.x % SLOT;
   const int ci = blockIdx.x * CPB + slot;
   const bool active = (col < N2) && (ci < ncl);
   const int64_t cell = active ? cells[ci] : 0;
   const int i = active ? col / N : 0, j = active ? col % N : 0;
   int32_t dof[N];
-  T u[N], yv[N];
+  T u[N], yv[N], f0[N], f1[N], f2[N];
+  V2 g[N][3];
 #pragma unroll
   for (int k = 0; k < N; ++k)
   {
@@ -164,9 +228,10 @@ stiff_cell_kernel(const int32_t* __restrict__ cells, int ncl, const int32_t* __r
     u[k] = active ? x[dof[k]] : T(0);
     yv[k] = 0;
   }
+  if (active) load_G<T, N>(G6 + cell * (int64_t)(6 * ND), col, g);
   __syncthreads(); // sD visible
-  cell_apply<T, N>(u, yv, G6 + cell * (int64_t)(6 * ND), s_w[slot][0], s_w[slot][1], s_w[slot][2],
-                   col, i, j, Dm, sD, coeff, active, BlockSync());
+  cell_phase1<T, N>(u, g, s_w[slot][0], s_w[slot][1], i, j, Dm, sD, coeff, active, BlockSync(), f0, f1, f2);
+  cell_phase2<T, N>(f0, f1, f2, s_w[slot][0], s_w[slot][1], i, j, Dm, sD + Pad<N>::DSZ, active, BlockSync(), yv);
   if (active)
   {
 #pragma unroll
@@ -196,48 +261,84 @@ template <typename T, int N, int SLOT, int W, int MINB>
 __global__ void __launch_bounds__(SLOT* W, MINB)
 stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
 {
-  constexpr int N2 = N * N, ND = N2 * N, NT = SLOT * W;
+  constexpr int N2 = N * N, ND = N2 * N, NT = SLOT * W, TILE = Pad<N>::TILE, U = 8;
+  using V2 = typename Vec2<T>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* xl = reinterpret_cast<T*>(smem_raw);
   T* yl = xl + a.nloc_pad;
   T* work = yl + a.nloc_pad;
-  T* sD = work + W * 3 * ND;
+  T* sD = work + W * 2 * TILE;
   pdl_launch_dependents(); // the next colour may start staging; it waits before touching y
   const int b = batch0 + blockIdx.x;
-  const int64_t d0 = a.dof_off[b];
-  const int nloc = (int)(a.dof_off[b + 1] - d0);
+  const int64_t d0 = __ldg(a.dof_off + b);
+  const int nloc = (int)(__ldg(a.dof_off + b + 1) - d0);
   const int tid = threadIdx.x;
-  if (tid < N * N) sD[tid] = Dm.d[tid];
-  for (int l = tid; l < nloc; l += NT)
-  {
-    xl[l] = a.x[a.bdofs[d0 + l] & BD_MASK];
-    yl[l] = T(0);
-  }
-  __syncthreads();
   const int slot = tid / SLOT, col = tid % SLOT;
   const bool lane_ok = col < N2;
   const int i = lane_ok ? col / N : 0, j = lane_ok ? col % N : 0;
-  T* su = work + slot * 3 * ND;
-  const int r1 = a.round_off[b + 1];
-  for (int r = a.round_off[b]; r < r1; ++r)
+  const int r0 = __ldg(a.round_off + b), r1 = __ldg(a.round_off + b + 1);
+
+  // metadata and G of the first round are requested before the dofs are staged
+  int cell_n = r0 < r1 ? __ldg(a.slot_cell + (int64_t)r0 * W + slot) : -1;
+  int li_n[N];
+  V2 g[N][3];
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+    li_n[k] = (lane_ok && cell_n >= 0) ? (int)__ldg(a.ldm + ((int64_t)r0 * W + slot) * ND + k * N2 + col) : 0;
+  if (lane_ok && cell_n >= 0) load_G<T, N>(a.G6 + (int64_t)cell_n * (6 * ND), col, g);
+
+  stage_D<T, N>(Dm, sD, tid, NT);
+  // stage the batch's dofs: U independent index loads, then U independent gathers
+  for (int base = tid; base < nloc; base += NT * U)
   {
-    const int64_t sidx = (int64_t)r * W + slot;
-    const int cell = a.slot_cell[sidx];
+    uint32_t e[U];
+    T v[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? __ldg(a.bdofs + d0 + base + q * NT) : 0u;
+#pragma unroll
+    for (int q = 0; q < U; ++q) v[q] = base + q * NT < nloc ? a.x[e[q] & BD_MASK] : T(0);
+#pragma unroll
+    for (int q = 0; q < U; ++q)
+      if (base + q * NT < nloc)
+      {
+        xl[base + q * NT] = v[q];
+        yl[base + q * NT] = T(0);
+      }
+  }
+  __syncthreads();
+
+  T* A = work + slot * 2 * TILE;
+  T* AT = A + TILE;
+  for (int r = r0; r < r1; ++r)
+  {
+    const int cell = cell_n;
     const bool active = lane_ok && cell >= 0;
     int li[N];
-    T u[N], yv[N];
+    T u[N], yv[N], f0[N], f1[N], f2[N];
 #pragma unroll
     for (int k = 0; k < N; ++k)
     {
-      li[k] = active ? (int)a.ldm[sidx * ND + k * N2 + col] : 0;
+      li[k] = li_n[k];
       u[k] = active ? xl[li[k]] : T(0);
       yv[k] = 0;
     }
-    const T* Gc = a.G6 + (int64_t)(active ? cell : 0) * (6 * ND);
+    // next round's metadata
+    const int64_t sn = (int64_t)(r + 1) * W + slot;
+    cell_n = r + 1 < r1 ? __ldg(a.slot_cell + sn) : -1;
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      li_n[k] = (lane_ok && r + 1 < r1) ? (int)__ldg(a.ldm + sn * ND + k * N2 + col) : 0;
     if constexpr (SLOT <= 32)
-      cell_apply<T, N>(u, yv, Gc, su, su + ND, su + 2 * ND, col, i, j, Dm, sD, a.coeff, active, WarpSync());
+      cell_phase1<T, N>(u, g, A, AT, i, j, Dm, sD, a.coeff, active, WarpSync(), f0, f1, f2);
     else
-      cell_apply<T, N>(u, yv, Gc, su, su + ND, su + 2 * ND, col, i, j, Dm, sD, a.coeff, active, BlockSync());
+      cell_phase1<T, N>(u, g, A, AT, i, j, Dm, sD, a.coeff, active, BlockSync(), f0, f1, f2);
+    // G of this cell is consumed: request the next cell's G into the same registers so
+    // that the loads fly during phase 2 and the next gather
+    if (lane_ok && cell_n >= 0) load_G<T, N>(a.G6 + (int64_t)cell_n * (6 * ND), col, g);
+    if constexpr (SLOT <= 32)
+      cell_phase2<T, N>(f0, f1, f2, A, AT, i, j, Dm, sD + Pad<N>::DSZ, active, WarpSync(), yv);
+    else
+      cell_phase2<T, N>(f0, f1, f2, A, AT, i, j, Dm, sD + Pad<N>::DSZ, active, BlockSync(), yv);
     if (active)
     {
 #pragma unroll
@@ -246,14 +347,23 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
     __syncthreads();
   }
   pdl_wait(); // earlier colours have finished their writes to y
-  for (int l = tid; l < nloc; l += NT)
+  for (int base = tid; base < nloc; base += NT * U)
   {
-    const uint32_t e = a.bdofs[d0 + l];
-    const uint32_t dof = e & BD_MASK;
-    T v = yl[l];
-    if (!(e & BD_FIRST) || a.beta) v += a.y[dof];
-    if ((e & BD_LAST) && a.scale) v *= a.scale[dof];
-    a.y[dof] = v;
+    uint32_t e[U];
+    T v[U], sc[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? __ldg(a.bdofs + d0 + base + q * NT) : BD_FIRST;
+#pragma unroll
+    for (int q = 0; q < U; ++q)
+    {
+      const bool ok = base + q * NT < nloc;
+      const uint32_t dof = e[q] & BD_MASK;
+      v[q] = (ok && (!(e[q] & BD_FIRST) || a.beta)) ? a.y[dof] : T(0);
+      sc[q] = (ok && (e[q] & BD_LAST) && a.scale) ? __ldg(a.scale + dof) : T(1);
+    }
+#pragma unroll
+    for (int q = 0; q < U; ++q)
+      if (base + q * NT < nloc) a.y[e[q] & BD_MASK] = (v[q] + yl[base + q * NT]) * sc[q];
   }
 }
 
@@ -521,7 +631,8 @@ extern "C" int wfx_stiffness_create(wfx_ctx* ctx, wfx_geom* geom, int64_t ndofs,
     else
     {
       const size_t esz = op->dtype == WFX_F64 ? 8 : 4;
-      const size_t work = (size_t)lc.W * 3 * op->nd * esz + (size_t)op->N * op->N * esz;
+      const int NPad = (op->N % 2) ? op->N + 1 : op->N;
+      const size_t work = ((size_t)lc.W * 2 * op->N * op->N * NPad + 2 * (size_t)op->N * NPad) * esz;
       const size_t avail = ctx->smem_optin > work + 1024 ? ctx->smem_optin - work - 1024 : 0;
       int nloc_cap = (int)std::min<size_t>(avail / (2 * esz), 65535);
       if (const char* e = std::getenv("WFX_NLOC_CAP")) nloc_cap = std::min(nloc_cap, std::atoi(e));
