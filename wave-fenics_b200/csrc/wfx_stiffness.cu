@@ -61,28 +61,13 @@ struct BlockSync
   __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
 
-// Shared-memory tiles of one cell slot: two [N][N][NP] tiles, rows padded to an even
-// length so that every row is a whole number of 16-byte (fp64) vectors.
+// Shared-memory tiles of one cell slot: four [N][N][N] tiles (A, AT, B0, B1).
 template <int N>
-struct Pad
+struct Tiles
 {
-  static constexpr int NP = (N % 2) ? N + 1 : N;
-  static constexpr int TILE = N * N * NP; // elements per tile
-  static constexpr int DSZ = N * NP;      // padded derivative matrix
+  static constexpr int TILE = N * N * N; // elements per tile
+  static constexpr int SLOT_ELEMS = 4 * TILE;
 };
-
-template <typename T, int NP>
-__device__ __forceinline__ void lds_row(const T* __restrict__ p, T (&r)[NP])
-{
-  using V2 = typename Vec2<T>::type;
-#pragma unroll
-  for (int q = 0; q < NP / 2; ++q)
-  {
-    const V2 v = reinterpret_cast<const V2*>(p)[q];
-    r[2 * q] = v.x;
-    r[2 * q + 1] = v.y;
-  }
-}
 
 // G of one cell for this thread's column: [k][pair] 2-vectors, streamed once from HBM.
 template <typename T, int N>
@@ -97,107 +82,124 @@ __device__ __forceinline__ void load_G(const T* __restrict__ Gc, int col,
     for (int p = 0; p < 3; ++p) g[k][p] = ld_stream(gp + (k * 3 + p) * (N * N));
 }
 
-// Phase 1 of one cell, one thread per (i,j) column: u[k] = nodal values of the column.
-//   w0 = sum_m D[i][m] u(m,j,k), w1 = sum_m D[j][m] u(i,m,k), w2 = sum_m D[k][m] u(i,j,m)
-//   f  = coeff * G w        
-// A holds u as [k][i][j], AT as [k][j][i], so both in-plane contractions read whole rows
-// with vector loads.  sDp = D padded [N][NP].  Inactive threads only synchronise.
+// Sum-factorised cell kernel, "one line per thread, three roles".  The N^2 threads of a
+// cell are indexed (p,q) and each plays three roles, owning a full grid line in registers:
+//    role K: points (i=p, j=q, k=*)   -- the gather/scatter role, holds u, G, f, y
+//    role J: points (i=p, j=*, k=q)
+//    role I: points (i=*, j=p, k=q)
+// A 1-D contraction along a line is register-only and its derivative-matrix operand is a
+// compile-time index into the kernel-parameter constant bank (no registers, no shared
+// memory for D).  Lines are exchanged between roles through four shared tiles:
+//    A [k][i][j], AT [k][j][i]  role K -> roles J / I   (u in part 1, f1 / f0 in part 2)
+//    B1[i][j][k], B0 [i][j][k]  roles J / I -> role K   (w1 / w0, then the y partial sums)
+// Part 1:  w0 = sum_m D[i][m] u(m,j,k), w1 = sum_m D[j][m] u(i,m,k), w2 = sum_m D[k][m] u(i,j,m),
+//          f = coeff * G w   (SURVEY.md App. A.9); f0 -> AT, f1 -> A, f2 stays in registers.
+// Part 2:  y(i,j,k) = sum_m D[m][i] f0(m,j,k) + D[m][j] f1(i,m,k) + D[m][k] f2(i,j,m).
+// Inactive threads (padding lanes / empty slots) only take part in the synchronisation.
 template <typename T, int N, typename Sync>
-__device__ __forceinline__ void cell_phase1(const T (&u)[N], const typename Vec2<T>::type (&g)[N][3],
-                                            T* __restrict__ A, T* __restrict__ AT, int i, int j,
-                                            const DMat<T, N>& Dm, const T* __restrict__ sDp, T coeff,
-                                            bool active, Sync sync, T (&f0)[N], T (&f1)[N], T (&f2)[N])
+__device__ __forceinline__ void cell_part1(const T (&u)[N], const typename Vec2<T>::type (&g)[N][3],
+                                           T* __restrict__ tiles, int p, int q,
+                                           const DMat<T, N>& Dm, T coeff, bool active, Sync sync,
+                                           T (&f2)[N])
 {
-  constexpr int NP = Pad<N>::NP;
+  constexpr int TILE = Tiles<N>::TILE;
+  T* A = tiles;
+  T* AT = tiles + TILE;
+  T* B0 = tiles + 2 * TILE;
+  T* B1 = tiles + 3 * TILE;
   if (active)
   {
 #pragma unroll
     for (int k = 0; k < N; ++k)
     {
-      A[(k * N + i) * NP + j] = u[k];
-      AT[(k * N + j) * NP + i] = u[k];
+      A[(k * N + p) * N + q] = u[k];
+      AT[(k * N + q) * N + p] = u[k];
     }
   }
   sync();
+  T w2[N];
   if (active)
   {
-    T Di[NP], Dj[NP];
-    lds_row<T, NP>(sDp + i * NP, Di);
-    lds_row<T, NP>(sDp + j * NP, Dj);
+    T lj[N], li[N];
 #pragma unroll
-    for (int k = 0; k < N; ++k)
+    for (int m = 0; m < N; ++m)
     {
-      T ri[NP], rj[NP];
-      lds_row<T, NP>(A + (k * N + i) * NP, ri);  // u(i, m, k)
-      lds_row<T, NP>(AT + (k * N + j) * NP, rj); // u(m, j, k)
-      T w0 = 0, w1 = 0, w2 = 0;
+      lj[m] = A[(q * N + p) * N + m];  // u(p, m, q)
+      li[m] = AT[(q * N + p) * N + m]; // u(m, p, q)
+    }
+#pragma unroll
+    for (int n = 0; n < N; ++n)
+    {
+      T s0 = 0, s1 = 0, s2 = 0;
 #pragma unroll
       for (int m = 0; m < N; ++m)
       {
-        w0 += Di[m] * rj[m];
-        w1 += Dj[m] * ri[m];
-        w2 += Dm.d[k * N + m] * u[m];
+        s1 += Dm.d[n * N + m] * lj[m];
+        s0 += Dm.d[n * N + m] * li[m];
+        s2 += Dm.d[n * N + m] * u[m];
       }
-      const T g00 = g[k][0].x, g01 = g[k][0].y, g02 = g[k][1].x;
-      const T g11 = g[k][1].y, g12 = g[k][2].x, g22 = g[k][2].y;
-      f0[k] = coeff * (g00 * w0 + g01 * w1 + g02 * w2);
-      f1[k] = coeff * (g01 * w0 + g11 * w1 + g12 * w2);
-      f2[k] = coeff * (g02 * w0 + g12 * w1 + g22 * w2);
-    }
-  }
-  sync(); // every read of A / AT is done: the tiles can take f
-}
-
-// Phase 2: y(i,j,k) = sum_m D[m][i] f0(m,j,k) + D[m][j] f1(i,m,k) + D[m][k] f2(i,j,m).
-// f0 goes to AT as [k][j][i], f1 to A as [k][i][j].  sDTp = D^T padded [N][NP].
-template <typename T, int N, typename Sync>
-__device__ __forceinline__ void cell_phase2(const T (&f0)[N], const T (&f1)[N], const T (&f2)[N],
-                                            T* __restrict__ A, T* __restrict__ AT, int i, int j,
-                                            const DMat<T, N>& Dm, const T* __restrict__ sDTp,
-                                            bool active, Sync sync, T (&yv)[N])
-{
-  constexpr int NP = Pad<N>::NP;
-  if (active)
-  {
-#pragma unroll
-    for (int k = 0; k < N; ++k)
-    {
-      AT[(k * N + j) * NP + i] = f0[k];
-      A[(k * N + i) * NP + j] = f1[k];
+      B1[(p * N + n) * N + q] = s1; // w1(p, n, q)
+      B0[(n * N + p) * N + q] = s0; // w0(n, p, q)
+      w2[n] = s2;                   // w2(p, q, n)
     }
   }
   sync();
   if (active)
   {
-    T DTi[NP], DTj[NP];
-    lds_row<T, NP>(sDTp + i * NP, DTi);
-    lds_row<T, NP>(sDTp + j * NP, DTj);
 #pragma unroll
     for (int k = 0; k < N; ++k)
     {
-      T r0[NP], r1[NP];
-      lds_row<T, NP>(AT + (k * N + j) * NP, r0); // f0(m, j, k)
-      lds_row<T, NP>(A + (k * N + i) * NP, r1);  // f1(i, m, k)
-      T s = 0;
-#pragma unroll
-      for (int m = 0; m < N; ++m) s += Dm.d[m * N + k] * f2[m];
-#pragma unroll
-      for (int m = 0; m < N; ++m) s += DTi[m] * r0[m] + DTj[m] * r1[m];
-      yv[k] = s;
+      const T w0 = B0[(p * N + q) * N + k];
+      const T w1 = B1[(p * N + q) * N + k];
+      const T g00 = g[k][0].x, g01 = g[k][0].y, g02 = g[k][1].x;
+      const T g11 = g[k][1].y, g12 = g[k][2].x, g22 = g[k][2].y;
+      AT[(k * N + q) * N + p] = coeff * (g00 * w0 + g01 * w1 + g02 * w2[k]); // f0
+      A[(k * N + p) * N + q] = coeff * (g01 * w0 + g11 * w1 + g12 * w2[k]);  // f1
+      f2[k] = coeff * (g02 * w0 + g12 * w1 + g22 * w2[k]);
     }
   }
 }
 
-// D and D^T, rows padded to NP, into shared memory (2 * N * NP elements at sDp)
-template <typename T, int N>
-__device__ __forceinline__ void stage_D(const DMat<T, N>& Dm, T* __restrict__ sDp, int tid, int nthreads)
+template <typename T, int N, typename Sync>
+__device__ __forceinline__ void cell_part2(const T (&f2)[N], T* __restrict__ tiles, int p, int q,
+                                           const DMat<T, N>& Dm, bool active, Sync sync, T (&yv)[N])
 {
-  constexpr int NP = Pad<N>::NP;
-  for (int e = tid; e < N * NP; e += nthreads)
+  constexpr int TILE = Tiles<N>::TILE;
+  T* A = tiles;
+  T* AT = tiles + TILE;
+  T* B0 = tiles + 2 * TILE;
+  T* B1 = tiles + 3 * TILE;
+  sync(); // f0 / f1 visible
+  if (active)
   {
-    const int r = e / NP, c = e % NP;
-    sDp[e] = c < N ? Dm.d[r * N + c] : T(0);
-    sDp[N * NP + e] = c < N ? Dm.d[c * N + r] : T(0);
+    T lj[N], li[N];
+#pragma unroll
+    for (int m = 0; m < N; ++m)
+    {
+      lj[m] = A[(q * N + p) * N + m];  // f1(p, m, q)
+      li[m] = AT[(q * N + p) * N + m]; // f0(m, p, q)
+    }
+#pragma unroll
+    for (int n = 0; n < N; ++n)
+    {
+      T s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+      for (int m = 0; m < N; ++m)
+      {
+        s1 += Dm.d[m * N + n] * lj[m];
+        s0 += Dm.d[m * N + n] * li[m];
+        s2 += Dm.d[m * N + n] * f2[m];
+      }
+      B1[(p * N + n) * N + q] = s1;
+      B0[(n * N + p) * N + q] = s0;
+      yv[n] = s2;
+    }
+  }
+  sync();
+  if (active)
+  {
+#pragma unroll
+    for (int k = 0; k < N; ++k) yv[k] += B0[(p * N + q) * N + k] + B1[(p * N + q) * N + k];
   }
 }
 
@@ -208,18 +210,16 @@ stiff_cell_kernel(const int32_t* __restrict__ cells, int ncl, const int32_t* __r
                   const T* __restrict__ G6, const T* __restrict__ x, T* __restrict__ y,
                   const DMat<T, N> Dm, T coeff)
 {
-  constexpr int N2 = N * N, ND = N2 * N, TILE = Pad<N>::TILE;
+  constexpr int N2 = N * N, ND = N2 * N;
   using V2 = typename Vec2<T>::type;
-  __shared__ __align__(16) T s_w[CPB][2][TILE];
-  __shared__ __align__(16) T sD[2 * Pad<N>::DSZ];
-  stage_D<T, N>(Dm, sD, threadIdx.x, SLOT * CPB);
+  __shared__ __align__(16) T s_w[CPB][Tiles<N>::SLOT_ELEMS];
   const int slot = threadIdx.x / SLOT, col = threadIdx.x % SLOT;
   const int ci = blockIdx.x * CPB + slot;
   const bool active = (col < N2) && (ci < ncl);
   const int64_t cell = active ? cells[ci] : 0;
   const int i = active ? col / N : 0, j = active ? col % N : 0;
   int32_t dof[N];
-  T u[N], yv[N], f0[N], f1[N], f2[N];
+  T u[N], yv[N], f2[N];
   V2 g[N][3];
 #pragma unroll
   for (int k = 0; k < N; ++k)
@@ -229,9 +229,8 @@ stiff_cell_kernel(const int32_t* __restrict__ cells, int ncl, const int32_t* __r
     yv[k] = 0;
   }
   if (active) load_G<T, N>(G6 + cell * (int64_t)(6 * ND), col, g);
-  __syncthreads(); // sD visible
-  cell_phase1<T, N>(u, g, s_w[slot][0], s_w[slot][1], i, j, Dm, sD, coeff, active, BlockSync(), f0, f1, f2);
-  cell_phase2<T, N>(f0, f1, f2, s_w[slot][0], s_w[slot][1], i, j, Dm, sD + Pad<N>::DSZ, active, BlockSync(), yv);
+  cell_part1<T, N>(u, g, s_w[slot], i, j, Dm, coeff, active, BlockSync(), f2);
+  cell_part2<T, N>(f2, s_w[slot], i, j, Dm, active, BlockSync(), yv);
   if (active)
   {
 #pragma unroll
@@ -261,13 +260,12 @@ template <typename T, int N, int SLOT, int W, int MINB>
 __global__ void __launch_bounds__(SLOT* W, MINB)
 stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
 {
-  constexpr int N2 = N * N, ND = N2 * N, NT = SLOT * W, TILE = Pad<N>::TILE, U = 8;
+  constexpr int N2 = N * N, ND = N2 * N, NT = SLOT * W, U = 8;
   using V2 = typename Vec2<T>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* xl = reinterpret_cast<T*>(smem_raw);
   T* yl = xl + a.nloc_pad;
   T* work = yl + a.nloc_pad;
-  T* sD = work + W * 2 * TILE;
   pdl_launch_dependents(); // the next colour may start staging; it waits before touching y
   const int b = batch0 + blockIdx.x;
   const int64_t d0 = __ldg(a.dof_off + b);
@@ -287,7 +285,6 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
     li_n[k] = (lane_ok && cell_n >= 0) ? (int)__ldg(a.ldm + ((int64_t)r0 * W + slot) * ND + k * N2 + col) : 0;
   if (lane_ok && cell_n >= 0) load_G<T, N>(a.G6 + (int64_t)cell_n * (6 * ND), col, g);
 
-  stage_D<T, N>(Dm, sD, tid, NT);
   // stage the batch's dofs: U independent index loads, then U independent gathers
   for (int base = tid; base < nloc; base += NT * U)
   {
@@ -307,14 +304,13 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   }
   __syncthreads();
 
-  T* A = work + slot * 2 * TILE;
-  T* AT = A + TILE;
+  T* tiles = work + slot * Tiles<N>::SLOT_ELEMS;
   for (int r = r0; r < r1; ++r)
   {
     const int cell = cell_n;
     const bool active = lane_ok && cell >= 0;
     int li[N];
-    T u[N], yv[N], f0[N], f1[N], f2[N];
+    T u[N], yv[N], f2[N];
 #pragma unroll
     for (int k = 0; k < N; ++k)
     {
@@ -328,17 +324,13 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
 #pragma unroll
     for (int k = 0; k < N; ++k)
       li_n[k] = (lane_ok && r + 1 < r1) ? (int)__ldg(a.ldm + sn * ND + k * N2 + col) : 0;
-    if constexpr (SLOT <= 32)
-      cell_phase1<T, N>(u, g, A, AT, i, j, Dm, sD, a.coeff, active, WarpSync(), f0, f1, f2);
-    else
-      cell_phase1<T, N>(u, g, A, AT, i, j, Dm, sD, a.coeff, active, BlockSync(), f0, f1, f2);
+    if constexpr (SLOT <= 32) cell_part1<T, N>(u, g, tiles, i, j, Dm, a.coeff, active, WarpSync(), f2);
+    else cell_part1<T, N>(u, g, tiles, i, j, Dm, a.coeff, active, BlockSync(), f2);
     // G of this cell is consumed: request the next cell's G into the same registers so
-    // that the loads fly during phase 2 and the next gather
+    // that the loads fly during part 2 and the next gather
     if (lane_ok && cell_n >= 0) load_G<T, N>(a.G6 + (int64_t)cell_n * (6 * ND), col, g);
-    if constexpr (SLOT <= 32)
-      cell_phase2<T, N>(f0, f1, f2, A, AT, i, j, Dm, sD + Pad<N>::DSZ, active, WarpSync(), yv);
-    else
-      cell_phase2<T, N>(f0, f1, f2, A, AT, i, j, Dm, sD + Pad<N>::DSZ, active, BlockSync(), yv);
+    if constexpr (SLOT <= 32) cell_part2<T, N>(f2, tiles, i, j, Dm, active, WarpSync(), yv);
+    else cell_part2<T, N>(f2, tiles, i, j, Dm, active, BlockSync(), yv);
     if (active)
     {
 #pragma unroll
@@ -631,8 +623,7 @@ extern "C" int wfx_stiffness_create(wfx_ctx* ctx, wfx_geom* geom, int64_t ndofs,
     else
     {
       const size_t esz = op->dtype == WFX_F64 ? 8 : 4;
-      const int NPad = (op->N % 2) ? op->N + 1 : op->N;
-      const size_t work = ((size_t)lc.W * 2 * op->N * op->N * NPad + 2 * (size_t)op->N * NPad) * esz;
+      const size_t work = (size_t)lc.W * 4 * op->nd * esz; // four [N][N][N] tiles per cell slot
       const size_t avail = ctx->smem_optin > work + 1024 ? ctx->smem_optin - work - 1024 : 0;
       int nloc_cap = (int)std::min<size_t>(avail / (2 * esz), 65535);
       if (const char* e = std::getenv("WFX_NLOC_CAP")) nloc_cap = std::min(nloc_cap, std::atoi(e));
