@@ -80,6 +80,7 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
   plan = BrickPlan();
   plan.P = P;
   plan.nd = nd;
+  plan.ndp = (nd + 7) & ~7;
   plan.W = W;
   plan.ncells = ncells;
   plan.ndofs = ndofs;
@@ -306,18 +307,19 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
         if (filled == 0)
         {
           plan.slot_cell.resize(plan.slot_cell.size() + W, -1);
-          plan.ldm.resize(plan.ldm.size() + (size_t)W * nd, 0);
+          plan.ldm.resize(plan.ldm.size() + (size_t)W * plan.ndp, 0);
           ++nrounds;
         }
         const size_t slot = plan.slot_cell.size() - W + filled;
         const int32_t cell = order[b.begin + q];
         plan.slot_cell[slot] = cell;
         const int32_t* d = tdm + (int64_t)cell * nd;
-        for (int t = 0; t < nd; ++t) plan.ldm[slot * nd + t] = (uint16_t)g2l[d[t]];
+        for (int t = 0; t < nd; ++t) plan.ldm[slot * plan.ndp + t] = (uint16_t)g2l[d[t]];
         filled = (filled + 1) % W;
       }
     }
     plan.round_off[i + 1] = plan.round_off[i] + nrounds;
+    plan.rounds_max = std::max(plan.rounds_max, nrounds);
     for (int32_t d : uniq) g2l[d] = -1;
   }
   plan.nrounds_total = plan.round_off[nb];
@@ -370,13 +372,13 @@ void verify_brick_plan(const BrickPlan& plan, const int32_t* tdm)
           ++cells_total;
           for (int t = 0; t < nd; ++t)
           {
-            const int l = plan.ldm[slot * nd + t];
+            const int l = plan.ldm[slot * plan.ndp + t];
             if (l >= nloc) fail("brick plan: local dof index out of range");
             if ((int32_t)(plan.bdofs[d0 + l] & BD_MASK) != tdm[(int64_t)cell * nd + t])
               fail("brick plan: local dofmap does not reproduce the dofmap");
             if (round_stamp[l] == r) fail("brick plan: two cells of one round share a dof");
           }
-          for (int t = 0; t < nd; ++t) round_stamp[plan.ldm[slot * nd + t]] = r;
+          for (int t = 0; t < nd; ++t) round_stamp[plan.ldm[slot * plan.ndp + t]] = r;
         }
     }
   if (cells_total != ncells) fail("brick plan: %lld of %lld cells covered", (long long)cells_total, (long long)ncells);

@@ -34,6 +34,8 @@ struct CellColourPlan
 struct BrickPlan
 {
   int P = 0, nd = 0, W = 0; // W = cell slots processed concurrently per round
+  int ndp = 0;              // slot stride of ldm: nd rounded up to 8 entries (16 bytes)
+  int rounds_max = 0;       // most rounds in one batch
   int64_t ncells = 0, ndofs = 0;
   int nbatches = 0, ncolours = 0;
   int nloc_max = 0;                // largest number of unique dofs in a batch
@@ -44,7 +46,7 @@ struct BrickPlan
   std::vector<uint32_t> bdofs;     // global dof | BD_FIRST | BD_LAST, ascending per batch
   std::vector<int32_t> round_off;  // [nbatches+1] into rounds
   std::vector<int32_t> slot_cell;  // [nrounds_total*W] cell id or -1
-  std::vector<uint16_t> ldm;       // [nrounds_total*W][nd] batch-local dof, k-major point order
+  std::vector<uint16_t> ldm;       // [nrounds_total*W][ndp] batch-local dof, k-major point order
   std::vector<int32_t> untouched;  // vector entries no cell references
   // statistics
   int64_t n_slots_padded = 0;

@@ -61,12 +61,13 @@ struct BlockSync
   __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
 
-// Shared-memory tiles of one cell slot: four [N][N][N] tiles (A, AT, B0, B1).
+// Shared-memory tiles of one cell slot: two [N][N][N] tiles, A [k][i][j] and AT [k][j][i].
 template <int N>
 struct Tiles
 {
   static constexpr int TILE = N * N * N; // elements per tile
-  static constexpr int SLOT_ELEMS = 4 * TILE;
+  static constexpr int SLOT_ELEMS = 2 * TILE;
+  static constexpr int NDP = (TILE + 7) & ~7; // slot stride of the local dofmap (16-byte units)
 };
 
 // G of one cell for this thread's column: [k][pair] 2-vectors, streamed once from HBM.
@@ -89,13 +90,32 @@ __device__ __forceinline__ void load_G(const T* __restrict__ Gc, int col,
 //    role I: points (i=*, j=p, k=q)
 // A 1-D contraction along a line is register-only and its derivative-matrix operand is a
 // compile-time index into the kernel-parameter constant bank (no registers, no shared
-// memory for D).  Lines are exchanged between roles through four shared tiles:
-//    A [k][i][j], AT [k][j][i]  role K -> roles J / I   (u in part 1, f1 / f0 in part 2)
-//    B1[i][j][k], B0 [i][j][k]  roles J / I -> role K   (w1 / w0, then the y partial sums)
+// memory for D).  Lines move between roles through two shared tiles, transformed IN PLACE:
+// role K writes A [k][i][j] and AT [k][j][i]; role J reads row (k=q,i=p) of A, contracts it
+// and writes the result over the same row (it is the row's only reader); role I does the
+// same with row (k=q,j=p) of AT; role K reads its column back with stride N^2.
 // Part 1:  w0 = sum_m D[i][m] u(m,j,k), w1 = sum_m D[j][m] u(i,m,k), w2 = sum_m D[k][m] u(i,j,m),
 //          f = coeff * G w   (SURVEY.md App. A.9); f0 -> AT, f1 -> A, f2 stays in registers.
 // Part 2:  y(i,j,k) = sum_m D[m][i] f0(m,j,k) + D[m][j] f1(i,m,k) + D[m][k] f2(i,j,m).
 // Inactive threads (padding lanes / empty slots) only take part in the synchronisation.
+template <typename T, int N, bool TRANSPOSE>
+__device__ __forceinline__ void line_transform(T* __restrict__ row, const DMat<T, N>& Dm)
+{
+  T l[N], o[N];
+#pragma unroll
+  for (int m = 0; m < N; ++m) l[m] = row[m];
+#pragma unroll
+  for (int n = 0; n < N; ++n)
+  {
+    T s = 0;
+#pragma unroll
+    for (int m = 0; m < N; ++m) s += (TRANSPOSE ? Dm.d[m * N + n] : Dm.d[n * N + m]) * l[m];
+    o[n] = s;
+  }
+#pragma unroll
+  for (int n = 0; n < N; ++n) row[n] = o[n];
+}
+
 template <typename T, int N, typename Sync>
 __device__ __forceinline__ void cell_part1(const T (&u)[N], const typename Vec2<T>::type (&g)[N][3],
                                            T* __restrict__ tiles, int p, int q,
@@ -105,8 +125,6 @@ __device__ __forceinline__ void cell_part1(const T (&u)[N], const typename Vec2<
   constexpr int TILE = Tiles<N>::TILE;
   T* A = tiles;
   T* AT = tiles + TILE;
-  T* B0 = tiles + 2 * TILE;
-  T* B1 = tiles + 3 * TILE;
   if (active)
   {
 #pragma unroll
@@ -117,31 +135,10 @@ __device__ __forceinline__ void cell_part1(const T (&u)[N], const typename Vec2<
     }
   }
   sync();
-  T w2[N];
   if (active)
   {
-    T lj[N], li[N];
-#pragma unroll
-    for (int m = 0; m < N; ++m)
-    {
-      lj[m] = A[(q * N + p) * N + m];  // u(p, m, q)
-      li[m] = AT[(q * N + p) * N + m]; // u(m, p, q)
-    }
-#pragma unroll
-    for (int n = 0; n < N; ++n)
-    {
-      T s0 = 0, s1 = 0, s2 = 0;
-#pragma unroll
-      for (int m = 0; m < N; ++m)
-      {
-        s1 += Dm.d[n * N + m] * lj[m];
-        s0 += Dm.d[n * N + m] * li[m];
-        s2 += Dm.d[n * N + m] * u[m];
-      }
-      B1[(p * N + n) * N + q] = s1; // w1(p, n, q)
-      B0[(n * N + p) * N + q] = s0; // w0(n, p, q)
-      w2[n] = s2;                   // w2(p, q, n)
-    }
+    line_transform<T, N, false>(A + (q * N + p) * N, Dm);  // u(p, ., q) -> w1(p, ., q)
+    line_transform<T, N, false>(AT + (q * N + p) * N, Dm); // u(., p, q) -> w0(., p, q)
   }
   sync();
   if (active)
@@ -149,13 +146,16 @@ __device__ __forceinline__ void cell_part1(const T (&u)[N], const typename Vec2<
 #pragma unroll
     for (int k = 0; k < N; ++k)
     {
-      const T w0 = B0[(p * N + q) * N + k];
-      const T w1 = B1[(p * N + q) * N + k];
+      T w2 = 0;
+#pragma unroll
+      for (int m = 0; m < N; ++m) w2 += Dm.d[k * N + m] * u[m];
+      const T w0 = AT[(k * N + q) * N + p];
+      const T w1 = A[(k * N + p) * N + q];
       const T g00 = g[k][0].x, g01 = g[k][0].y, g02 = g[k][1].x;
       const T g11 = g[k][1].y, g12 = g[k][2].x, g22 = g[k][2].y;
-      AT[(k * N + q) * N + p] = coeff * (g00 * w0 + g01 * w1 + g02 * w2[k]); // f0
-      A[(k * N + p) * N + q] = coeff * (g01 * w0 + g11 * w1 + g12 * w2[k]);  // f1
-      f2[k] = coeff * (g02 * w0 + g12 * w1 + g22 * w2[k]);
+      AT[(k * N + q) * N + p] = coeff * (g00 * w0 + g01 * w1 + g02 * w2); // f0
+      A[(k * N + p) * N + q] = coeff * (g01 * w0 + g11 * w1 + g12 * w2);  // f1
+      f2[k] = coeff * (g02 * w0 + g12 * w1 + g22 * w2);
     }
   }
 }
@@ -167,39 +167,23 @@ __device__ __forceinline__ void cell_part2(const T (&f2)[N], T* __restrict__ til
   constexpr int TILE = Tiles<N>::TILE;
   T* A = tiles;
   T* AT = tiles + TILE;
-  T* B0 = tiles + 2 * TILE;
-  T* B1 = tiles + 3 * TILE;
   sync(); // f0 / f1 visible
   if (active)
   {
-    T lj[N], li[N];
-#pragma unroll
-    for (int m = 0; m < N; ++m)
-    {
-      lj[m] = A[(q * N + p) * N + m];  // f1(p, m, q)
-      li[m] = AT[(q * N + p) * N + m]; // f0(m, p, q)
-    }
-#pragma unroll
-    for (int n = 0; n < N; ++n)
-    {
-      T s0 = 0, s1 = 0, s2 = 0;
-#pragma unroll
-      for (int m = 0; m < N; ++m)
-      {
-        s1 += Dm.d[m * N + n] * lj[m];
-        s0 += Dm.d[m * N + n] * li[m];
-        s2 += Dm.d[m * N + n] * f2[m];
-      }
-      B1[(p * N + n) * N + q] = s1;
-      B0[(n * N + p) * N + q] = s0;
-      yv[n] = s2;
-    }
+    line_transform<T, N, true>(A + (q * N + p) * N, Dm);  // f1(p, ., q) -> sum_m D[m][.] f1(p,m,q)
+    line_transform<T, N, true>(AT + (q * N + p) * N, Dm); // f0(., p, q) -> sum_m D[m][.] f0(m,p,q)
   }
   sync();
   if (active)
   {
 #pragma unroll
-    for (int k = 0; k < N; ++k) yv[k] += B0[(p * N + q) * N + k] + B1[(p * N + q) * N + k];
+    for (int k = 0; k < N; ++k)
+    {
+      T s = AT[(k * N + q) * N + p] + A[(k * N + p) * N + q];
+#pragma unroll
+      for (int m = 0; m < N; ++m) s += Dm.d[m * N + k] * f2[m];
+      yv[k] = s;
+    }
   }
 }
 
@@ -252,20 +236,27 @@ struct BrickArgs
   T* y;
   const T* scale; // nullable: applied on the LAST touch of a dof
   T coeff;
-  int beta;      // 0: FIRST touch overwrites y; 1: accumulates into y
-  int nloc_pad;  // capacity of the shared dof arrays (even)
+  int beta;       // 0: FIRST touch overwrites y; 1: accumulates into y
+  int nloc_pad;   // capacity of the shared dof arrays (even)
+  int rounds_max; // capacity (rounds) of the shared local-dofmap staging area
 };
 
+// Shared memory of one CTA:  xl[nloc_pad] | yl[nloc_pad] | tiles[W][2][N^3] | sldm[rounds_max*W*NDP] (u16)
+//                            | scell[rounds_max*W] (i32)
 template <typename T, int N, int SLOT, int W, int MINB>
 __global__ void __launch_bounds__(SLOT* W, MINB)
 stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
 {
-  constexpr int N2 = N * N, ND = N2 * N, NT = SLOT * W, U = 8;
+  constexpr int N2 = N * N, ND = N2 * N, NT = SLOT * W, U = 8, NDP = Tiles<N>::NDP;
   using V2 = typename Vec2<T>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* xl = reinterpret_cast<T*>(smem_raw);
   T* yl = xl + a.nloc_pad;
   T* work = yl + a.nloc_pad;
+  // 16-byte aligned for the vector copies below
+  const size_t meta_off = ((size_t)(2 * a.nloc_pad + W * Tiles<N>::SLOT_ELEMS) * sizeof(T) + 15) & ~(size_t)15;
+  uint16_t* sldm = reinterpret_cast<uint16_t*>(smem_raw + meta_off);
+  int32_t* scell = reinterpret_cast<int32_t*>(sldm + (size_t)a.rounds_max * W * NDP);
   pdl_launch_dependents(); // the next colour may start staging; it waits before touching y
   const int b = batch0 + blockIdx.x;
   const int64_t d0 = __ldg(a.dof_off + b);
@@ -274,17 +265,22 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   const int slot = tid / SLOT, col = tid % SLOT;
   const bool lane_ok = col < N2;
   const int i = lane_ok ? col / N : 0, j = lane_ok ? col % N : 0;
-  const int r0 = __ldg(a.round_off + b), r1 = __ldg(a.round_off + b + 1);
+  const int r0 = __ldg(a.round_off + b), nr = __ldg(a.round_off + b + 1) - r0;
 
-  // metadata and G of the first round are requested before the dofs are staged
-  int cell_n = r0 < r1 ? __ldg(a.slot_cell + (int64_t)r0 * W + slot) : -1;
-  int li_n[N];
+  // G of the first cell is requested before anything is staged
   V2 g[N][3];
-#pragma unroll
-  for (int k = 0; k < N; ++k)
-    li_n[k] = (lane_ok && cell_n >= 0) ? (int)__ldg(a.ldm + ((int64_t)r0 * W + slot) * ND + k * N2 + col) : 0;
-  if (lane_ok && cell_n >= 0) load_G<T, N>(a.G6 + (int64_t)cell_n * (6 * ND), col, g);
-
+  {
+    const int c0 = nr > 0 ? __ldg(a.slot_cell + (int64_t)r0 * W + slot) : -1;
+    if (lane_ok && c0 >= 0) load_G<T, N>(a.G6 + (int64_t)c0 * (6 * ND), col, g);
+  }
+  // stage the batch's local dofmap (16-byte copies) and cell list
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.ldm + (int64_t)r0 * W * NDP);
+    uint4* dst = reinterpret_cast<uint4*>(sldm);
+    const int nv = nr * W * (NDP / 8);
+    for (int v = tid; v < nv; v += NT) dst[v] = __ldg(src + v);
+    for (int v = tid; v < nr * W; v += NT) scell[v] = __ldg(a.slot_cell + (int64_t)r0 * W + v);
+  }
   // stage the batch's dofs: U independent index loads, then U independent gathers
   for (int base = tid; base < nloc; base += NT * U)
   {
@@ -305,30 +301,28 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   __syncthreads();
 
   T* tiles = work + slot * Tiles<N>::SLOT_ELEMS;
-  for (int r = r0; r < r1; ++r)
+  for (int r = 0; r < nr; ++r)
   {
-    const int cell = cell_n;
+    const int cell = scell[r * W + slot];
     const bool active = lane_ok && cell >= 0;
+    const uint16_t* lrow = sldm + (r * W + slot) * NDP + col;
     int li[N];
     T u[N], yv[N], f2[N];
 #pragma unroll
     for (int k = 0; k < N; ++k)
     {
-      li[k] = li_n[k];
+      li[k] = active ? (int)lrow[k * N2] : 0;
       u[k] = active ? xl[li[k]] : T(0);
       yv[k] = 0;
     }
-    // next round's metadata
-    const int64_t sn = (int64_t)(r + 1) * W + slot;
-    cell_n = r + 1 < r1 ? __ldg(a.slot_cell + sn) : -1;
-#pragma unroll
-    for (int k = 0; k < N; ++k)
-      li_n[k] = (lane_ok && r + 1 < r1) ? (int)__ldg(a.ldm + sn * ND + k * N2 + col) : 0;
     if constexpr (SLOT <= 32) cell_part1<T, N>(u, g, tiles, i, j, Dm, a.coeff, active, WarpSync(), f2);
     else cell_part1<T, N>(u, g, tiles, i, j, Dm, a.coeff, active, BlockSync(), f2);
     // G of this cell is consumed: request the next cell's G into the same registers so
     // that the loads fly during part 2 and the next gather
-    if (lane_ok && cell_n >= 0) load_G<T, N>(a.G6 + (int64_t)cell_n * (6 * ND), col, g);
+    {
+      const int cn = r + 1 < nr ? scell[(r + 1) * W + slot] : -1;
+      if (lane_ok && cn >= 0) load_G<T, N>(a.G6 + (int64_t)cn * (6 * ND), col, g);
+    }
     if constexpr (SLOT <= 32) cell_part2<T, N>(f2, tiles, i, j, Dm, active, WarpSync(), yv);
     else cell_part2<T, N>(f2, tiles, i, j, Dm, active, BlockSync(), yv);
     if (active)
@@ -408,7 +402,7 @@ struct wfx_stiffness
   CellColourPlan cplan;
   DevBuf<int32_t> d_cells, d_tdm;
   // brick path
-  int ncolours = 0, nloc_pad = 0, W = 0;
+  int ncolours = 0, nloc_pad = 0, W = 0, rounds_max = 0;
   size_t smem_bytes = 0;
   std::vector<int32_t> colour_off;
   DevBuf<int64_t> d_dof_off;
@@ -459,6 +453,7 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   a.coeff = (T)(-1.0 * op->c0 * op->c0);
   a.beta = beta;
   a.nloc_pad = op->nloc_pad;
+  a.rounds_max = op->rounds_max;
   if (!beta && op->d_untouched.n)
   {
     const int n = (int)op->d_untouched.n;
@@ -623,7 +618,13 @@ extern "C" int wfx_stiffness_create(wfx_ctx* ctx, wfx_geom* geom, int64_t ndofs,
     else
     {
       const size_t esz = op->dtype == WFX_F64 ? 8 : 4;
-      const size_t work = (size_t)lc.W * 4 * op->nd * esz; // four [N][N][N] tiles per cell slot
+      // two [N][N][N] tiles per cell slot + the staged local dofmap / cell list of a batch;
+      // the latter depends on the plan (rounds per batch), so budget for the regular case
+      // (brick_edge^3 cells, 8 colours) first and verify after planning
+      const int ndp = (op->nd + 7) & ~7;
+      auto meta_bytes = [&](int rounds) { return (size_t)rounds * lc.W * (ndp * 2 + 4); };
+      const int rounds_guess = std::max(8, (lc.BE * lc.BE * lc.BE + lc.W - 1) / lc.W);
+      const size_t work = (size_t)lc.W * 2 * op->nd * esz + meta_bytes(rounds_guess) + 16;
       const size_t avail = ctx->smem_optin > work + 1024 ? ctx->smem_optin - work - 1024 : 0;
       int nloc_cap = (int)std::min<size_t>(avail / (2 * esz), 65535);
       if (const char* e = std::getenv("WFX_NLOC_CAP")) nloc_cap = std::min(nloc_cap, std::atoi(e));
@@ -636,7 +637,9 @@ extern "C" int wfx_stiffness_create(wfx_ctx* ctx, wfx_geom* geom, int64_t ndofs,
       op->colour_off = bp.colour_off;
       op->W = bp.W;
       op->nloc_pad = (bp.nloc_max + 1) & ~1;
-      op->smem_bytes = (size_t)op->nloc_pad * 2 * esz + work;
+      op->rounds_max = bp.rounds_max;
+      op->smem_bytes = ((((size_t)op->nloc_pad * 2 + (size_t)lc.W * 2 * op->nd) * esz + 15) & ~(size_t)15)
+                       + meta_bytes(bp.rounds_max);
       if (op->smem_bytes > ctx->smem_optin) fail("stiffness: batch needs %zu B shared memory", op->smem_bytes);
       op->d_dof_off.upload(bp.dof_off);
       op->d_bdofs.upload(bp.bdofs);
