@@ -42,11 +42,16 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: experiment builds (e.g. -DWFX_P4_W=1) into another file name."""
+    global LIB, STAMP
+    if out:
+        LIB, STAMP = os.path.join(HERE, out), os.path.join(HERE, "." + out + ".stamp")
+    FLAGS.extend(defines)
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read() == dig:
         return LIB
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + ("_" + out if out else ""))
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
@@ -77,4 +82,7 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs,
+                out=outs[0] if outs else None))

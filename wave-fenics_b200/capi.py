@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwavefx.so")
+LIB_PATH = os.environ.get("WFX_LIB") or os.path.join(HERE, "libwavefx.so")
 
 F64, F32 = 0, 1
 STIFF_AUTO, STIFF_CELL_COLOUR = 0, 1

@@ -61,14 +61,47 @@ struct BlockSync
   __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
 
-// Shared-memory tiles of one cell slot: two [N][N][N] tiles, A [k][i][j] and AT [k][j][i].
+// Shared-memory tiles of one cell slot: A [k][i][j] and AT [k][j][i], with plane strides and
+// row offsets chosen so that every access pattern of the three roles below is free of bank
+// conflicts for 64-bit words (16 banks of 8 bytes per half-warp).  For N = 5 the layout was
+// found by search (rows of AT at offsets {0,20,7,26,13} inside a 33-word plane); other
+// degrees use the plain layout.
 template <int N>
 struct Tiles
 {
-  static constexpr int TILE = N * N * N; // elements per tile
-  static constexpr int SLOT_ELEMS = 2 * TILE;
-  static constexpr int NDP = (TILE + 7) & ~7; // slot stride of the local dofmap (16-byte units)
+  static constexpr int PS_A = N * N, PS_T = N * N;
+  __host__ __device__ static constexpr int boff(int j) { return j * N; }
 };
+template <>
+struct Tiles<5>
+{
+  static constexpr int PS_A = 25, PS_T = 33;
+  __host__ __device__ static constexpr int boff(int j)
+  {
+    return j == 0 ? 0 : (j == 1 ? 20 : (j == 2 ? 7 : (j == 3 ? 26 : 13)));
+  }
+};
+template <int N> __host__ __device__ constexpr int tile_a_elems() { return N * Tiles<N>::PS_A; }
+template <int N> __host__ __device__ constexpr int slot_elems() { return N * (Tiles<N>::PS_A + Tiles<N>::PS_T); }
+template <int N> __host__ __device__ constexpr int ndp_of() { return (N * N * N + 7) & ~7; } // ldm slot stride
+
+// per-thread tile offsets of the three roles (constant for the whole kernel)
+struct RoleOff
+{
+  int kA, kT; // role K: element (k) of this thread's column is A[k*PS_A + kA], AT[k*PS_T + kT]
+  int rA, rT; // roles J / I: this thread's row starts at A[rA], AT[rT]
+};
+template <int N>
+__device__ __forceinline__ RoleOff role_offsets(int lane)
+{
+  const int hi = lane / N, lo = lane % N;
+  RoleOff o;
+  o.kA = hi * N + lo;                       // role K: i = hi, j = lo
+  o.kT = Tiles<N>::boff(lo) + hi;
+  o.rA = hi * Tiles<N>::PS_A + lo * N;      // role J: k = hi, i = lo, row over j
+  o.rT = hi * Tiles<N>::PS_T + Tiles<N>::boff(lo); // role I: k = hi, j = lo, row over i
+  return o;
+}
 
 // G of one cell for this thread's column: [k][pair] 2-vectors, streamed once from HBM.
 template <typename T, int N>
@@ -83,17 +116,17 @@ __device__ __forceinline__ void load_G(const T* __restrict__ Gc, int col,
     for (int p = 0; p < 3; ++p) g[k][p] = ld_stream(gp + (k * 3 + p) * (N * N));
 }
 
-// Sum-factorised cell kernel, "one line per thread, three roles".  The N^2 threads of a
-// cell are indexed (p,q) and each plays three roles, owning a full grid line in registers:
-//    role K: points (i=p, j=q, k=*)   -- the gather/scatter role, holds u, G, f, y
-//    role J: points (i=p, j=*, k=q)
-//    role I: points (i=*, j=p, k=q)
+// Sum-factorised cell kernel, "one line per thread, three roles".  Each of the N^2 threads
+// of a cell (lane = hi*N + lo) plays three roles, owning a full grid line in registers:
+//    role K: points (i=hi, j=lo, k=*)   -- the gather/scatter role, holds u, G, f, y
+//    role J: points (k=hi, i=lo, j=*)
+//    role I: points (k=hi, j=lo, i=*)
 // A 1-D contraction along a line is register-only and its derivative-matrix operand is a
 // compile-time index into the kernel-parameter constant bank (no registers, no shared
 // memory for D).  Lines move between roles through two shared tiles, transformed IN PLACE:
-// role K writes A [k][i][j] and AT [k][j][i]; role J reads row (k=q,i=p) of A, contracts it
-// and writes the result over the same row (it is the row's only reader); role I does the
-// same with row (k=q,j=p) of AT; role K reads its column back with stride N^2.
+// role K writes A [k][i][j] and AT [k][j][i]; role J reads its row of A, contracts it and
+// writes the result over the same row (it is the row's only reader); role I does the same
+// with its row of AT; role K reads its column back.
 // Part 1:  w0 = sum_m D[i][m] u(m,j,k), w1 = sum_m D[j][m] u(i,m,k), w2 = sum_m D[k][m] u(i,j,m),
 //          f = coeff * G w   (SURVEY.md App. A.9); f0 -> AT, f1 -> A, f2 stays in registers.
 // Part 2:  y(i,j,k) = sum_m D[m][i] f0(m,j,k) + D[m][j] f1(i,m,k) + D[m][k] f2(i,j,m).
@@ -118,27 +151,27 @@ __device__ __forceinline__ void line_transform(T* __restrict__ row, const DMat<T
 
 template <typename T, int N, typename Sync>
 __device__ __forceinline__ void cell_part1(const T (&u)[N], const typename Vec2<T>::type (&g)[N][3],
-                                           T* __restrict__ tiles, int p, int q,
+                                           T* __restrict__ tiles, const RoleOff& ro,
                                            const DMat<T, N>& Dm, T coeff, bool active, Sync sync,
                                            T (&f2)[N])
 {
-  constexpr int TILE = Tiles<N>::TILE;
+  constexpr int PS_A = Tiles<N>::PS_A, PS_T = Tiles<N>::PS_T;
   T* A = tiles;
-  T* AT = tiles + TILE;
+  T* AT = tiles + tile_a_elems<N>();
   if (active)
   {
 #pragma unroll
     for (int k = 0; k < N; ++k)
     {
-      A[(k * N + p) * N + q] = u[k];
-      AT[(k * N + q) * N + p] = u[k];
+      A[k * PS_A + ro.kA] = u[k];
+      AT[k * PS_T + ro.kT] = u[k];
     }
   }
   sync();
   if (active)
   {
-    line_transform<T, N, false>(A + (q * N + p) * N, Dm);  // u(p, ., q) -> w1(p, ., q)
-    line_transform<T, N, false>(AT + (q * N + p) * N, Dm); // u(., p, q) -> w0(., p, q)
+    line_transform<T, N, false>(A + ro.rA, Dm);  // u(i, ., k) -> w1(i, ., k)
+    line_transform<T, N, false>(AT + ro.rT, Dm); // u(., j, k) -> w0(., j, k)
   }
   sync();
   if (active)
@@ -149,29 +182,29 @@ __device__ __forceinline__ void cell_part1(const T (&u)[N], const typename Vec2<
       T w2 = 0;
 #pragma unroll
       for (int m = 0; m < N; ++m) w2 += Dm.d[k * N + m] * u[m];
-      const T w0 = AT[(k * N + q) * N + p];
-      const T w1 = A[(k * N + p) * N + q];
+      const T w0 = AT[k * PS_T + ro.kT];
+      const T w1 = A[k * PS_A + ro.kA];
       const T g00 = g[k][0].x, g01 = g[k][0].y, g02 = g[k][1].x;
       const T g11 = g[k][1].y, g12 = g[k][2].x, g22 = g[k][2].y;
-      AT[(k * N + q) * N + p] = coeff * (g00 * w0 + g01 * w1 + g02 * w2); // f0
-      A[(k * N + p) * N + q] = coeff * (g01 * w0 + g11 * w1 + g12 * w2);  // f1
+      AT[k * PS_T + ro.kT] = coeff * (g00 * w0 + g01 * w1 + g02 * w2); // f0
+      A[k * PS_A + ro.kA] = coeff * (g01 * w0 + g11 * w1 + g12 * w2);  // f1
       f2[k] = coeff * (g02 * w0 + g12 * w1 + g22 * w2);
     }
   }
 }
 
 template <typename T, int N, typename Sync>
-__device__ __forceinline__ void cell_part2(const T (&f2)[N], T* __restrict__ tiles, int p, int q,
+__device__ __forceinline__ void cell_part2(const T (&f2)[N], T* __restrict__ tiles, const RoleOff& ro,
                                            const DMat<T, N>& Dm, bool active, Sync sync, T (&yv)[N])
 {
-  constexpr int TILE = Tiles<N>::TILE;
+  constexpr int PS_A = Tiles<N>::PS_A, PS_T = Tiles<N>::PS_T;
   T* A = tiles;
-  T* AT = tiles + TILE;
+  T* AT = tiles + tile_a_elems<N>();
   sync(); // f0 / f1 visible
   if (active)
   {
-    line_transform<T, N, true>(A + (q * N + p) * N, Dm);  // f1(p, ., q) -> sum_m D[m][.] f1(p,m,q)
-    line_transform<T, N, true>(AT + (q * N + p) * N, Dm); // f0(., p, q) -> sum_m D[m][.] f0(m,p,q)
+    line_transform<T, N, true>(A + ro.rA, Dm);  // f1(i, ., k) -> sum_m D[m][.] f1(i,m,k)
+    line_transform<T, N, true>(AT + ro.rT, Dm); // f0(., j, k) -> sum_m D[m][.] f0(m,j,k)
   }
   sync();
   if (active)
@@ -179,7 +212,7 @@ __device__ __forceinline__ void cell_part2(const T (&f2)[N], T* __restrict__ til
 #pragma unroll
     for (int k = 0; k < N; ++k)
     {
-      T s = AT[(k * N + q) * N + p] + A[(k * N + p) * N + q];
+      T s = AT[k * PS_T + ro.kT] + A[k * PS_A + ro.kA];
 #pragma unroll
       for (int m = 0; m < N; ++m) s += Dm.d[m * N + k] * f2[m];
       yv[k] = s;
@@ -196,12 +229,12 @@ stiff_cell_kernel(const int32_t* __restrict__ cells, int ncl, const int32_t* __r
 {
   constexpr int N2 = N * N, ND = N2 * N;
   using V2 = typename Vec2<T>::type;
-  __shared__ __align__(16) T s_w[CPB][Tiles<N>::SLOT_ELEMS];
+  __shared__ __align__(16) T s_w[CPB][slot_elems<N>()];
   const int slot = threadIdx.x / SLOT, col = threadIdx.x % SLOT;
   const int ci = blockIdx.x * CPB + slot;
   const bool active = (col < N2) && (ci < ncl);
   const int64_t cell = active ? cells[ci] : 0;
-  const int i = active ? col / N : 0, j = active ? col % N : 0;
+  const RoleOff ro = role_offsets<N>(active ? col : 0);
   int32_t dof[N];
   T u[N], yv[N], f2[N];
   V2 g[N][3];
@@ -213,8 +246,8 @@ stiff_cell_kernel(const int32_t* __restrict__ cells, int ncl, const int32_t* __r
     yv[k] = 0;
   }
   if (active) load_G<T, N>(G6 + cell * (int64_t)(6 * ND), col, g);
-  cell_part1<T, N>(u, g, s_w[slot], i, j, Dm, coeff, active, BlockSync(), f2);
-  cell_part2<T, N>(f2, s_w[slot], i, j, Dm, active, BlockSync(), yv);
+  cell_part1<T, N>(u, g, s_w[slot], ro, Dm, coeff, active, BlockSync(), f2);
+  cell_part2<T, N>(f2, s_w[slot], ro, Dm, active, BlockSync(), yv);
   if (active)
   {
 #pragma unroll
@@ -247,14 +280,14 @@ template <typename T, int N, int SLOT, int W, int MINB>
 __global__ void __launch_bounds__(SLOT* W, MINB)
 stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
 {
-  constexpr int N2 = N * N, ND = N2 * N, NT = SLOT * W, U = 8, NDP = Tiles<N>::NDP;
+  constexpr int N2 = N * N, ND = N2 * N, NT = SLOT * W, U = 10, NDP = ndp_of<N>();
   using V2 = typename Vec2<T>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* xl = reinterpret_cast<T*>(smem_raw);
   T* yl = xl + a.nloc_pad;
   T* work = yl + a.nloc_pad;
   // 16-byte aligned for the vector copies below
-  const size_t meta_off = ((size_t)(2 * a.nloc_pad + W * Tiles<N>::SLOT_ELEMS) * sizeof(T) + 15) & ~(size_t)15;
+  const size_t meta_off = ((size_t)(2 * a.nloc_pad + W * slot_elems<N>()) * sizeof(T) + 15) & ~(size_t)15;
   uint16_t* sldm = reinterpret_cast<uint16_t*>(smem_raw + meta_off);
   int32_t* scell = reinterpret_cast<int32_t*>(sldm + (size_t)a.rounds_max * W * NDP);
   pdl_launch_dependents(); // the next colour may start staging; it waits before touching y
@@ -264,7 +297,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   const int tid = threadIdx.x;
   const int slot = tid / SLOT, col = tid % SLOT;
   const bool lane_ok = col < N2;
-  const int i = lane_ok ? col / N : 0, j = lane_ok ? col % N : 0;
+  const RoleOff ro = role_offsets<N>(lane_ok ? col : 0);
   const int r0 = __ldg(a.round_off + b), nr = __ldg(a.round_off + b + 1) - r0;
 
   // G of the first cell is requested before anything is staged
@@ -300,7 +333,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   }
   __syncthreads();
 
-  T* tiles = work + slot * Tiles<N>::SLOT_ELEMS;
+  T* tiles = work + slot * slot_elems<N>();
   for (int r = 0; r < nr; ++r)
   {
     const int cell = scell[r * W + slot];
@@ -315,16 +348,16 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
       u[k] = active ? xl[li[k]] : T(0);
       yv[k] = 0;
     }
-    if constexpr (SLOT <= 32) cell_part1<T, N>(u, g, tiles, i, j, Dm, a.coeff, active, WarpSync(), f2);
-    else cell_part1<T, N>(u, g, tiles, i, j, Dm, a.coeff, active, BlockSync(), f2);
+    if constexpr (SLOT <= 32) cell_part1<T, N>(u, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2);
+    else cell_part1<T, N>(u, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2);
     // G of this cell is consumed: request the next cell's G into the same registers so
     // that the loads fly during part 2 and the next gather
     {
       const int cn = r + 1 < nr ? scell[(r + 1) * W + slot] : -1;
       if (lane_ok && cn >= 0) load_G<T, N>(a.G6 + (int64_t)cn * (6 * ND), col, g);
     }
-    if constexpr (SLOT <= 32) cell_part2<T, N>(f2, tiles, i, j, Dm, active, WarpSync(), yv);
-    else cell_part2<T, N>(f2, tiles, i, j, Dm, active, BlockSync(), yv);
+    if constexpr (SLOT <= 32) cell_part2<T, N>(f2, tiles, ro, Dm, active, WarpSync(), yv);
+    else cell_part2<T, N>(f2, tiles, ro, Dm, active, BlockSync(), yv);
     if (active)
     {
 #pragma unroll
@@ -365,7 +398,12 @@ template <int N> struct Cfg;
 //                          SLOT  W  brick edge  cells/block (simple)  min CTAs/SM (brick)
 template <> struct Cfg<3> { static constexpr int SLOT = 16, W = 16, BE = 8, CPB = 16, MINB = 2; };
 template <> struct Cfg<4> { static constexpr int SLOT = 16, W = 8, BE = 4, CPB = 16, MINB = 4; };
-template <> struct Cfg<5> { static constexpr int SLOT = 32, W = 8, BE = 4, CPB = 8, MINB = 2; };
+#ifndef WFX_P4_W
+#define WFX_P4_W 8
+#define WFX_P4_BE 4
+#define WFX_P4_MINB 2
+#endif
+template <> struct Cfg<5> { static constexpr int SLOT = 32, W = WFX_P4_W, BE = WFX_P4_BE, CPB = 8, MINB = WFX_P4_MINB; };
 template <> struct Cfg<6> { static constexpr int SLOT = 64, W = 1, BE = 2, CPB = 4, MINB = 8; };
 template <> struct Cfg<7> { static constexpr int SLOT = 64, W = 1, BE = 2, CPB = 4, MINB = 5; };
 template <> struct Cfg<8> { static constexpr int SLOT = 64, W = 1, BE = 2, CPB = 2, MINB = 3; };
@@ -374,6 +412,19 @@ struct LaunchCfg
 {
   int SLOT, W, BE, CPB;
 };
+int slot_elems_rt(int N)
+{
+  switch (N)
+  {
+  case 3: return slot_elems<3>();
+  case 4: return slot_elems<4>();
+  case 5: return slot_elems<5>();
+  case 6: return slot_elems<6>();
+  case 7: return slot_elems<7>();
+  case 8: return slot_elems<8>();
+  }
+  return 2 * N * N * N;
+}
 LaunchCfg launch_cfg(int N)
 {
   switch (N)
@@ -624,7 +675,8 @@ extern "C" int wfx_stiffness_create(wfx_ctx* ctx, wfx_geom* geom, int64_t ndofs,
       const int ndp = (op->nd + 7) & ~7;
       auto meta_bytes = [&](int rounds) { return (size_t)rounds * lc.W * (ndp * 2 + 4); };
       const int rounds_guess = std::max(8, (lc.BE * lc.BE * lc.BE + lc.W - 1) / lc.W);
-      const size_t work = (size_t)lc.W * 2 * op->nd * esz + meta_bytes(rounds_guess) + 16;
+      const size_t tiles_bytes = (size_t)lc.W * slot_elems_rt(op->N) * esz;
+      const size_t work = tiles_bytes + meta_bytes(rounds_guess) + 16;
       const size_t avail = ctx->smem_optin > work + 1024 ? ctx->smem_optin - work - 1024 : 0;
       int nloc_cap = (int)std::min<size_t>(avail / (2 * esz), 65535);
       if (const char* e = std::getenv("WFX_NLOC_CAP")) nloc_cap = std::min(nloc_cap, std::atoi(e));
@@ -638,7 +690,7 @@ extern "C" int wfx_stiffness_create(wfx_ctx* ctx, wfx_geom* geom, int64_t ndofs,
       op->W = bp.W;
       op->nloc_pad = (bp.nloc_max + 1) & ~1;
       op->rounds_max = bp.rounds_max;
-      op->smem_bytes = ((((size_t)op->nloc_pad * 2 + (size_t)lc.W * 2 * op->nd) * esz + 15) & ~(size_t)15)
+      op->smem_bytes = (((size_t)op->nloc_pad * 2 * esz + tiles_bytes + 15) & ~(size_t)15)
                        + meta_bytes(bp.rounds_max);
       if (op->smem_bytes > ctx->smem_optin) fail("stiffness: batch needs %zu B shared memory", op->smem_bytes);
       op->d_dof_off.upload(bp.dof_off);
