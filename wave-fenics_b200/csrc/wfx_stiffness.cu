@@ -43,6 +43,38 @@ __device__ __forceinline__ float2 ld_stream(const float2* p)
   return r;
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// asynchronous global -> shared copy of one scalar (LDGSTS): no register staging, no stall at issue
+__device__ __forceinline__ void cp_async_scalar(double* dst_smem, const double* src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_scalar(float* dst_smem, const float* src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// one-shot TMA bulk copy global -> shared with mbarrier completion (bytes multiple of 16)
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+}
+
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -51,6 +83,27 @@ struct DMat
 {
   T d[N * N]; // D[q*N+i] = l_i'(x_q), [0,1,interior] ordering, clamped
 };
+
+// Optional phase timer (build with -DWFX_TIMING): lane 0 of every warp accumulates the
+// cycles spent between marks; no-op otherwise.
+#ifdef WFX_TIMING
+__device__ long long* g_wfx_timing = nullptr;
+struct PhaseTimer
+{
+  long long acc[12], last;
+  bool on;
+  __device__ void start(bool lane0) { on = lane0; for (int q = 0; q < 12; ++q) acc[q] = 0; last = clock64(); }
+  __device__ __forceinline__ void mark(int ph) { if (on) { long long t = clock64(); acc[ph] += t - last; last = t; } }
+  __device__ void flush(int gwarp) { if (on && g_wfx_timing) for (int q = 0; q < 12; ++q) g_wfx_timing[(long long)gwarp * 12 + q] = acc[q]; }
+};
+#else
+struct PhaseTimer
+{
+  __device__ __forceinline__ void start(bool) {}
+  __device__ __forceinline__ void mark(int) {}
+  __device__ __forceinline__ void flush(int) {}
+};
+#endif
 
 struct WarpSync
 {
@@ -153,7 +206,7 @@ template <typename T, int N, typename Sync>
 __device__ __forceinline__ void cell_part1(const T (&u)[N], const typename Vec2<T>::type (&g)[N][3],
                                            T* __restrict__ tiles, const RoleOff& ro,
                                            const DMat<T, N>& Dm, T coeff, bool active, Sync sync,
-                                           T (&f2)[N])
+                                           T (&f2)[N], PhaseTimer& tm)
 {
   constexpr int PS_A = Tiles<N>::PS_A, PS_T = Tiles<N>::PS_T;
   T* A = tiles;
@@ -168,12 +221,14 @@ __device__ __forceinline__ void cell_part1(const T (&u)[N], const typename Vec2<
     }
   }
   sync();
+  tm.mark(1);
   if (active)
   {
     line_transform<T, N, false>(A + ro.rA, Dm);  // u(i, ., k) -> w1(i, ., k)
     line_transform<T, N, false>(AT + ro.rT, Dm); // u(., j, k) -> w0(., j, k)
   }
   sync();
+  tm.mark(2);
   if (active)
   {
 #pragma unroll
@@ -191,11 +246,13 @@ __device__ __forceinline__ void cell_part1(const T (&u)[N], const typename Vec2<
       f2[k] = coeff * (g02 * w0 + g12 * w1 + g22 * w2);
     }
   }
+  tm.mark(3);
 }
 
 template <typename T, int N, typename Sync>
 __device__ __forceinline__ void cell_part2(const T (&f2)[N], T* __restrict__ tiles, const RoleOff& ro,
-                                           const DMat<T, N>& Dm, bool active, Sync sync, T (&yv)[N])
+                                           const DMat<T, N>& Dm, bool active, Sync sync, T (&yv)[N],
+                                           PhaseTimer& tm)
 {
   constexpr int PS_A = Tiles<N>::PS_A, PS_T = Tiles<N>::PS_T;
   T* A = tiles;
@@ -207,6 +264,7 @@ __device__ __forceinline__ void cell_part2(const T (&f2)[N], T* __restrict__ til
     line_transform<T, N, true>(AT + ro.rT, Dm); // f0(., j, k) -> sum_m D[m][.] f0(m,j,k)
   }
   sync();
+  tm.mark(5);
   if (active)
   {
 #pragma unroll
@@ -246,8 +304,10 @@ stiff_cell_kernel(const int32_t* __restrict__ cells, int ncl, const int32_t* __r
     yv[k] = 0;
   }
   if (active) load_G<T, N>(G6 + cell * (int64_t)(6 * ND), col, g);
-  cell_part1<T, N>(u, g, s_w[slot], ro, Dm, coeff, active, BlockSync(), f2);
-  cell_part2<T, N>(f2, s_w[slot], ro, Dm, active, BlockSync(), yv);
+  PhaseTimer tm;
+  tm.start(false);
+  cell_part1<T, N>(u, g, s_w[slot], ro, Dm, coeff, active, BlockSync(), f2, tm);
+  cell_part2<T, N>(f2, s_w[slot], ro, Dm, active, BlockSync(), yv, tm);
   if (active)
   {
 #pragma unroll
@@ -274,23 +334,30 @@ struct BrickArgs
   int rounds_max; // capacity (rounds) of the shared local-dofmap staging area
 };
 
-// Shared memory of one CTA:  xl[nloc_pad] | yl[nloc_pad] | tiles[W][2][N^3] | sldm[rounds_max*W*NDP] (u16)
-//                            | scell[rounds_max*W] (i32)
+// Shared memory of one CTA:  xl[nloc_pad] | yl[nloc_pad] | tiles[W][slot_elems] | sldm[rounds_max*W*NDP] (u16)
+//                            | scell[rounds_max*W] (i32) | mbarrier (u64)
 template <typename T, int N, int SLOT, int W, int MINB>
 __global__ void __launch_bounds__(SLOT* W, MINB)
 stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
 {
-  constexpr int N2 = N * N, ND = N2 * N, NT = SLOT * W, U = 10, NDP = ndp_of<N>();
+  // U: batch dofs handled per thread in one pass of the staging / write-back loops; all their
+  // loads are issued before the first is consumed (two dependent memory round trips per pass)
+  constexpr int N2 = N * N, ND = N2 * N, NT = SLOT * W, NDP = ndp_of<N>();
+  constexpr int U = 20;
   using V2 = typename Vec2<T>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* xl = reinterpret_cast<T*>(smem_raw);
   T* yl = xl + a.nloc_pad;
   T* work = yl + a.nloc_pad;
-  // 16-byte aligned for the vector copies below
+  // 16-byte aligned for the bulk copy below
   const size_t meta_off = ((size_t)(2 * a.nloc_pad + W * slot_elems<N>()) * sizeof(T) + 15) & ~(size_t)15;
   uint16_t* sldm = reinterpret_cast<uint16_t*>(smem_raw + meta_off);
   int32_t* scell = reinterpret_cast<int32_t*>(sldm + (size_t)a.rounds_max * W * NDP);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(
+      smem_raw + ((meta_off + (size_t)a.rounds_max * W * (NDP * 2 + 4) + 7) & ~(size_t)7));
   pdl_launch_dependents(); // the next colour may start staging; it waits before touching y
+  PhaseTimer tm;
+  tm.start(threadIdx.x % 32 == 0);
   const int b = batch0 + blockIdx.x;
   const int64_t d0 = __ldg(a.dof_off + b);
   const int nloc = (int)(__ldg(a.dof_off + b + 1) - d0);
@@ -300,38 +367,33 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   const RoleOff ro = role_offsets<N>(lane_ok ? col : 0);
   const int r0 = __ldg(a.round_off + b), nr = __ldg(a.round_off + b + 1) - r0;
 
-  // G of the first cell is requested before anything is staged
+  // the batch's local dofmap: one TMA bulk copy, waited for after the dofs are staged
+  if (tid == 0 && nr > 0) bulk_copy_g2s(sldm, a.ldm + (int64_t)r0 * W * NDP, (uint32_t)(nr * W * NDP * 2), bar);
+  // G of the first cell is requested before anything else is staged
   V2 g[N][3];
   {
     const int c0 = nr > 0 ? __ldg(a.slot_cell + (int64_t)r0 * W + slot) : -1;
     if (lane_ok && c0 >= 0) load_G<T, N>(a.G6 + (int64_t)c0 * (6 * ND), col, g);
   }
-  // stage the batch's local dofmap (16-byte copies) and cell list
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(a.ldm + (int64_t)r0 * W * NDP);
-    uint4* dst = reinterpret_cast<uint4*>(sldm);
-    const int nv = nr * W * (NDP / 8);
-    for (int v = tid; v < nv; v += NT) dst[v] = __ldg(src + v);
-    for (int v = tid; v < nr * W; v += NT) scell[v] = __ldg(a.slot_cell + (int64_t)r0 * W + v);
-  }
-  // stage the batch's dofs: U independent index loads, then U independent gathers
+  for (int v = tid; v < nr * W; v += NT) scell[v] = __ldg(a.slot_cell + (int64_t)r0 * W + v);
+  // stage the batch's dofs: U independent index loads, then U asynchronous gathers into xl
   for (int base = tid; base < nloc; base += NT * U)
   {
     uint32_t e[U];
-    T v[U];
 #pragma unroll
     for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? __ldg(a.bdofs + d0 + base + q * NT) : 0u;
-#pragma unroll
-    for (int q = 0; q < U; ++q) v[q] = base + q * NT < nloc ? a.x[e[q] & BD_MASK] : T(0);
 #pragma unroll
     for (int q = 0; q < U; ++q)
       if (base + q * NT < nloc)
       {
-        xl[base + q * NT] = v[q];
+        cp_async_scalar(xl + base + q * NT, a.x + (e[q] & BD_MASK));
         yl[base + q * NT] = T(0);
       }
   }
+  cp_async_wait_all();
+  if (nr > 0) mbar_wait(bar, 0);
   __syncthreads();
+  tm.mark(0);
 
   T* tiles = work + slot * slot_elems<N>();
   for (int r = 0; r < nr; ++r)
@@ -348,30 +410,39 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
       u[k] = active ? xl[li[k]] : T(0);
       yv[k] = 0;
     }
-    if constexpr (SLOT <= 32) cell_part1<T, N>(u, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2);
-    else cell_part1<T, N>(u, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2);
+    if constexpr (SLOT <= 32) cell_part1<T, N>(u, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2, tm);
+    else cell_part1<T, N>(u, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2, tm);
     // G of this cell is consumed: request the next cell's G into the same registers so
     // that the loads fly during part 2 and the next gather
     {
       const int cn = r + 1 < nr ? scell[(r + 1) * W + slot] : -1;
       if (lane_ok && cn >= 0) load_G<T, N>(a.G6 + (int64_t)cn * (6 * ND), col, g);
     }
-    if constexpr (SLOT <= 32) cell_part2<T, N>(f2, tiles, ro, Dm, active, WarpSync(), yv);
-    else cell_part2<T, N>(f2, tiles, ro, Dm, active, BlockSync(), yv);
+    tm.mark(4);
+    if constexpr (SLOT <= 32) cell_part2<T, N>(f2, tiles, ro, Dm, active, WarpSync(), yv, tm);
+    else cell_part2<T, N>(f2, tiles, ro, Dm, active, BlockSync(), yv, tm);
     if (active)
     {
 #pragma unroll
       for (int k = 0; k < N; ++k) yl[li[k]] += yv[k]; // cells of one round share no dof
     }
+    tm.mark(6);
     __syncthreads();
+    tm.mark(7);
   }
-  pdl_wait(); // earlier colours have finished their writes to y
+  // write-back: every batch dof exactly once.  Index loads first, then (after the earlier
+  // colours have finished) all y / scale loads of the pass, then the stores.
   for (int base = tid; base < nloc; base += NT * U)
   {
     uint32_t e[U];
     T v[U], sc[U];
 #pragma unroll
     for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? __ldg(a.bdofs + d0 + base + q * NT) : BD_FIRST;
+    if (base == tid)
+    {
+      pdl_wait(); // earlier colours have finished their writes to y
+      tm.mark(8);
+    }
 #pragma unroll
     for (int q = 0; q < U; ++q)
     {
@@ -384,6 +455,9 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
     for (int q = 0; q < U; ++q)
       if (base + q * NT < nloc) a.y[e[q] & BD_MASK] = (v[q] + yl[base + q * NT]) * sc[q];
   }
+  if (nloc <= tid) pdl_wait(); // threads without a batch dof still honour the dependency
+  tm.mark(9);
+  tm.flush((batch0 + blockIdx.x) * W + slot);
 }
 
 template <typename T>
@@ -630,6 +704,16 @@ void build_tensor_dofmap(int P, int64_t ncells, int64_t ndofs, const int32_t* do
 }
 } // namespace wfx
 
+#ifdef WFX_TIMING
+// debug builds only: device buffer [nbatches*W][12] of int64 phase cycle counts
+extern "C" int wfx_debug_set_timing_buffer(void* buf)
+{
+  WFX_API_BEGIN
+  WFX_CUDA(cudaMemcpyToSymbol(g_wfx_timing, &buf, sizeof(buf)));
+  WFX_API_END
+}
+#endif
+
 extern "C" int wfx_stiffness_create(wfx_ctx* ctx, wfx_geom* geom, int64_t ndofs,
                                     const int32_t* dofmap_host, double c0, int flags,
                                     wfx_stiffness** out)
@@ -676,7 +760,7 @@ extern "C" int wfx_stiffness_create(wfx_ctx* ctx, wfx_geom* geom, int64_t ndofs,
       auto meta_bytes = [&](int rounds) { return (size_t)rounds * lc.W * (ndp * 2 + 4); };
       const int rounds_guess = std::max(8, (lc.BE * lc.BE * lc.BE + lc.W - 1) / lc.W);
       const size_t tiles_bytes = (size_t)lc.W * slot_elems_rt(op->N) * esz;
-      const size_t work = tiles_bytes + meta_bytes(rounds_guess) + 16;
+      const size_t work = tiles_bytes + meta_bytes(rounds_guess) + 32;
       const size_t avail = ctx->smem_optin > work + 1024 ? ctx->smem_optin - work - 1024 : 0;
       int nloc_cap = (int)std::min<size_t>(avail / (2 * esz), 65535);
       if (const char* e = std::getenv("WFX_NLOC_CAP")) nloc_cap = std::min(nloc_cap, std::atoi(e));
@@ -691,7 +775,7 @@ extern "C" int wfx_stiffness_create(wfx_ctx* ctx, wfx_geom* geom, int64_t ndofs,
       op->nloc_pad = (bp.nloc_max + 1) & ~1;
       op->rounds_max = bp.rounds_max;
       op->smem_bytes = (((size_t)op->nloc_pad * 2 * esz + tiles_bytes + 15) & ~(size_t)15)
-                       + meta_bytes(bp.rounds_max);
+                       + meta_bytes(bp.rounds_max) + 16; // + mbarrier
       if (op->smem_bytes > ctx->smem_optin) fail("stiffness: batch needs %zu B shared memory", op->smem_bytes);
       op->d_dof_off.upload(bp.dof_off);
       op->d_bdofs.upload(bp.bdofs);
