@@ -153,9 +153,9 @@ def run_b200(args):
     stiff = wfx.StiffnessOperator(mesh, P, ctx=ctx, geometry=geo)
     mass = wfx.MassOperator(mesh, P, ctx=ctx, geometry=geo)
     info = stiff.info()
-    minv_ptr = mass.inverse_diagonal_ptr()
     if halo is not None:
-        minv_ptr = partition.assembled_inverse_mass(mass, halo)
+        mass.assemble(halo)
+    minv_ptr = mass.inverse_diagonal_ptr()
 
     dev = torch.device("cuda", local_rank)
     g = torch.Generator(device=dev).manual_seed(42 + rank)
@@ -170,7 +170,7 @@ def run_b200(args):
         else:
             stiff.apply(x, y, beta=0)
             halo.update_rev_fwd(y)
-            partition.scale_inplace(y, minv_ptr)
+            mass.apply_inverse(y, y)
 
     def sync_all():
         torch.cuda.synchronize()

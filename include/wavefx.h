@@ -155,6 +155,13 @@ int wfx_mass_apply_host(wfx_mass* op, const void* x_host, void* y_host, int beta
 /* device pointers owned by the operator: m = M.1 (LinearGLL.hpp:102-110) and 1/m */
 int wfx_mass_diagonal(wfx_mass* op, const void** m_dev);
 int wfx_mass_inverse_diagonal(wfx_mass* op, const void** minv_dev);
+/* y = x ./ m  (the b/m of common/LinearGLL.hpp:188-191 with the reciprocal precomputed);
+ * x and y may alias. */
+int wfx_mass_apply_inverse(wfx_mass* op, const void* x_dev, void* y_dev, void* stream);
+/* Distributed meshes: sum the per-rank partial diagonals over the ranks sharing a dof
+ * (m.scatter_rev(add), LinearGLL.hpp:110, followed by a forward update so that ghost copies
+ * hold the assembled value too) and recompute 1/m.  Call once after wfx_mass_create. */
+int wfx_mass_assemble(wfx_mass* op, wfx_halo* halo_f64);
 int wfx_mass_destroy(wfx_mass* op);
 
 /* ---- dofmap gather / scatter-add: gather<T>, scatter<T> (common/cuda/scatter.cu:47-65) */

@@ -310,3 +310,20 @@ def test_gather_and_scatter_add(wfx, torch):
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), want)
     capi.call("wfx_scatter_plan_destroy", plan)
+
+
+# ---- e: multi-GPU (NCCL halo) -- runs when the box has at least two GPUs ---------------------------
+def test_multi_gpu_halo_and_rk4(torch):
+    import os
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 8 if n >= 8 else (4 if n >= 4 else 2)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "mgpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "mgpu_check ok" in r.stdout

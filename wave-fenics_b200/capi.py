@@ -65,6 +65,8 @@ _SIG = {
     "wfx_mass_create": [_vp, _vp, C.c_int64, _c_i32p, _vpp],
     "wfx_mass_apply": [_vp, _vp, _vp, C.c_int, _vp],
     "wfx_mass_apply_host": [_vp, _vp, _vp, C.c_int],
+    "wfx_mass_apply_inverse": [_vp, _vp, _vp, _vp],
+    "wfx_mass_assemble": [_vp, _vp],
     "wfx_mass_diagonal": [_vp, _vpp],
     "wfx_mass_inverse_diagonal": [_vp, _vpp],
     "wfx_mass_destroy": [_vp],

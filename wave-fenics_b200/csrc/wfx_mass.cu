@@ -252,6 +252,41 @@ extern "C" int wfx_mass_apply_host(wfx_mass* op, const void* x_host, void* y_hos
   WFX_API_END
 }
 
+extern "C" int wfx_mass_apply_inverse(wfx_mass* op, const void* x, void* y, void* stream)
+{
+  WFX_API_BEGIN
+  if (!op) fail("mass operator is NULL");
+  if (op->ndofs == 0) return 0;
+  if (!x || !y) fail("mass: NULL vector");
+  ScopedDevice sd(op->ctx->device);
+  const unsigned grid = (unsigned)((op->ndofs + 255) / 256);
+  if (op->dtype == WFX_F64)
+    diag_apply_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        op->ndofs, (const double*)op->d_minv, (const double*)x, (double*)y, 0);
+  else
+    diag_apply_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        op->ndofs, (const float*)op->d_minv, (const float*)x, (float*)y, 0);
+  WFX_CUDA(cudaGetLastError());
+  WFX_API_END
+}
+
+extern "C" int wfx_mass_assemble(wfx_mass* op, wfx_halo* halo)
+{
+  WFX_API_BEGIN
+  if (!op || !halo) fail("NULL argument");
+  if (op->ndofs == 0) return 0;
+  ScopedDevice sd(op->ctx->device);
+  if (wfx_halo_update_rev_fwd(halo, op->d_m64.p, nullptr)) fail("%s", wfx_last_error());
+  const unsigned grid = (unsigned)((op->ndofs + 255) / 256);
+  if (op->dtype == WFX_F64)
+    mass_finish_kernel<double><<<grid, 256>>>(op->ndofs, op->d_m64.p, nullptr, (double*)op->d_minv);
+  else
+    mass_finish_kernel<float><<<grid, 256>>>(op->ndofs, op->d_m64.p, (float*)op->d_m, (float*)op->d_minv);
+  WFX_CUDA(cudaGetLastError());
+  WFX_CUDA(cudaDeviceSynchronize());
+  WFX_API_END
+}
+
 extern "C" int wfx_mass_diagonal(wfx_mass* op, const void** m)
 {
   WFX_API_BEGIN

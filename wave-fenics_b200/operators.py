@@ -200,6 +200,16 @@ class MassOperator(_Operator):
             capi.call("wfx_mass_apply_host", self.handle, C.c_void_p(x.ctypes.data),
                       C.c_void_p(y.ctypes.data), int(beta))
 
+    def apply_inverse(self, x, y):
+        """y = x ./ m (x and y may be the same tensor)."""
+        self._check(x, y)
+        capi.call("wfx_mass_apply_inverse", self.handle, C.c_void_p(x.data_ptr()),
+                  C.c_void_p(y.data_ptr()), _stream_ptr())
+
+    def assemble(self, halo):
+        """Distributed meshes: sum the diagonal over the ranks sharing a dof (fp64 halo)."""
+        capi.call("wfx_mass_assemble", self.handle, halo.handle)
+
     def _ptr(self, name):
         p = C.c_void_p()
         capi.call(name, self.handle, C.byref(p))
@@ -291,6 +301,8 @@ class LinearGLLOpt:
                                           mode=stiffness_mode)                           # :120
         self.bnd_op = BoundaryOperator(mesh, self.k_, dtype, self.ctx)                   # :113-115
         self.halo = halo
+        if halo is not None:
+            self.mass_op.assemble(halo)                                                  # :110
         self.handle = C.c_void_p()
         capi.call("wfx_wave_create", self.ctx.handle, self.stiff_op.handle, self.mass_op.handle,
                   self.bnd_op.handle, halo.handle if halo is not None else None, int(mesh.size_local),
