@@ -219,11 +219,43 @@ def run_b200(args):
         e2e = {"value": mesh.ndofs / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": mesh.ndofs * 8,
                "d2h_bytes_per_step": mesh.ndofs * 8, "ms_per_step": dt * 1e3}
 
+    # second half of the BASELINE metric: one full RK4 step (4 x stiffness + boundary term +
+    # halo + fused stage update) of the wave model on the same mesh, through wfx_wave_rk4
+    rk4 = None
+    if not args.no_rk4:
+        del x, y
+        eqn = wfx.LinearGLLOpt(mesh, None, P, 1500.0, 0.5e6, 6e4, ctx=ctx, halo=halo)
+        eqn.init()
+        dt_w = wfx.cfl_timestep(mesh.h_min, 1500.0, P, 0.5e6)
+        eqn.rk4(0.0, 1.0, dt_w, max_steps=2)
+        sync_all()
+        k_rk = max(3, min(args.steps, 10))
+        ev0.record()
+        eqn.rk4(2 * dt_w, 1.0, dt_w, max_steps=k_rk)
+        ev1.record()
+        sync_all()
+        ms_rk = ev0.elapsed_time(ev1) / k_rk
+        if world > 1:
+            t = torch.tensor([ms_rk], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_rk = float(t.item())
+        u_chk, _ = eqn.get_state()
+        assert np.isfinite(u_chk).all() and np.abs(u_chk).max() > 0
+        # algorithmic bytes per step: 4 stages x (G + dofmap + read un +
+        # write b) + the fused stage updates (10 + 11 + 11 + 7 vector passes)
+        s8 = 8
+        b_step = 4 * (info["num_cells"] * info["num_dofs"] * (6 * s8 + 4) + mesh.ndofs * 2 * s8) + 39 * mesh.ndofs * s8
+        rk4 = {"ms_per_step": ms_rk, "steps": k_rk, "dofs_global": int(ndofs_global),
+               "gdof_steps_per_s": ndofs_global / (ms_rk * 1e-3) / 1e9,
+               "bytes_per_step_per_gpu": b_step, "achieved_gbs_per_gpu": b_step / (ms_rk * 1e-3) / 1e9}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     peak, peak_src = measured_peak()
+    if rk4:
+        rk4["frac_of_hbm_peak"] = rk4["achieved_gbs_per_gpu"] / peak
     # dominant kernel = stiff_brick_kernel: the step is its `nlaunches` colour launches, so the
     # kernel's average launch duration is ms / nlaunches and its algorithmic bytes per launch are
     # bytes / nlaunches; achieved = bytes per step / step time.
@@ -254,7 +286,7 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "stiff_brick_kernel",
                          "bytes_per_step": info["bytes"], "launches_per_step": info["nlaunches"]},
-            "cpu_baseline": cpu}
+            "cpu_baseline": cpu, "rk4": rk4}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -271,6 +303,7 @@ def main():
     ap.add_argument("--perturb", type=float, default=0.15)
     ap.add_argument("--ref-cells", type=int, default=48, help="CPU sample mesh (cells per axis)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rk4", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

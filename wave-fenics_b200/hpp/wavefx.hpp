@@ -1,0 +1,251 @@
+// wavefx.hpp -- header-only C++17 wrappers over the C ABI (include/wavefx.h) with the call
+// shape of the reference classes, so that host code written against
+//   common/operators.hpp   MassOperatorCPU<T>(V, degree), StiffnessOperator<T>(V, degree, params),
+//                          void operator()(const Vector& x, Vector& y)   ==>  y += A x
+//   common/LinearGLL.hpp   LinearGLLOpt(mesh, meshtags, degree, c0, f0, p0), init(), rk4(t0, tf, dt)
+// can switch to the B200 path by changing the include and the type of `V`.
+//
+// The reference pulls everything it needs out of a dolfinx::fem::FunctionSpace.  DOLFINx is not
+// a dependency here: `wavefx::SpaceView` carries the same arrays as plain pointers, and
+// INTEGRATION.md shows the six-line adapter that fills it from a FunctionSpace.
+// Vectors are any type with data() and size() over contiguous T (std::vector<T>,
+// dolfinx::la::Vector<T>::mutable_array(), xtl::span<T>) holding HOST memory in DOLFINx layout
+// [owned | ghosts]; the *_device overloads take raw device pointers and a cudaStream_t.
+// Errors become std::runtime_error like the reference's CUDA classes
+// (common/cuda/array.hpp:15-17).
+#pragma once
+
+#include "wavefx.h"
+
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+namespace wavefx
+{
+inline void check(int status)
+{
+  if (status != 0) throw std::runtime_error(std::string("wavefx: ") + wfx_last_error());
+}
+
+template <typename T>
+constexpr int dtype_of()
+{
+  static_assert(std::is_same_v<T, double> || std::is_same_v<T, float>, "T must be double or float");
+  return std::is_same_v<T, double> ? WFX_F64 : WFX_F32;
+}
+
+// What the operators read from V (fem::FunctionSpace) and its mesh.
+struct SpaceView
+{
+  int degree = 0;
+  std::int64_t ncells = 0;               // mesh->topology().index_map(tdim)->size_local()
+  std::int64_t npoints = 0;              // geometry.x().size() / 3
+  const double* x = nullptr;             // geometry.x().data()
+  const std::int32_t* xdofs = nullptr;   // geometry.dofmap().array().data()  [ncells][8]
+  std::int64_t ndofs = 0;                // index_map->size_local() + num_ghosts()
+  std::int64_t size_local = 0;           // index_map->size_local()
+  const std::int32_t* dofmap = nullptr;  // V->dofmap()->list().array().data()  [ncells][(P+1)^3]
+  // exterior facets with tags (the MeshTags handed to create_form, LinearGLL.hpp:113-115)
+  std::int64_t nfacets = 0;
+  const std::int32_t* facet_cell = nullptr;
+  const std::int32_t* facet_local = nullptr;
+  const std::int32_t* facet_tag = nullptr;
+};
+
+class Context
+{
+public:
+  explicit Context(int device = 0) { check(wfx_ctx_create(device, &_h)); }
+  ~Context() { wfx_ctx_destroy(_h); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  wfx_ctx* get() const { return _h; }
+  void synchronize() const { check(wfx_ctx_sync(_h)); }
+
+private:
+  wfx_ctx* _h = nullptr;
+};
+
+// precompute_geometric_data(mesh, p) (common/precomputation.hpp:18-110)
+template <typename T>
+class Geometry
+{
+public:
+  Geometry(std::shared_ptr<Context> ctx, const SpaceView& V) : _ctx(std::move(ctx))
+  {
+    check(wfx_geometry_create(_ctx->get(), V.degree, dtype_of<T>(), V.ncells, V.npoints, V.x, V.xdofs, &_h));
+  }
+  ~Geometry() { wfx_geometry_destroy(_h); }
+  Geometry(const Geometry&) = delete;
+  Geometry& operator=(const Geometry&) = delete;
+  wfx_geom* get() const { return _h; }
+  const std::shared_ptr<Context>& context() const { return _ctx; }
+  // (G [ncells][nq][3][3], detJ [ncells][nq]) in the reference layout
+  void get(std::vector<double>& G, std::vector<double>& detJ, std::int64_t ncells, int nq) const
+  {
+    G.resize((std::size_t)ncells * nq * 9);
+    detJ.resize((std::size_t)ncells * nq);
+    check(wfx_geometry_get(_h, G.data(), detJ.data()));
+  }
+
+private:
+  std::shared_ptr<Context> _ctx;
+  wfx_geom* _h = nullptr;
+};
+
+template <typename T>
+class StiffnessOperator
+{
+public:
+  // `params` is accepted and -- exactly like the reference (common/operators.hpp:113-115) --
+  // not used for the speed of sound: c0 = 1500 is hard-coded there.
+  StiffnessOperator(std::shared_ptr<Geometry<T>> geom, const SpaceView& V, int bdegree,
+                    std::map<std::string, double>& params)
+      : _geom(std::move(geom)), _ndofs(V.ndofs), _params(params)
+  {
+    if (bdegree != V.degree) throw std::runtime_error("wavefx: degree mismatch");
+    check(wfx_stiffness_create(_geom->context()->get(), _geom->get(), V.ndofs, V.dofmap, 1500.0,
+                               WFX_STIFF_AUTO, &_h));
+  }
+  ~StiffnessOperator() { wfx_stiffness_destroy(_h); }
+  StiffnessOperator(const StiffnessOperator&) = delete;
+  StiffnessOperator& operator=(const StiffnessOperator&) = delete;
+
+  // y += A x on host vectors (the reference functor, operators.hpp:182-200)
+  template <typename VecIn, typename VecOut>
+  void operator()(const VecIn& x, VecOut& y)
+  {
+    if ((std::int64_t)x.size() != _ndofs || (std::int64_t)y.size() != _ndofs)
+      throw std::runtime_error("wavefx: vector size does not match the function space");
+    check(wfx_stiffness_apply_host(_h, x.data(), y.data(), 1));
+  }
+  // device pointers, asynchronous on `stream`
+  void apply_device(const T* x, T* y, int beta = 1, void* stream = nullptr)
+  {
+    check(wfx_stiffness_apply(_h, x, y, beta, stream));
+  }
+  void apply_scaled_device(const T* x, const T* scale, T* y, void* stream = nullptr)
+  {
+    check(wfx_stiffness_apply_scaled(_h, x, scale, y, stream));
+  }
+  std::size_t num_cells() const { return (std::size_t)info().ncells; }
+  std::size_t num_dofs() const { return (std::size_t)info().nd; }
+  double flops() const { return info().flops; }
+  wfx_stiffness* get() const { return _h; }
+
+private:
+  struct Info
+  {
+    std::int64_t ncells, ndofs;
+    int nd, ncol, nl;
+    double flops, bytes;
+  };
+  Info info() const
+  {
+    Info i{};
+    check(wfx_stiffness_info(_h, &i.ncells, &i.nd, &i.ndofs, &i.flops, &i.bytes, &i.ncol, &i.nl));
+    return i;
+  }
+  std::shared_ptr<Geometry<T>> _geom;
+  std::int64_t _ndofs;
+  std::map<std::string, double> _params;
+  wfx_stiffness* _h = nullptr;
+};
+
+// MassOperatorCPU<T> (common/operators.hpp:43-109); LinearGLL.hpp:63 spells it MassOperator.
+template <typename T>
+class MassOperator
+{
+public:
+  MassOperator(std::shared_ptr<Geometry<T>> geom, const SpaceView& V, int bdegree)
+      : _geom(std::move(geom)), _ndofs(V.ndofs)
+  {
+    if (bdegree != V.degree) throw std::runtime_error("wavefx: degree mismatch");
+    check(wfx_mass_create(_geom->context()->get(), _geom->get(), V.ndofs, V.dofmap, &_h));
+  }
+  ~MassOperator() { wfx_mass_destroy(_h); }
+  MassOperator(const MassOperator&) = delete;
+  MassOperator& operator=(const MassOperator&) = delete;
+  template <typename VecIn, typename VecOut>
+  void operator()(const VecIn& x, VecOut& y)
+  {
+    if ((std::int64_t)x.size() != _ndofs || (std::int64_t)y.size() != _ndofs)
+      throw std::runtime_error("wavefx: vector size does not match the function space");
+    check(wfx_mass_apply_host(_h, x.data(), y.data(), 1));
+  }
+  void apply_device(const T* x, T* y, int beta = 1, void* stream = nullptr) { check(wfx_mass_apply(_h, x, y, beta, stream)); }
+  const T* inverse_diagonal_device() const
+  {
+    const void* p = nullptr;
+    check(wfx_mass_inverse_diagonal(_h, &p));
+    return static_cast<const T*>(p);
+  }
+  wfx_mass* get() const { return _h; }
+
+private:
+  std::shared_ptr<Geometry<T>> _geom;
+  std::int64_t _ndofs;
+  wfx_mass* _h = nullptr;
+};
+template <typename T>
+using MassOperatorCPU = MassOperator<T>;
+
+// The wave model and its RK4 driver (common/LinearGLL.hpp:37-287), fp64 like the reference.
+class LinearGLLOpt
+{
+public:
+  LinearGLLOpt(std::shared_ptr<Context> ctx, const SpaceView& V, int& degreeOfBasis, double& speedOfSound,
+               double& sourceFrequency, double& pressureAmplitude)
+      : _ctx(std::move(ctx)), _ndofs(V.ndofs)
+  {
+    _geom = std::make_shared<Geometry<double>>(_ctx, V);
+    mass_op = std::make_shared<MassOperator<double>>(_geom, V, degreeOfBasis);                 // :105
+    std::map<std::string, double> params{{"c0", speedOfSound}};
+    stiff_op = std::make_shared<StiffnessOperator<double>>(_geom, V, degreeOfBasis, params);    // :120
+    check(wfx_boundary_create(_ctx->get(), V.degree, WFX_F64, V.nfacets, V.facet_cell, V.facet_local,
+                              V.facet_tag, V.npoints, V.x, V.xdofs, V.ndofs, V.dofmap, &_bnd));  // :113-115
+    check(wfx_wave_create(_ctx->get(), stiff_op->get(), mass_op->get(), _bnd, nullptr, V.size_local,
+                          speedOfSound, sourceFrequency, pressureAmplitude, &_wave));
+  }
+  ~LinearGLLOpt()
+  {
+    wfx_wave_destroy(_wave);
+    wfx_boundary_destroy(_bnd);
+  }
+  LinearGLLOpt(const LinearGLLOpt&) = delete;
+  LinearGLLOpt& operator=(const LinearGLLOpt&) = delete;
+
+  void init() { check(wfx_wave_init(_wave)); }                                                  // :131-134
+  // rk4(startTime, finalTime, timeStep) (:198-287); returns the number of steps taken
+  std::int64_t rk4(double& startTime, double& finalTime, double& timeStep)
+  {
+    std::int64_t steps = 0;
+    double t_end = 0;
+    check(wfx_wave_rk4(_wave, startTime, finalTime, timeStep, 0, &steps, &t_end, nullptr));
+    _ctx->synchronize();
+    return steps;
+  }
+  // u_n, v_n after the solve (:282-285), host copies
+  void solution(std::vector<double>& u_n, std::vector<double>& v_n) const
+  {
+    u_n.resize((std::size_t)_ndofs);
+    v_n.resize((std::size_t)_ndofs);
+    check(wfx_wave_get_state(_wave, u_n.data(), v_n.data()));
+  }
+
+  std::shared_ptr<MassOperator<double>> mass_op;
+  std::shared_ptr<StiffnessOperator<double>> stiff_op;
+
+private:
+  std::shared_ptr<Context> _ctx;
+  std::shared_ptr<Geometry<double>> _geom;
+  std::int64_t _ndofs;
+  wfx_boundary* _bnd = nullptr;
+  wfx_wave* _wave = nullptr;
+};
+} // namespace wavefx
