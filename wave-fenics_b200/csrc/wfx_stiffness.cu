@@ -18,6 +18,7 @@
 #include "wfx_internal.h"
 #include "wfx_plan.h"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -460,6 +461,209 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   tm.flush((batch0 + blockIdx.x) * W + slot);
 }
 
+// ---- product kernel, persistent form: ONE cooperative launch per apply ---------------------
+// Every CTA walks the colour-sorted batch list with stride gridDim.x.  What the multi-launch
+// kernel pays around the rounds of each batch (two dependent memory round trips to stage the
+// dofs, two more to write back, at ~3 us loaded latency) is overlapped here:
+//  * after the last round of batch t the shared x array is dead, so the dof list of batch t+g is
+//    loaded and its gather (cp.async), local dofmap (TMA bulk copy) and cell list are issued
+//    BEFORE batch t is written back; they land while the write-back runs;
+//  * the G prefetch rotation carries across batches (the last round requests the first cell of
+//    the next batch).
+// Colour order is enforced inside the launch: a batch of colour c is written back only after all
+// batches of colour c-1 are (a per-colour completion counter, monotonic across applies so it never
+// needs resetting).  All CTAs are co-resident (cooperative launch), and every CTA finishes its
+// colour c-1 batches before it touches colour c, so the wait cannot deadlock.
+struct PersistArgs
+{
+  const uint8_t* batch_colour;   // [nbatches]
+  const int32_t* colour_count;   // [ncolours] batches per colour
+  unsigned long long* done;      // [ncolours] completed batches, accumulated over applies
+  unsigned long long epoch;      // 1-based apply counter of this operator
+  int nbatches;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <typename T, int N, int SLOT, int W, int MINB>
+__global__ void __launch_bounds__(SLOT* W, MINB)
+stiff_brick_persistent(const BrickArgs<T> a, const PersistArgs pa, const DMat<T, N> Dm)
+{
+  constexpr int N2 = N * N, ND = N2 * N, NT = SLOT * W, NDP = ndp_of<N>(), U = 20;
+  using V2 = typename Vec2<T>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* xl = reinterpret_cast<T*>(smem_raw);
+  T* yl = xl + a.nloc_pad;
+  T* work = yl + a.nloc_pad;
+  const size_t meta_off = ((size_t)(2 * a.nloc_pad + W * slot_elems<N>()) * sizeof(T) + 15) & ~(size_t)15;
+  uint16_t* sldm = reinterpret_cast<uint16_t*>(smem_raw + meta_off);
+  int32_t* scell = reinterpret_cast<int32_t*>(sldm + (size_t)a.rounds_max * W * NDP);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(
+      smem_raw + ((meta_off + (size_t)a.rounds_max * W * (NDP * 2 + 4) + 7) & ~(size_t)7));
+  const int tid = threadIdx.x;
+  const int slot = tid / SLOT, col = tid % SLOT;
+  const bool lane_ok = col < N2;
+  const RoleOff ro = role_offsets<N>(lane_ok ? col : 0);
+  T* tiles = work + slot * slot_elems<N>();
+  PhaseTimer tm;
+  tm.start(tid % 32 == 0);
+
+  if (tid == 0)
+  {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int l = tid; l < a.nloc_pad; l += NT) yl[l] = T(0);
+  __syncthreads();
+  uint32_t bar_parity = 0;
+
+  // issue the staging of batch tb: dof list -> registers -> asynchronous gather into xl; local
+  // dofmap by TMA; cell list.  Completion is awaited by wait_staged().
+  auto stage = [&](int tb) {
+    const int64_t d0 = __ldg(a.dof_off + tb);
+    const int nloc = (int)(__ldg(a.dof_off + tb + 1) - d0);
+    const int r0 = __ldg(a.round_off + tb), nr = __ldg(a.round_off + tb + 1) - r0;
+    if (tid == 0)
+    {
+      const uint32_t bytes = (uint32_t)(nr * W * NDP * 2);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(sldm)),
+                   "l"(a.ldm + (int64_t)r0 * W * NDP), "r"(bytes), "r"(smem_u32(bar))
+                   : "memory");
+    }
+    for (int v = tid; v < nr * W; v += NT) scell[v] = __ldg(a.slot_cell + (int64_t)r0 * W + v);
+    for (int base = tid; base < nloc; base += NT * U)
+    {
+      uint32_t e[U];
+#pragma unroll
+      for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? __ldg(a.bdofs + d0 + base + q * NT) : 0u;
+#pragma unroll
+      for (int q = 0; q < U; ++q)
+        if (base + q * NT < nloc) cp_async_scalar(xl + base + q * NT, a.x + (e[q] & BD_MASK));
+    }
+  };
+
+  int t = blockIdx.x;
+  V2 g[N][3];
+#ifdef WFX_STAGGER_NS
+  // de-synchronise the CTAs: without it all of them reach their latency-bound write-back /
+  // staging phases at the same moment, wave after wave
+  {
+    const unsigned h = (blockIdx.x * 2654435761u) >> 22; // 0..1023
+    const unsigned ns = (unsigned)((unsigned long long)h * WFX_STAGGER_NS >> 10);
+    for (unsigned w = 0; w < ns; w += 1000) __nanosleep(1000);
+  }
+#endif
+  if (t < pa.nbatches)
+  {
+    const int c0 = __ldg(a.slot_cell + (int64_t)__ldg(a.round_off + t) * W + slot);
+    if (lane_ok && c0 >= 0) load_G<T, N>(a.G6 + (int64_t)c0 * (6 * ND), col, g);
+    stage(t);
+  }
+  for (; t < pa.nbatches; t += gridDim.x)
+  {
+    const int tn = t + gridDim.x;
+    const int64_t d0 = __ldg(a.dof_off + t);
+    const int nloc = (int)(__ldg(a.dof_off + t + 1) - d0);
+    const int nr = __ldg(a.round_off + t + 1) - __ldg(a.round_off + t);
+    const int cn_first = tn < pa.nbatches ? __ldg(a.slot_cell + (int64_t)__ldg(a.round_off + tn) * W + slot) : -1;
+    // staged data of this batch has landed
+    cp_async_wait_all();
+    mbar_wait(bar, bar_parity);
+    bar_parity ^= 1;
+    __syncthreads();
+    tm.mark(0);
+
+    for (int r = 0; r < nr; ++r)
+    {
+      const int cell = scell[r * W + slot];
+      const bool active = lane_ok && cell >= 0;
+      const uint16_t* lrow = sldm + (r * W + slot) * NDP + col;
+      int li[N];
+      T u[N], yv[N], f2[N];
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+      {
+        li[k] = active ? (int)lrow[k * N2] : 0;
+        u[k] = active ? xl[li[k]] : T(0);
+        yv[k] = 0;
+      }
+      if constexpr (SLOT <= 32) cell_part1<T, N>(u, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2, tm);
+      else cell_part1<T, N>(u, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2, tm);
+      {
+        // next cell of this batch, or the first cell of this CTA's next batch
+        int cn = -1;
+        if (r + 1 < nr) cn = scell[(r + 1) * W + slot];
+        else cn = cn_first;
+        if (lane_ok && cn >= 0) load_G<T, N>(a.G6 + (int64_t)cn * (6 * ND), col, g);
+      }
+      tm.mark(4);
+      if constexpr (SLOT <= 32) cell_part2<T, N>(f2, tiles, ro, Dm, active, WarpSync(), yv, tm);
+      else cell_part2<T, N>(f2, tiles, ro, Dm, active, BlockSync(), yv, tm);
+      if (active)
+      {
+#pragma unroll
+        for (int k = 0; k < N; ++k) yl[li[k]] += yv[k]; // cells of one round share no dof
+      }
+      tm.mark(6);
+      __syncthreads();
+      tm.mark(7);
+    }
+    // xl, sldm and scell are dead: start staging the next batch, then write this one back
+    if (tn < pa.nbatches) stage(tn);
+    const int colour = pa.batch_colour[t];
+    if (colour > 0)
+    {
+      if (tid == 0)
+      {
+        // all batches of the previous colour have been written back
+        const unsigned long long target = pa.epoch * (unsigned long long)pa.colour_count[colour - 1];
+        while (ld_acquire_u64(pa.done + colour - 1) < target) __nanosleep(100);
+      }
+      __syncthreads();
+    }
+    tm.mark(8);
+    for (int base = tid; base < nloc; base += NT * U)
+    {
+      uint32_t e[U];
+      T v[U], sc[U];
+#pragma unroll
+      for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? __ldg(a.bdofs + d0 + base + q * NT) : BD_FIRST;
+#pragma unroll
+      for (int q = 0; q < U; ++q)
+        sc[q] = (base + q * NT < nloc && (e[q] & BD_LAST) && a.scale) ? __ldg(a.scale + (e[q] & BD_MASK)) : T(1);
+#pragma unroll
+      for (int q = 0; q < U; ++q)
+      {
+        const bool ok = base + q * NT < nloc;
+        // y is written by other SMs inside this launch: bypass L1
+        v[q] = (ok && (!(e[q] & BD_FIRST) || a.beta)) ? __ldcg(a.y + (e[q] & BD_MASK)) : T(0);
+      }
+#pragma unroll
+      for (int q = 0; q < U; ++q)
+        if (base + q * NT < nloc)
+        {
+          a.y[e[q] & BD_MASK] = (v[q] + yl[base + q * NT]) * sc[q];
+          yl[base + q * NT] = T(0);
+        }
+    }
+    __syncthreads();
+    tm.mark(9);
+    if (tid == 0)
+    {
+      __threadfence();
+      atomicAdd(pa.done + colour, 1ull);
+    }
+  }
+  tm.flush(blockIdx.x * W + slot);
+}
+
 template <typename T>
 __global__ void zero_entries_kernel(const int32_t* __restrict__ idx, int n, T* __restrict__ y)
 {
@@ -534,6 +738,15 @@ struct wfx_stiffness
   DevBuf<uint32_t> d_bdofs;
   DevBuf<int32_t> d_round_off, d_slot_cell, d_untouched;
   DevBuf<uint16_t> d_ldm;
+  // persistent (single cooperative launch) form: experimental, WFX_PERSISTENT=1.  Measured slower
+  // than the chained colour launches in round 1 (0.91 vs 0.70 ms at 64^3 P4: the write-back
+  // phase runs 4x longer while the next batch's staging traffic is in flight), so it is off.
+  bool persistent = false;
+  int nbatches = 0, persist_grid = 0;
+  unsigned long long epoch = 0;
+  DevBuf<uint8_t> d_batch_colour;
+  DevBuf<int32_t> d_colour_count;
+  DevBuf<unsigned long long> d_done;
   // host-call staging
   DevBuf<unsigned char> d_hx, d_hy;
 };
@@ -584,6 +797,27 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
     const int n = (int)op->d_untouched.n;
     zero_entries_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(op->d_untouched.p, n, y);
   }
+  if (op->persistent)
+  {
+    auto pk = stiff_brick_persistent<T, N, C::SLOT, C::W, C::MINB>;
+    if (op->persist_grid == 0)
+    {
+      int occ = 0;
+      WFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pk, C::SLOT * C::W, op->smem_bytes));
+      if (occ < 1) fail("stiffness: persistent kernel does not fit on an SM");
+      op->persist_grid = std::min(op->nbatches, occ * op->ctx->num_sms);
+    }
+    PersistArgs pa;
+    pa.batch_colour = op->d_batch_colour.p;
+    pa.colour_count = op->d_colour_count.p;
+    pa.done = op->d_done.p;
+    pa.epoch = ++op->epoch;
+    pa.nbatches = op->nbatches;
+    void* args[] = {(void*)&a, (void*)&pa, (void*)&Dm};
+    WFX_CUDA(cudaLaunchCooperativeKernel((void*)pk, dim3(op->persist_grid), dim3(C::SLOT * C::W), args,
+                                         op->smem_bytes, st));
+    return;
+  }
   bool first = true;
   for (int k = 0; k < op->ncolours; ++k)
   {
@@ -612,6 +846,8 @@ void configure_brick(wfx_stiffness* op)
 {
   using C = Cfg<N>;
   WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->ctx->smem_optin));
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persistent<T, N, C::SLOT, C::W, C::MINB>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->ctx->smem_optin));
 }
 template <typename T>
@@ -782,6 +1018,21 @@ extern "C" int wfx_stiffness_create(wfx_ctx* ctx, wfx_geom* geom, int64_t ndofs,
       op->d_round_off.upload(bp.round_off);
       op->d_slot_cell.upload(bp.slot_cell);
       op->d_ldm.upload(bp.ldm);
+      op->nbatches = bp.nbatches;
+      {
+        std::vector<uint8_t> bc((size_t)bp.nbatches);
+        std::vector<int32_t> cc((size_t)bp.ncolours);
+        for (int c = 0; c < bp.ncolours; ++c)
+        {
+          cc[c] = bp.colour_off[c + 1] - bp.colour_off[c];
+          for (int b = bp.colour_off[c]; b < bp.colour_off[c + 1]; ++b) bc[b] = (uint8_t)c;
+        }
+        op->d_batch_colour.upload(bc);
+        op->d_colour_count.upload(cc);
+        op->d_done.alloc((size_t)bp.ncolours);
+        WFX_CUDA(cudaMemset(op->d_done.p, 0, (size_t)bp.ncolours * sizeof(unsigned long long)));
+      }
+      if (const char* e = std::getenv("WFX_PERSISTENT")) op->persistent = std::atoi(e) != 0;
       if (!bp.untouched.empty()) op->d_untouched.upload(bp.untouched);
       if (op->dtype == WFX_F64) configure_any<double>(op.get());
       else configure_any<float>(op.get());
