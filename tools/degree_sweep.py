@@ -1,0 +1,118 @@
+"""BASELINE config 3: polynomial degree sweep P2..P7 of the operator apply on one B200, fp64 and
+fp32, ~17 M dofs each: the sum-factorised kernel (libwavefx) against the "batched TSMM"
+formulation of the reference's cuBLAS demos (gather -> GEMM with the dense nd x nd derivative
+tables -> G -> GEMM -> atomic scatter; demo/gpu_operator/main.cpp:144-160, demo/gpu_tsmm), here
+through torch.matmul as a COMPARATOR only.
+
+    python tools/degree_sweep.py [--out profiles/r1_degree_sweep.md]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import wave_fenics_b200 as wfx  # noqa: E402
+
+L = 0.1
+CELLS = {2: 128, 3: 86, 4: 64, 5: 51, 6: 43, 7: 37}
+
+
+def time_ms(fn, reps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def dense_tables(P, dtype):
+    """dphi[a][q][dof] = D (x) delta (x) delta in DOLFINx dof order (common/operators.hpp:13-32)."""
+    n, nd = P + 1, (P + 1) ** 3
+    D = wfx.capi.deriv_1d(P)
+    perm = wfx.capi.compute_permutations(P)
+    T = np.zeros((3, nd, nd))
+    for a in range(n):
+        for b in range(n):
+            for c in range(n):
+                q = (a * n + b) * n + c
+                for i in range(n):
+                    T[0, q, perm[(i * n + b) * n + c]] = D[a, i]
+                    T[1, q, perm[(a * n + i) * n + c]] = D[b, i]
+                    T[2, q, perm[(a * n + b) * n + i]] = D[c, i]
+    return torch.from_numpy(T).to("cuda", dtype)
+
+
+def tsmm_apply(x, y, dofmap, tables, G9, coeff):
+    """y += A x as batched dense GEMMs (k >> m ~ n): the comparator."""
+    xe = x[dofmap]                                           # gather   [nc, nd]
+    w = torch.stack([xe @ tables[a].T for a in range(3)])    # 3 GEMMs  [3, nc, nq]
+    f = coeff * torch.einsum("cqrs,scq->rcq", G9, w)         # pointwise G
+    ye = sum(f[a] @ tables[a] for a in range(3))             # 3 GEMMs  [nc, nd]
+    y.index_add_(0, dofmap.reshape(-1), ye.reshape(-1))      # atomic scatter
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--degrees", default="2,3,4,5,6,7")
+    args = ap.parse_args()
+    peak = 6538.6
+    pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peak = json.load(open(pk))["hbm_gbs"]
+    rows = []
+    for P in [int(p) for p in args.degrees.split(",")]:
+        N = CELLS[P]
+        mesh = wfx.create_box_hex(N, P, (L, L, L), perturb=0.15)
+        for dt, tdt in ((np.float64, torch.float64), (np.float32, torch.float32)):
+            geo = wfx.Geometry(mesh, P, dt)
+            op = wfx.StiffnessOperator(mesh, P, dtype=dt, geometry=geo)
+            mass = wfx.MassOperator(mesh, P, dtype=dt, geometry=geo)
+            info = op.info()
+            x = torch.randn(mesh.ndofs, dtype=tdt, device="cuda")
+            y = torch.empty_like(x)
+            ms = time_ms(lambda: op.apply_scaled(x, mass.inverse_diagonal_ptr(), y), args.reps)
+            # comparator on a slab of the mesh that fits comfortably (dense tables: nd^2 per cell flops)
+            ncc = min(mesh.ncells, 32768)
+            dm = torch.from_numpy(mesh.dofmap[:ncc].astype(np.int64)).cuda()
+            G9, _ = geo.get() if mesh.ncells <= 300000 and P <= 4 else (None, None)
+            tsmm = None
+            if G9 is not None:
+                G9t = torch.from_numpy(G9[:ncc]).to("cuda", tdt)
+                tabs = dense_tables(P, tdt)
+                y2 = torch.zeros_like(x)
+                ms_t = time_ms(lambda: tsmm_apply(x, y2, dm, tabs, G9t, -1500.0 ** 2), max(2, args.reps // 3))
+                tsmm = ncc * (P ** 3) / (ms_t * 1e-3) / 1e9  # dofs ~ P^3 per cell
+                del G9t, tabs, y2
+            gd = mesh.ndofs / (ms * 1e-3) / 1e9
+            gbs = info["bytes"] / (ms * 1e-3) / 1e9
+            rows.append((P, N, mesh.ndofs, "f64" if dt == np.float64 else "f32", ms, gd, gbs, gbs / peak, info["flops"] / (ms * 1e-3) / 1e12, tsmm))
+            print(rows[-1], flush=True)
+            del op, mass, geo, x, y
+            torch.cuda.empty_cache()
+    lines = ["# Degree sweep (BASELINE config 3), one B200, stiffness + mass apply, ~17 M dofs per case",
+             "", f"HBM peak used for the fraction: {peak} GB/s (MEASURED_PEAKS.json). `TSMM` = dense-table batched GEMM",
+             "comparator (torch.matmul/cuBLAS, gather + 6 GEMMs + G + atomic scatter) on a 32 768-cell slab, in GDoF/s.", "",
+             "| P | cells/axis | dofs | dtype | ms/apply | GDoF/s | algorithmic GB/s | frac of HBM peak | TFLOP/s (sum-fact count) | TSMM GDoF/s |",
+             "|---|---|---|---|---|---|---|---|---|---|"]
+    for r in rows:
+        lines.append(f"| {r[0]} | {r[1]} | {r[2]} | {r[3]} | {r[4]:.3f} | {r[5]:.2f} | {r[6]:.0f} | {r[7]:.3f} | {r[8]:.2f} | "
+                     + (f"{r[9]:.2f}" if r[9] else "n/a") + " |")
+    text = "\n".join(lines) + "\n"
+    print(text)
+    if args.out:
+        open(args.out, "w").write(text)
+
+
+if __name__ == "__main__":
+    main()
