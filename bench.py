@@ -164,13 +164,20 @@ def run_b200(args):
 
     import ctypes as C
 
+    comm_stream = torch.cuda.Stream(device=dev) if halo is not None else None
+
     def step():
         if halo is None:
             stiff.apply_scaled(x, minv_ptr, y)
         else:
-            stiff.apply(x, y, beta=0)
-            halo.update_rev_fwd(y)
-            mass.apply_inverse(y, y)
+            # interface cells -> their ghost reduction (+ 1/m on the owner) on a side stream while
+            # the interior cells run with the fused 1/m; shared dofs are never scaled in-kernel
+            main = torch.cuda.current_stream()
+            stiff.apply_part(x, y, 0, beta=0, scale_ptr=minv_ptr)
+            comm_stream.wait_stream(main)
+            halo.update_rev_fwd_scaled(y, minv_ptr, stream=comm_stream.cuda_stream)
+            stiff.apply_part(x, y, 1, beta=0, scale_ptr=minv_ptr)
+            main.wait_stream(comm_stream)
 
     def sync_all():
         torch.cuda.synchronize()

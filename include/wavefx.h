@@ -124,6 +124,20 @@ int wfx_compute_jacobian_data(wfx_ctx* ctx, int64_t ncells, int64_t npts, const 
 int wfx_stiffness_create(wfx_ctx* ctx, wfx_geom* geom, int64_t ndofs, const int32_t* dofmap_host,
                          double c0, int flags, wfx_stiffness** op);
 int wfx_stiffness_apply(wfx_stiffness* op, const void* x_dev, void* y_dev, int beta, void* stream);
+/* Distributed meshes (one rank per GPU, GhostMode::none as demo/cpu_planar3d/main.cpp:42):
+ * shared_dofs_host lists the local vector entries that also live on another rank (the union
+ * of the halo's send and receive indices).  Cells touching them are scheduled first
+ * (part 0, "interface"), the rest is part 1 ("interior"), so that the ghost reduction of
+ * part 0's result can overlap part 1:  apply_part(.., 0) ; halo on another stream ;
+ * apply_part(.., 1).  The fused scaling of wfx_stiffness_apply_scaled is then applied to
+ * non-shared dofs only; shared dofs are scaled by wfx_halo_update_rev_fwd_scaled after
+ * their sum is complete.  part = -1 runs both parts. */
+int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, int64_t ndofs,
+                                     const int32_t* dofmap_host, double c0, int flags,
+                                     int64_t nshared, const int32_t* shared_dofs_host,
+                                     wfx_stiffness** op);
+int wfx_stiffness_apply_part(wfx_stiffness* op, const void* x_dev, const void* scale_dev,
+                             void* y_dev, int beta, int part, void* stream);
 /* Fused operator+mass-inverse apply, the headline "stiffness + mass apply":
  *   y = scale .* (-c0^2 K x)   with scale_dev = 1/m (wfx_mass_inverse_diagonal).
  * Replaces stiff_op(u_n, b) followed by b/m (common/LinearGLL.hpp:173-191). */
@@ -191,6 +205,9 @@ int wfx_boundary_apply(wfx_boundary* op, double c0, double g, const void* vn_dev
                        void* stream);
 /* dense copies of m1 / m2 (length ndofs, fp64) for checks */
 int wfx_boundary_get(wfx_boundary* op, double* m1_host, double* m2_host);
+/* Distributed meshes: sum the facet masses over the ranks sharing a boundary dof (fp64 halo), so
+ * that every copy of the dof can add the complete boundary term after the ghost reduction. */
+int wfx_boundary_assemble(wfx_boundary* op, wfx_halo* halo_f64);
 int wfx_boundary_destroy(wfx_boundary* op);
 
 /* ---- ghost-dof halo exchange: VectorUpdater (demo/gpu_scatter_mpi/VectorUpdater.hpp:21-230)
@@ -214,6 +231,9 @@ int wfx_halo_create(wfx_ctx* ctx, wfx_comm* comm, int dtype, int n_send_nbr,
 int wfx_halo_update_fwd(wfx_halo* halo, void* x_dev, void* stream);
 int wfx_halo_update_rev(wfx_halo* halo, void* x_dev, void* stream);
 int wfx_halo_update_rev_fwd(wfx_halo* halo, void* x_dev, void* stream);
+/* as update_rev_fwd, the owner multiplying the completed sum by scale_dev[i] before it is sent
+ * back to the ghosts (the b/m of common/LinearGLL.hpp:188-191 for shared dofs) */
+int wfx_halo_update_rev_fwd_scaled(wfx_halo* halo, void* x_dev, const void* scale_dev, void* stream);
 int wfx_halo_destroy(wfx_halo* halo);
 
 /* ---- wave model + RK4: LinearGLLOpt (common/LinearGLL.hpp:37-287) ----------

@@ -43,6 +43,27 @@ def main():
     err = np.linalg.norm(y.cpu().numpy() - ref) / np.linalg.norm(ref)
     assert err < 1e-12, f"rank {rank}: halo-reduced apply differs, rel L2 {err:.3e}"
 
+    # split form: interface cells, scaled ghost reduction on a side stream, interior cells with the
+    # fused 1/m -- must equal (assembled K x) / (assembled m) on every copy
+    geo = wfx.Geometry(mesh, P, ctx=ctx)
+    mass = wfx.MassOperator(mesh, P, ctx=ctx, geometry=geo)
+    mass.assemble(halo)
+    gmass = wfx.MassOperator(gmesh, P, ctx=ctx)
+    want = (yg.cpu().numpy() / gmass.diagonal())[mesh.global_dofs]
+    assert np.allclose(mass.diagonal(), gmass.diagonal()[mesh.global_dofs], rtol=1e-14, atol=0)
+    y2 = torch.full((mesh.ndofs,), float("nan"), dtype=torch.float64, device=dev)
+    xl = torch.from_numpy(xg[mesh.global_dofs]).to(dev)
+    side = torch.cuda.Stream(device=dev)
+    minv = mass.inverse_diagonal_ptr()
+    op.apply_part(xl, y2, 0, beta=0, scale_ptr=minv)
+    side.wait_stream(torch.cuda.current_stream())
+    halo.update_rev_fwd_scaled(y2, minv, stream=side.cuda_stream)
+    op.apply_part(xl, y2, 1, beta=0, scale_ptr=minv)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    err2 = np.linalg.norm(y2.cpu().numpy() - want) / np.linalg.norm(want)
+    assert err2 < 1e-12, f"rank {rank}: split/scaled apply differs, rel L2 {err2:.3e}"
+
     # forward update alone: ghosts take the owner's value
     z = torch.from_numpy(xg[mesh.global_dofs].copy()).to(dev)
     z[mesh.size_local:] = -1.0

@@ -56,6 +56,11 @@ _SIG = {
                                   _c_f64p, _c_f64p, _c_f64p, _c_f64p, _c_f64p],
     "wfx_stiffness_create": [_vp, _vp, C.c_int64, _c_i32p, C.c_double, C.c_int, _vpp],
     "wfx_stiffness_apply": [_vp, _vp, _vp, C.c_int, _vp],
+    "wfx_stiffness_create_partitioned": [_vp, _vp, C.c_int64, _c_i32p, C.c_double, C.c_int, C.c_int64,
+                                         _c_i32p, _vpp],
+    "wfx_stiffness_apply_part": [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp],
+    "wfx_halo_update_rev_fwd_scaled": [_vp, _vp, _vp, _vp],
+    "wfx_boundary_assemble": [_vp, _vp],
     "wfx_stiffness_apply_scaled": [_vp, _vp, _vp, _vp, _vp],
     "wfx_stiffness_apply_host": [_vp, _vp, _vp, C.c_int],
     "wfx_stiffness_mass_apply_host": [_vp, _vp, _vp, _vp],

@@ -19,6 +19,7 @@ struct wfx_boundary
   DevBuf<double> d_m1, d_m2; // compact, fp64 (tiny)
   std::vector<int32_t> h_idx;
   std::vector<double> h_m1, h_m2;
+  bool assembled = false; // facet masses summed over the ranks (wfx_boundary_assemble)
 };
 
 namespace
@@ -161,6 +162,52 @@ extern "C" int wfx_boundary_get(wfx_boundary* op, double* m1, double* m2)
   {
     if (m1) m1[op->h_idx[t]] = op->h_m1[t];
     if (m2) m2[op->h_idx[t]] = op->h_m2[t];
+  }
+  WFX_API_END
+}
+
+extern "C" int wfx_boundary_assemble(wfx_boundary* op, wfx_halo* halo)
+{
+  WFX_API_BEGIN
+  if (!op || !halo) fail("NULL argument");
+  if (op->assembled) return 0; // idempotent
+  op->assembled = true;
+  ScopedDevice sd(op->ctx->device);
+  // dense fp64 vectors through the ghost reduction, then compact again: a dof may carry a
+  // boundary term here only because a neighbouring rank owns the tagged facet
+  std::vector<double> m1((size_t)op->ndofs, 0.0), m2((size_t)op->ndofs, 0.0);
+  for (int64_t t = 0; t < op->nb; ++t)
+  {
+    m1[op->h_idx[t]] = op->h_m1[t];
+    m2[op->h_idx[t]] = op->h_m2[t];
+  }
+  DevBuf<double> d1((size_t)op->ndofs), d2((size_t)op->ndofs);
+  d1.upload(m1);
+  d2.upload(m2);
+  if (op->ndofs)
+  {
+    if (wfx_halo_update_rev_fwd(halo, d1.p, nullptr)) fail("%s", wfx_last_error());
+    if (wfx_halo_update_rev_fwd(halo, d2.p, nullptr)) fail("%s", wfx_last_error());
+    WFX_CUDA(cudaDeviceSynchronize());
+    d1.download(m1.data(), m1.size());
+    d2.download(m2.data(), m2.size());
+  }
+  op->h_idx.clear();
+  op->h_m1.clear();
+  op->h_m2.clear();
+  for (int64_t i = 0; i < op->ndofs; ++i)
+    if (m1[i] != 0.0 || m2[i] != 0.0)
+    {
+      op->h_idx.push_back((int32_t)i);
+      op->h_m1.push_back(m1[i]);
+      op->h_m2.push_back(m2[i]);
+    }
+  op->nb = (int64_t)op->h_idx.size();
+  if (op->nb)
+  {
+    op->d_idx.upload(op->h_idx);
+    op->d_m1.upload(op->h_m1);
+    op->d_m2.upload(op->h_m2);
   }
   WFX_API_END
 }

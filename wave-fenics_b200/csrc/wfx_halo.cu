@@ -106,19 +106,21 @@ __global__ void unpack_copy_kernel(int64_t n, const int32_t* __restrict__ idx,
 template <typename T>
 __global__ void unpack_add_kernel(int64_t nuniq, const int32_t* __restrict__ uniq,
                                   const int64_t* __restrict__ off, const int32_t* __restrict__ src,
-                                  const T* __restrict__ buf, T* __restrict__ x)
+                                  const T* __restrict__ buf, T* __restrict__ x,
+                                  const T* __restrict__ scale)
 {
   const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (j >= nuniq) return;
   T s = x[uniq[j]];
   for (int64_t p = off[j]; p < off[j + 1]; ++p) s += buf[src[p]];
+  if (scale) s *= scale[uniq[j]];
   x[uniq[j]] = s;
 }
 
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 template <typename T>
-void exchange(wfx_halo* h, bool forward, T* x, cudaStream_t st)
+void exchange(wfx_halo* h, bool forward, T* x, cudaStream_t st, const T* scale = nullptr)
 {
   const ncclDataType_t dt = sizeof(T) == 8 ? ncclDouble : ncclFloat;
   T* sbuf = (T*)h->d_send_buf.p;
@@ -144,12 +146,12 @@ void exchange(wfx_halo* h, bool forward, T* x, cudaStream_t st)
       WFX_NCCL(nccl().Send(rbuf + h->recv_off[i], h->recv_off[i + 1] - h->recv_off[i], dt, h->recv_ranks[i], h->comm->comm, st));
     WFX_NCCL(nccl().GroupEnd());
     if (h->nuniq)
-      unpack_add_kernel<T><<<grid_for(h->nuniq), 256, 0, st>>>(h->nuniq, h->d_uniq.p, h->d_useg_off.p, h->d_useg_src.p, sbuf, x);
+      unpack_add_kernel<T><<<grid_for(h->nuniq), 256, 0, st>>>(h->nuniq, h->d_uniq.p, h->d_useg_off.p, h->d_useg_src.p, sbuf, x, scale);
   }
   WFX_CUDA(cudaGetLastError());
 }
 
-void run(wfx_halo* h, int what, void* x, void* stream)
+void run(wfx_halo* h, int what, void* x, void* stream, const void* scale = nullptr)
 {
   if (!h) fail("halo is NULL");
   if (!x) fail("halo: NULL vector");
@@ -157,16 +159,21 @@ void run(wfx_halo* h, int what, void* x, void* stream)
   cudaStream_t st = (cudaStream_t)stream;
   if (h->dtype == WFX_F64)
   {
-    if (what & 1) exchange<double>(h, false, (double*)x, st);
+    if (what & 1) exchange<double>(h, false, (double*)x, st, (const double*)scale);
     if (what & 2) exchange<double>(h, true, (double*)x, st);
   }
   else
   {
-    if (what & 1) exchange<float>(h, false, (float*)x, st);
+    if (what & 1) exchange<float>(h, false, (float*)x, st, (const float*)scale);
     if (what & 2) exchange<float>(h, true, (float*)x, st);
   }
 }
 } // namespace
+
+namespace wfx
+{
+int halo_dtype(const wfx_halo* h) { return h->dtype; }
+} // namespace wfx
 
 extern "C" int wfx_comm_unique_id(char id[128])
 {
@@ -287,6 +294,14 @@ extern "C" int wfx_halo_update_rev_fwd(wfx_halo* h, void* x, void* stream)
 {
   WFX_API_BEGIN
   run(h, 3, x, stream);
+  WFX_API_END
+}
+
+extern "C" int wfx_halo_update_rev_fwd_scaled(wfx_halo* h, void* x, const void* scale, void* stream)
+{
+  WFX_API_BEGIN
+  if (!scale) fail("halo: scale vector is NULL");
+  run(h, 3, x, stream, scale);
   WFX_API_END
 }
 

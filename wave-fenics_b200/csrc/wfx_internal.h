@@ -15,6 +15,7 @@
 #define WFX_MAXN 12 // max GLL points per direction handled by the host tables
 
 struct wfx_stiffness;
+struct wfx_halo;
 
 namespace wfx
 {
@@ -99,7 +100,9 @@ void deriv_1d(int P, double* D, bool clamp);              // D[q*n+i]
 void tensor_perm(int P, int32_t* perm);                   // tensor index -> DOLFINx dof
 double clamp_m101(double v);                              // xt::isclose clamp to -1/0/1
 
-int stiffness_dtype(const struct ::wfx_stiffness* op); // wfx_stiffness.cu
+int stiffness_dtype(const struct ::wfx_stiffness* op);    // wfx_stiffness.cu
+bool stiffness_has_split(const struct ::wfx_stiffness* op); // interface/interior parts present
+int halo_dtype(const struct ::wfx_halo* h);                // wfx_halo.cu
 
 struct ScopedDevice
 {

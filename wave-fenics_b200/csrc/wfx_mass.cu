@@ -34,6 +34,7 @@ struct wfx_mass
   void* d_m = nullptr;  // dtype T (aliases d_m64 for fp64)
   void* d_minv = nullptr;
   DevBuf<unsigned char> d_hx, d_hy;
+  bool assembled = false; // diagonal summed over the ranks (wfx_mass_assemble)
   ~wfx_mass()
   {
     if (d_minv) cudaFree(d_minv);
@@ -274,7 +275,8 @@ extern "C" int wfx_mass_assemble(wfx_mass* op, wfx_halo* halo)
 {
   WFX_API_BEGIN
   if (!op || !halo) fail("NULL argument");
-  if (op->ndofs == 0) return 0;
+  if (op->ndofs == 0 || op->assembled) return 0; // idempotent
+  op->assembled = true;
   ScopedDevice sd(op->ctx->device);
   if (wfx_halo_update_rev_fwd(halo, op->d_m64.p, nullptr)) fail("%s", wfx_last_error());
   const unsigned grid = (unsigned)((op->ndofs + 255) / 256);

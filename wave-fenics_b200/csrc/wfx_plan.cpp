@@ -69,7 +69,7 @@ void verify_cell_colour_plan(const CellColourPlan& plan, int nd, int64_t ncells,
 
 void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
                       const float* centroid, int brick_edge, int W, int nloc_cap,
-                      BrickPlan& plan)
+                      BrickPlan& plan, const uint8_t* dof_shared)
 {
   const int n = P + 1, nd = n * n * n;
   if (ndofs > (int64_t)BD_MASK) fail("brick plan: more than 2^30 local dofs");
@@ -224,6 +224,26 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
     for (auto& b : batches) b.colour = remap[b.colour];
     ncol = k;
   }
+  // Distributed meshes: batches that touch a dof shared with another rank ("interface"
+  // batches) run first so that the halo exchange of those dofs can overlap the interior
+  // batches.  Execution colour = part * ncol + colour, part 0 = interface, 1 = interior.
+  plan.part_split = 0;
+  if (dof_shared)
+  {
+    for (auto& b : batches)
+    {
+      bool iface = false;
+      for (int64_t p = b.begin; p < b.end && !iface; ++p)
+      {
+        const int32_t* d = tdm + (int64_t)order[p] * nd;
+        for (int t = 0; t < nd; ++t)
+          if (dof_shared[d[t]]) { iface = true; break; }
+      }
+      if (!iface) b.colour += ncol;
+    }
+    plan.part_split = ncol;
+    ncol *= 2;
+  }
   plan.ncolours = ncol;
   std::stable_sort(batches.begin(), batches.end(),
                    [](const Batch& a, const Batch& b) { return a.colour < b.colour; });
@@ -231,16 +251,16 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
   for (auto& b : batches) plan.colour_off[b.colour + 1]++;
   for (int c = 0; c < ncol; ++c) plan.colour_off[c + 1] += plan.colour_off[c];
 
-  // first / last colour touching each dof
-  std::vector<int8_t> cmin((size_t)ndofs, 127), cmax((size_t)ndofs, -1);
+  // first / last (execution) colour touching each dof
+  std::vector<int16_t> cmin((size_t)ndofs, 32767), cmax((size_t)ndofs, -1);
   for (auto& b : batches)
     for (int64_t p = b.begin; p < b.end; ++p)
     {
       const int32_t* d = tdm + (int64_t)order[p] * nd;
       for (int t = 0; t < nd; ++t)
       {
-        cmin[d[t]] = std::min<int8_t>(cmin[d[t]], (int8_t)b.colour);
-        cmax[d[t]] = std::max<int8_t>(cmax[d[t]], (int8_t)b.colour);
+        cmin[d[t]] = std::min<int16_t>(cmin[d[t]], (int16_t)b.colour);
+        cmax[d[t]] = std::max<int16_t>(cmax[d[t]], (int16_t)b.colour);
       }
     }
   for (int64_t i = 0; i < ndofs; ++i)
@@ -277,7 +297,8 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
       g2l[d] = l;
       uint32_t e = (uint32_t)d;
       if (cmin[d] == b.colour) e |= BD_FIRST;
-      if (cmax[d] == b.colour) e |= BD_LAST;
+      // shared dofs are complete only after the halo sum: never LAST (no fused scaling) here
+      if (cmax[d] == b.colour && !(dof_shared && dof_shared[d])) e |= BD_LAST;
       if ((e & BD_FIRST) && (e & BD_LAST)) plan.n_private++;
       plan.bdofs.push_back(e);
     }
@@ -326,7 +347,7 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
   plan.n_slots_padded = plan.nrounds_total * W - ncells;
 }
 
-void verify_brick_plan(const BrickPlan& plan, const int32_t* tdm)
+void verify_brick_plan(const BrickPlan& plan, const int32_t* tdm, const uint8_t* dof_shared)
 {
   const int nd = plan.nd, W = plan.W, nb = plan.nbatches;
   const int64_t ncells = plan.ncells, ndofs = plan.ndofs;
@@ -351,6 +372,8 @@ void verify_brick_plan(const BrickPlan& plan, const int32_t* tdm)
         if (d < 0 || d >= ndofs) fail("brick plan: dof out of range");
         if (l > d0 && (plan.bdofs[l - 1] & BD_MASK) >= (uint32_t)d) fail("brick plan: batch dofs not ascending/unique");
         if (colour_stamp[d] == col) fail("brick plan: two batches of colour %d share dof %d", col, d);
+        if (dof_shared && dof_shared[d] && col >= plan.part_split && plan.part_split > 0)
+          fail("brick plan: interior batch touches shared dof %d", d);
         colour_stamp[d] = col;
         const bool first = e & BD_FIRST, last = e & BD_LAST;
         if (first && touched[d]) fail("brick plan: FIRST flag on an already touched dof");
@@ -386,7 +409,8 @@ void verify_brick_plan(const BrickPlan& plan, const int32_t* tdm)
   for (int64_t d = 0; d < ndofs; ++d)
   {
     if (!touched[d]) { ++nunt; continue; }
-    if (nfirst[d] != 1 || nlast[d] != 1) fail("brick plan: dof %lld has %d FIRST / %d LAST marks", (long long)d, nfirst[d], nlast[d]);
+    const int want_last = (dof_shared && dof_shared[d]) ? 0 : 1;
+    if (nfirst[d] != 1 || nlast[d] != want_last) fail("brick plan: dof %lld has %d FIRST / %d LAST marks", (long long)d, nfirst[d], nlast[d]);
   }
   if (nunt != (int64_t)plan.untouched.size()) fail("brick plan: untouched list inconsistent");
 }

@@ -37,7 +37,8 @@ struct BrickPlan
   int ndp = 0;              // slot stride of ldm: nd rounded up to 8 entries (16 bytes)
   int rounds_max = 0;       // most rounds in one batch
   int64_t ncells = 0, ndofs = 0;
-  int nbatches = 0, ncolours = 0;
+  int nbatches = 0, ncolours = 0;  // ncolours = execution colours (2x the graph colours when split)
+  int part_split = 0;              // first execution colour of the interior part (0 = no split)
   int nloc_max = 0;                // largest number of unique dofs in a batch
   int64_t nrounds_total = 0;
   // batches are stored sorted by colour
@@ -62,10 +63,10 @@ void build_cell_colour_plan(int nd, int64_t ncells, int64_t ndofs, const int32_t
 // shared-memory dof arrays.
 void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
                       const float* centroid, int brick_edge, int W, int nloc_cap,
-                      BrickPlan& plan);
+                      BrickPlan& plan, const uint8_t* dof_shared = nullptr);
 
 // Checks every invariant the kernels rely on; throws wfx::Error on violation.
-void verify_brick_plan(const BrickPlan& plan, const int32_t* tdm);
+void verify_brick_plan(const BrickPlan& plan, const int32_t* tdm, const uint8_t* dof_shared = nullptr);
 void verify_cell_colour_plan(const CellColourPlan& plan, int nd, int64_t ncells, int64_t ndofs,
                              const int32_t* tdm);
 } // namespace wfx

@@ -732,6 +732,8 @@ struct wfx_stiffness
   DevBuf<int32_t> d_cells, d_tdm;
   // brick path
   int ncolours = 0, nloc_pad = 0, W = 0, rounds_max = 0;
+  int part_split = 0; // first execution colour of the interior part (distributed meshes)
+  int cur_part = -1;  // part selected by the running apply: -1 all, 0 interface, 1 interior
   size_t smem_bytes = 0;
   std::vector<int32_t> colour_off;
   DevBuf<int64_t> d_dof_off;
@@ -792,12 +794,12 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   a.beta = beta;
   a.nloc_pad = op->nloc_pad;
   a.rounds_max = op->rounds_max;
-  if (!beta && op->d_untouched.n)
+  if (!beta && op->d_untouched.n && op->cur_part != 1)
   {
     const int n = (int)op->d_untouched.n;
     zero_entries_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(op->d_untouched.p, n, y);
   }
-  if (op->persistent)
+  if (op->persistent && op->cur_part < 0)
   {
     auto pk = stiff_brick_persistent<T, N, C::SLOT, C::W, C::MINB>;
     if (op->persist_grid == 0)
@@ -819,7 +821,10 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
     return;
   }
   bool first = true;
-  for (int k = 0; k < op->ncolours; ++k)
+  // execution colours of the requested part: interface batches [0, part_split), interior the rest
+  const int k0 = op->cur_part == 1 ? op->part_split : 0;
+  const int k1 = op->cur_part == 0 ? op->part_split : op->ncolours;
+  for (int k = k0; k < k1; ++k)
   {
     const int beg = op->colour_off[k], nb = op->colour_off[k + 1] - beg;
     if (nb == 0) continue;
@@ -919,6 +924,7 @@ void apply_any(wfx_stiffness* op, const void* x, const void* scale, void* y, int
 namespace wfx
 {
 int stiffness_dtype(const wfx_stiffness* op) { return op->dtype; }
+bool stiffness_has_split(const wfx_stiffness* op) { return op->part_split > 0; }
 
 // tensor-ordered dofmap in the kernels' k-major point order
 void build_tensor_dofmap(int P, int64_t ncells, int64_t ndofs, const int32_t* dofmap,
@@ -954,8 +960,27 @@ extern "C" int wfx_stiffness_create(wfx_ctx* ctx, wfx_geom* geom, int64_t ndofs,
                                     const int32_t* dofmap_host, double c0, int flags,
                                     wfx_stiffness** out)
 {
+  return wfx_stiffness_create_partitioned(ctx, geom, ndofs, dofmap_host, c0, flags, 0, nullptr, out);
+}
+
+extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, int64_t ndofs,
+                                                const int32_t* dofmap_host, double c0, int flags,
+                                                int64_t nshared, const int32_t* shared_dofs_host,
+                                                wfx_stiffness** out)
+{
   WFX_API_BEGIN
   if (!ctx || !geom || !out) fail("NULL argument");
+  if (nshared < 0 || (nshared > 0 && !shared_dofs_host)) fail("bad shared dof list");
+  std::vector<uint8_t> shared;
+  if (nshared > 0)
+  {
+    shared.assign((size_t)ndofs, 0);
+    for (int64_t i = 0; i < nshared; ++i)
+    {
+      if (shared_dofs_host[i] < 0 || shared_dofs_host[i] >= ndofs) fail("shared dof out of range");
+      shared[shared_dofs_host[i]] = 1;
+    }
+  }
   if (geom->ctx != ctx) fail("geometry belongs to another context");
   if (ndofs < 0) fail("negative ndofs");
   if (ndofs >= (1ll << 31)) fail("more than 2^31 local dofs");
@@ -1004,8 +1029,10 @@ extern "C" int wfx_stiffness_create(wfx_ctx* ctx, wfx_geom* geom, int64_t ndofs,
       if (const char* e = std::getenv("WFX_BRICK_EDGE")) be = std::max(1, std::atoi(e));
       BrickPlan bp;
       build_brick_plan(op->P, op->ncells, ndofs, tdm.data(),
-                       geom->centroid.empty() ? nullptr : geom->centroid.data(), be, lc.W, nloc_cap, bp);
+                       geom->centroid.empty() ? nullptr : geom->centroid.data(), be, lc.W, nloc_cap, bp,
+                       shared.empty() ? nullptr : shared.data());
       op->ncolours = bp.ncolours;
+      op->part_split = bp.part_split;
       op->colour_off = bp.colour_off;
       op->W = bp.W;
       op->nloc_pad = (bp.nloc_max + 1) & ~1;
@@ -1046,6 +1073,28 @@ extern "C" int wfx_stiffness_apply(wfx_stiffness* op, const void* x, void* y, in
 {
   WFX_API_BEGIN
   apply_any(op, x, nullptr, y, beta, stream);
+  WFX_API_END
+}
+
+extern "C" int wfx_stiffness_apply_part(wfx_stiffness* op, const void* x, const void* scale, void* y,
+                                        int beta, int part, void* stream)
+{
+  WFX_API_BEGIN
+  if (!op) fail("stiffness operator is NULL");
+  if (part < -1 || part > 1) fail("part must be -1, 0 or 1");
+  if (op->mode == WFX_STIFF_CELL_COLOUR && part >= 0) fail("stiffness: parts need the brick kernel");
+  if (op->ncells == 0 && part == 1) return 0;
+  op->cur_part = part;
+  try
+  {
+    apply_any(op, x, scale, y, beta, stream);
+  }
+  catch (...)
+  {
+    op->cur_part = -1;
+    throw;
+  }
+  op->cur_part = -1;
   WFX_API_END
 }
 

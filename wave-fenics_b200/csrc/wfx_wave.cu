@@ -28,6 +28,15 @@ struct wfx_wave
   const void* minv = nullptr;
   // u_, v_: solution; u0, v0: start of step; un, vn: stage state; b: right-hand side
   DevBuf<unsigned char> u_, v_, u0, v0, un, vn, b;
+  // distributed runs: the ghost reduction runs on its own stream, ordered by events
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_iface = nullptr, ev_halo = nullptr;
+  ~wfx_wave()
+  {
+    if (ev_iface) cudaEventDestroy(ev_iface);
+    if (ev_halo) cudaEventDestroy(ev_halo);
+    if (comm_stream) cudaStreamDestroy(comm_stream);
+  }
 };
 
 namespace
@@ -117,6 +126,19 @@ extern "C" int wfx_wave_create(wfx_ctx* ctx, wfx_stiffness* stiff, wfx_mass* mas
   w->f0 = f0;
   w->p0 = p0;
   w->dtype = stiffness_dtype(stiff);
+  if (halo)
+  {
+    // m.scatter_rev(add) (LinearGLL.hpp:110) and the same for the facet masses; both idempotent
+    // (they need an fp64 halo: an fp32 model must have assembled them beforehand)
+    if (halo_dtype(halo) == WFX_F64)
+    {
+      if (wfx_mass_assemble(mass, halo)) fail("%s", wfx_last_error());
+      if (bnd && wfx_boundary_assemble(bnd, halo)) fail("%s", wfx_last_error());
+    }
+    WFX_CUDA(cudaStreamCreateWithFlags(&w->comm_stream, cudaStreamNonBlocking));
+    WFX_CUDA(cudaEventCreateWithFlags(&w->ev_iface, cudaEventDisableTiming));
+    WFX_CUDA(cudaEventCreateWithFlags(&w->ev_halo, cudaEventDisableTiming));
+  }
   if (wfx_mass_inverse_diagonal(mass, &w->minv)) fail("%s", wfx_last_error());
   const size_t nb = (size_t)ndofs * (w->dtype == WFX_F64 ? 8 : 4);
   for (auto* v : {&w->u_, &w->v_, &w->u0, &w->v0, &w->un, &w->vn, &w->b})
@@ -196,9 +218,27 @@ extern "C" int wfx_wave_rk4(wfx_wave* w, double t0, double tf, double dt, int64_
       // f1 (:151-192)
       const double window = tn < T * alpha ? 0.5 * (1.0 - std::cos(w->f0 * M_PI * tn / alpha)) : 1.0;
       const double g = window * w->p0 * w0 / w->c0 * std::cos(w0 * tn); // :162
-      if (wfx_stiffness_apply(w->stiff, un, w->b.p, 0, st)) fail("%s", wfx_last_error()); // :173-174
-      if (w->bnd && wfx_boundary_apply(w->bnd, w->c0, g, vn, w->b.p, st)) fail("%s", wfx_last_error()); // :175
-      if (w->halo && wfx_halo_update_rev_fwd(w->halo, w->b.p, st)) fail("%s", wfx_last_error()); // :176 (+ :164,167 of the next stage)
+      if (!w->halo)
+      {
+        if (wfx_stiffness_apply(w->stiff, un, w->b.p, 0, st)) fail("%s", wfx_last_error()); // :173-174
+        if (w->bnd && wfx_boundary_apply(w->bnd, w->c0, g, vn, w->b.p, st)) fail("%s", wfx_last_error()); // :175
+      }
+      else
+      {
+        // distributed: interface cells first, their ghost reduction (:176, which also stands
+        // for the scatter_fwd of the next stage, :164,167) on the comm stream while the interior
+        // cells run; the boundary term (facet masses assembled over the ranks) is added by
+        // every copy of a dof after the reduction.
+        const bool split = stiffness_has_split(w->stiff);
+        if (wfx_stiffness_apply_part(w->stiff, un, nullptr, w->b.p, 0, split ? 0 : -1, st)) fail("%s", wfx_last_error());
+        WFX_CUDA(cudaEventRecord(w->ev_iface, st));
+        WFX_CUDA(cudaStreamWaitEvent(w->comm_stream, w->ev_iface, 0));
+        if (wfx_halo_update_rev_fwd(w->halo, w->b.p, w->comm_stream)) fail("%s", wfx_last_error());
+        WFX_CUDA(cudaEventRecord(w->ev_halo, w->comm_stream));
+        if (split && wfx_stiffness_apply_part(w->stiff, un, nullptr, w->b.p, 0, 1, st)) fail("%s", wfx_last_error());
+        WFX_CUDA(cudaStreamWaitEvent(st, w->ev_halo, 0));
+        if (w->bnd && wfx_boundary_apply(w->bnd, w->c0, g, vn, w->b.p, st)) fail("%s", wfx_last_error());
+      }
       if (w->dtype == WFX_F64)
         launch_stage<double>(i, w->n, w->b.p, w->minv, w->u_.p, w->v_.p, w->u0.p, w->v0.p, w->un.p,
                              w->vn.p, dt * b_runge[i], dt * a_runge[i + 1], st);

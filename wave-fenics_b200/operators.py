@@ -141,8 +141,14 @@ class StiffnessOperator(_Operator):
         self.c0 = c0
         self.handle = C.c_void_p()
         dm = np.ascontiguousarray(V.dofmap, dtype=np.int32)
-        capi.call("wfx_stiffness_create", self.ctx.handle, self.geometry.handle, self.ndofs,
-                  capi.i32p(dm.reshape(-1)), c0, mode, C.byref(self.handle))
+        # distributed mesh: the dofs that also live on another rank (halo send + receive lists)
+        halo = getattr(V, "halo", None) or {}
+        shared = None
+        if len(halo.get("send_indices", ())) or len(halo.get("recv_indices", ())):
+            shared = np.unique(np.concatenate([halo["send_indices"], halo["recv_indices"]])).astype(np.int32)
+        self.nshared = 0 if shared is None else len(shared)
+        capi.call("wfx_stiffness_create_partitioned", self.ctx.handle, self.geometry.handle, self.ndofs,
+                  capi.i32p(dm.reshape(-1)), c0, mode, self.nshared, capi.i32p(shared), C.byref(self.handle))
 
     def __call__(self, x, y):
         self.apply(x, y, beta=1)
@@ -154,6 +160,14 @@ class StiffnessOperator(_Operator):
         else:
             capi.call("wfx_stiffness_apply_host", self.handle, C.c_void_p(x.ctypes.data),
                       C.c_void_p(y.ctypes.data), int(beta))
+
+    def apply_part(self, x, y, part, beta=0, scale_ptr=None, stream=None):
+        """Distributed meshes: part 0 = cells touching rank-shared dofs, 1 = the rest, -1 = both.
+        scale_ptr (1/m) is applied on the last touch of NON-shared dofs only."""
+        self._check(x, y)
+        capi.call("wfx_stiffness_apply_part", self.handle, C.c_void_p(x.data_ptr()),
+                  C.c_void_p(scale_ptr) if scale_ptr else None, C.c_void_p(y.data_ptr()), int(beta),
+                  int(part), stream if stream is not None else _stream_ptr())
 
     def apply_scaled(self, x, scale_ptr, y):
         """y = scale .* (-c0^2 K x): the fused stiffness + lumped-mass-inverse apply."""

@@ -176,6 +176,13 @@ class Halo:
     def update_rev_fwd(self, x):
         self._run("wfx_halo_update_rev_fwd", x)
 
+    def update_rev_fwd_scaled(self, x, scale_ptr, stream=None):
+        """ghost -> owner add, owner multiplies the sum by scale (1/m), owner -> ghost copy"""
+        import torch
+        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        capi.call("wfx_halo_update_rev_fwd_scaled", self.handle, C.c_void_p(x.data_ptr()),
+                  C.c_void_p(scale_ptr), C.c_void_p(st))
+
     def __del__(self):
         if getattr(self, "handle", None):
             capi.lib.wfx_halo_destroy(self.handle)
