@@ -247,7 +247,8 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_rk = float(t.item())
         u_chk, _ = eqn.get_state()
-        assert np.isfinite(u_chk).all() and np.abs(u_chk).max() > 0
+        # (the wave starts at x = 0: ranks away from the source face are still at rest)
+        assert np.isfinite(u_chk).all() and (rank != 0 or np.abs(u_chk).max() > 0)
         # algorithmic bytes per step: 4 stages x (G + dofmap + read un +
         # write b) + the fused stage updates (10 + 11 + 11 + 7 vector passes)
         s8 = 8

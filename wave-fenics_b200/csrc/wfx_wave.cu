@@ -7,6 +7,7 @@
 #include "wfx_internal.h"
 
 #include <cmath>
+#include <cstdlib>
 
 using namespace wfx;
 
@@ -229,7 +230,8 @@ extern "C" int wfx_wave_rk4(wfx_wave* w, double t0, double tf, double dt, int64_
         // for the scatter_fwd of the next stage, :164,167) on the comm stream while the interior
         // cells run; the boundary term (facet masses assembled over the ranks) is added by
         // every copy of a dof after the reduction.
-        const bool split = stiffness_has_split(w->stiff);
+        static const bool overlap = [] { const char* e = std::getenv("WFX_WAVE_OVERLAP"); return !e || std::atoi(e) != 0; }();
+        const bool split = overlap && stiffness_has_split(w->stiff);
         if (wfx_stiffness_apply_part(w->stiff, un, nullptr, w->b.p, 0, split ? 0 : -1, st)) fail("%s", wfx_last_error());
         WFX_CUDA(cudaEventRecord(w->ev_iface, st));
         WFX_CUDA(cudaStreamWaitEvent(w->comm_stream, w->ev_iface, 0));
