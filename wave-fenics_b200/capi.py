@@ -194,5 +194,5 @@ def debug_plan_stats(P, dofmap, ndofs, centroid=None, brick_edge=4, W=8, nloc_ca
     call("wfx_debug_plan_stats", P, ncells, ndofs, i32p(dofmap.reshape(-1)), cptr, brick_edge, W,
          nloc_cap, stats.ctypes.data_as(_c_i64p))
     keys = ["cell_colours", "batches", "batch_colours", "nloc_max", "rounds", "padded_slots",
-            "private_dofs", "batch_dofs", "untouched"]
+            "private_dofs", "batch_dofs", "untouched", "regular_batches", "Sx", "Sy"]
     return dict(zip(keys, stats.tolist()))

@@ -17,6 +17,50 @@ inline int lowest_zero_bit(uint64_t m)
   if (~m == 0) return -1;
   return __builtin_ctzll(~m);
 }
+
+// ascending lattice position of 1-D dof a in the [0, 1, interior] ordering
+inline int ascpos(int a, int P) { return a == 0 ? 0 : (a == 1 ? P : a - 1); }
+
+// Strides (Sx, Sy) of the in-brick placement X*Sx + Y*Sy + Z: injective on the (P*be+1)^3 lattice
+// and, if possible, such that the lanes (i,j) of a cell hit distinct shared-memory banks when they
+// access one k-plane.  word_bytes = 8: 16 banks of 8 bytes per half-warp; 4: 32 banks per warp.
+struct Strides
+{
+  bool ok = false;
+  int Sx = 0, Sy = 0;
+};
+Strides find_strides(int P, int be, int word_bytes)
+{
+  const int n = P + 1, E = P * be + 1;
+  const int banks = word_bytes == 8 ? 16 : 32;
+  Strides best;
+  int best_conf = 1 << 30, best_cap = 1 << 30;
+  for (int Sy = E; Sy < E + 32; ++Sy)
+    for (int Sx = (E - 1) * Sy + E; Sx < (E - 1) * Sy + E + 32; ++Sx)
+    {
+      int conf = 0;
+      for (int g0 = 0; g0 < n * n; g0 += banks)
+      {
+        int cnt[32] = {0};
+        for (int lane = g0; lane < std::min(n * n, g0 + banks); ++lane)
+        {
+          const int bk = (ascpos(lane / n, P) * Sx + ascpos(lane % n, P) * Sy) % banks;
+          conf += cnt[bk]++;
+        }
+      }
+      const int cap = (E - 1) * (Sx + Sy) + E;
+      if (cap > E * E * E + (E * E * E) / 25) continue; // at most 4 % padding
+      if (conf < best_conf || (conf == best_conf && cap < best_cap))
+      {
+        best_conf = conf;
+        best_cap = cap;
+        best.Sx = Sx;
+        best.Sy = Sy;
+        best.ok = true;
+      }
+    }
+  return best;
+}
 } // namespace
 
 void build_cell_colour_plan(int nd, int64_t ncells, int64_t ndofs, const int32_t* tdm,
@@ -69,7 +113,7 @@ void verify_cell_colour_plan(const CellColourPlan& plan, int nd, int64_t ncells,
 
 void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
                       const float* centroid, int brick_edge, int W, int nloc_cap,
-                      BrickPlan& plan, const uint8_t* dof_shared)
+                      BrickPlan& plan, const uint8_t* dof_shared, int word_bytes)
 {
   const int n = P + 1, nd = n * n * n;
   if (ndofs > (int64_t)BD_MASK) fail("brick plan: more than 2^30 local dofs");
@@ -88,8 +132,10 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
   // ---- 1. spatial keys -------------------------------------------------------
   std::vector<uint64_t> key((size_t)ncells);
   std::vector<uint32_t> parity((size_t)ncells, 0);
+  std::vector<int32_t> cell_ijk; // integer grid coordinates of the cells (when centroids are given)
   if (centroid && ncells > 0)
   {
+    cell_ijk.resize((size_t)ncells * 3);
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (int64_t c = 0; c < ncells; ++c)
       for (int a = 0; a < 3; ++a)
@@ -115,6 +161,7 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
         if (ia > 0xFFFF) ia = 0xFFFF;
         b[a] = (uint64_t)(ia / brick_edge);
         loc[a] = (uint64_t)(ia % brick_edge);
+        cell_ijk[3 * c + a] = (int32_t)ia;
       }
       // brick coordinates in the high bits, in-brick position in the low bits
       key[c] = (b[0] << 44) | (b[1] << 28) | (b[2] << 12) | (loc[0] << 8) | (loc[1] << 4) | loc[2];
@@ -270,7 +317,12 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
   plan.dof_off.assign(nb + 1, 0);
   plan.round_off.assign(nb + 1, 0);
   std::vector<uint64_t> lmask;
-  std::vector<int> ccol;
+  std::vector<int> ccol, place;
+  std::vector<uint8_t> slot_used;
+  const bool have_coords = !cell_ijk.empty();
+  const Strides lay = have_coords ? find_strides(P, brick_edge, word_bytes) : Strides();
+  plan.Sx = lay.Sx;
+  plan.Sy = lay.Sy;
   for (int i = 0; i < nb; ++i)
   {
     const Batch& b = batches[i];
@@ -288,20 +340,80 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
         }
     }
     std::sort(uniq.begin(), uniq.end());
-    const int nloc = (int)uniq.size();
+    int nloc = (int)uniq.size();
     if (nloc > 65535) fail("brick plan: batch with %d dofs exceeds 16-bit local index", nloc);
-    plan.nloc_max = std::max(plan.nloc_max, nloc);
+    for (int l = 0; l < nloc; ++l) g2l[uniq[l]] = l;
+    // Placement of the batch dofs in the shared arrays.  Default: ascending global dof.  If the
+    // batch is a regular brick (every dof gets one consistent lattice coordinate from the
+    // integer cell coordinates and the tensor index of its points), place dof (X,Y,Z) at
+    // X*Sx + Y*Sy + Z with strides searched so that the per-cell gather / scatter of a k-plane
+    // (one lane per (i,j)) is free of shared-memory bank conflicts; unused positions are holes.
+    place.assign(nloc, -1);
+    int nslots = nloc;
+    if (have_coords && lay.ok)
+    {
+      const int E = P * brick_edge + 1;
+      int org[3] = {1 << 30, 1 << 30, 1 << 30};
+      for (int64_t p = b.begin; p < b.end; ++p)
+        for (int a = 0; a < 3; ++a) org[a] = std::min(org[a], cell_ijk[3 * (int64_t)order[p] + a]);
+      bool regular = true;
+      for (int64_t p = b.begin; p < b.end && regular; ++p)
+      {
+        const int32_t c = order[p];
+        const int32_t* d = tdm + (int64_t)c * nd;
+        int l3[3];
+        for (int a = 0; a < 3; ++a) l3[a] = cell_ijk[3 * (int64_t)c + a] - org[a];
+        if (l3[0] >= brick_edge || l3[1] >= brick_edge || l3[2] >= brick_edge) { regular = false; break; }
+        for (int k = 0; k < n && regular; ++k)
+          for (int ii = 0; ii < n && regular; ++ii)
+            for (int jj = 0; jj < n; ++jj)
+            {
+              const int X = P * l3[0] + ascpos(ii, P), Y = P * l3[1] + ascpos(jj, P), Z = P * l3[2] + ascpos(k, P);
+              const int ps = X * lay.Sx + Y * lay.Sy + Z;
+              int& cur = place[g2l[d[k * n * n + ii * n + jj]]];
+              if (cur >= 0 && cur != ps) { regular = false; break; }
+              cur = ps;
+            }
+      }
+      if (regular)
+      {
+        nslots = (E - 1) * (lay.Sx + lay.Sy) + E;
+        if (nslots > nloc_cap || nslots > 65535) regular = false;
+        // positions must be distinct
+        if (regular)
+        {
+          slot_used.assign(nslots, 0);
+          for (int l = 0; l < nloc && regular; ++l)
+          {
+            if (place[l] < 0 || place[l] >= nslots || slot_used[place[l]]) regular = false;
+            else slot_used[place[l]] = 1;
+          }
+        }
+      }
+      if (!regular)
+      {
+        nslots = nloc;
+        place.assign(nloc, -1);
+      }
+      else plan.n_regular++;
+    }
+    if (place.empty() || (nloc > 0 && place[0] < 0))
+      for (int l = 0; l < nloc; ++l) place[l] = l;
+    plan.nloc_max = std::max(plan.nloc_max, nslots);
+    const size_t base = plan.bdofs.size();
+    plan.bdofs.resize(base + nslots, BD_HOLE);
     for (int l = 0; l < nloc; ++l)
     {
       const int32_t d = uniq[l];
-      g2l[d] = l;
       uint32_t e = (uint32_t)d;
       if (cmin[d] == b.colour) e |= BD_FIRST;
       // shared dofs are complete only after the halo sum: never LAST (no fused scaling) here
       if (cmax[d] == b.colour && !(dof_shared && dof_shared[d])) e |= BD_LAST;
       if ((e & BD_FIRST) && (e & BD_LAST)) plan.n_private++;
-      plan.bdofs.push_back(e);
+      plan.bdofs[base + place[l]] = e;
+      g2l[d] = place[l]; // local index used by the cells = position in the shared arrays
     }
+    nloc = nslots;
     plan.dof_off[i + 1] = (int64_t)plan.bdofs.size();
     // colour the batch's cells so that cells of one round share no local dof
     lmask.assign(nloc, 0);
@@ -368,9 +480,9 @@ void verify_brick_plan(const BrickPlan& plan, const int32_t* tdm, const uint8_t*
       for (int64_t l = d0; l < d1; ++l)
       {
         const uint32_t e = plan.bdofs[l];
+        if (e == BD_HOLE) continue; // unused position of a regular-brick placement
         const int32_t d = (int32_t)(e & BD_MASK);
         if (d < 0 || d >= ndofs) fail("brick plan: dof out of range");
-        if (l > d0 && (plan.bdofs[l - 1] & BD_MASK) >= (uint32_t)d) fail("brick plan: batch dofs not ascending/unique");
         if (colour_stamp[d] == col) fail("brick plan: two batches of colour %d share dof %d", col, d);
         if (dof_shared && dof_shared[d] && col >= plan.part_split && plan.part_split > 0)
           fail("brick plan: interior batch touches shared dof %d", d);
@@ -457,6 +569,9 @@ extern "C" int wfx_debug_plan_stats(int P, int64_t ncells, int64_t ndofs,
     stats[6] = bp.n_private;
     stats[7] = (int64_t)bp.bdofs.size();
     stats[8] = (int64_t)bp.untouched.size();
+    stats[9] = bp.n_regular;
+    stats[10] = bp.Sx;
+    stats[11] = bp.Sy;
   }
   WFX_API_END
 }

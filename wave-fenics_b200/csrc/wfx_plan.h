@@ -23,6 +23,7 @@ namespace wfx
 constexpr uint32_t BD_FIRST = 1u << 30;
 constexpr uint32_t BD_LAST = 1u << 31;
 constexpr uint32_t BD_MASK = (1u << 30) - 1;
+constexpr uint32_t BD_HOLE = BD_MASK; // unused position in a batch's dof list (no flags set)
 
 struct CellColourPlan
 {
@@ -52,6 +53,8 @@ struct BrickPlan
   // statistics
   int64_t n_slots_padded = 0;
   int64_t n_private = 0;           // bdofs entries that are FIRST and LAST
+  int n_regular = 0;               // batches placed as regular bricks (bank-conflict-free layout)
+  int Sx = 0, Sy = 0;              // strides of that placement
 };
 
 // tdm: tensor-ordered dofmap in the kernels' k-major point order, [ncells][nd]
@@ -63,7 +66,7 @@ void build_cell_colour_plan(int nd, int64_t ncells, int64_t ndofs, const int32_t
 // shared-memory dof arrays.
 void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
                       const float* centroid, int brick_edge, int W, int nloc_cap,
-                      BrickPlan& plan, const uint8_t* dof_shared = nullptr);
+                      BrickPlan& plan, const uint8_t* dof_shared = nullptr, int word_bytes = 8);
 
 // Checks every invariant the kernels rely on; throws wfx::Error on violation.
 void verify_brick_plan(const BrickPlan& plan, const int32_t* tdm, const uint8_t* dof_shared = nullptr);

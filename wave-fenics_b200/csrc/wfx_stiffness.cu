@@ -382,14 +382,13 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   {
     uint32_t e[U];
 #pragma unroll
-    for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? __ldg(a.bdofs + d0 + base + q * NT) : 0u;
+    for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? __ldg(a.bdofs + d0 + base + q * NT) : BD_HOLE;
 #pragma unroll
     for (int q = 0; q < U; ++q)
-      if (base + q * NT < nloc)
-      {
-        cp_async_scalar(xl + base + q * NT, a.x + (e[q] & BD_MASK));
-        yl[base + q * NT] = T(0);
-      }
+    {
+      if (e[q] != BD_HOLE) cp_async_scalar(xl + base + q * NT, a.x + (e[q] & BD_MASK));
+      if (base + q * NT < nloc) yl[base + q * NT] = T(0);
+    }
   }
   cp_async_wait_all();
   if (nr > 0) mbar_wait(bar, 0);
@@ -438,7 +437,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
     uint32_t e[U];
     T v[U], sc[U];
 #pragma unroll
-    for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? __ldg(a.bdofs + d0 + base + q * NT) : BD_FIRST;
+    for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? __ldg(a.bdofs + d0 + base + q * NT) : BD_HOLE;
     if (base == tid)
     {
       pdl_wait(); // earlier colours have finished their writes to y
@@ -447,14 +446,14 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
 #pragma unroll
     for (int q = 0; q < U; ++q)
     {
-      const bool ok = base + q * NT < nloc;
+      const bool ok = e[q] != BD_HOLE; // in range and a real dof (regular bricks have unused positions)
       const uint32_t dof = e[q] & BD_MASK;
       v[q] = (ok && (!(e[q] & BD_FIRST) || a.beta)) ? a.y[dof] : T(0);
       sc[q] = (ok && (e[q] & BD_LAST) && a.scale) ? __ldg(a.scale + dof) : T(1);
     }
 #pragma unroll
     for (int q = 0; q < U; ++q)
-      if (base + q * NT < nloc) a.y[e[q] & BD_MASK] = (v[q] + yl[base + q * NT]) * sc[q];
+      if (e[q] != BD_HOLE) a.y[e[q] & BD_MASK] = (v[q] + yl[base + q * NT]) * sc[q];
   }
   if (nloc <= tid) pdl_wait(); // threads without a batch dof still honour the dependency
   tm.mark(9);
@@ -542,10 +541,10 @@ stiff_brick_persistent(const BrickArgs<T> a, const PersistArgs pa, const DMat<T,
     {
       uint32_t e[U];
 #pragma unroll
-      for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? __ldg(a.bdofs + d0 + base + q * NT) : 0u;
+      for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? __ldg(a.bdofs + d0 + base + q * NT) : BD_HOLE;
 #pragma unroll
       for (int q = 0; q < U; ++q)
-        if (base + q * NT < nloc) cp_async_scalar(xl + base + q * NT, a.x + (e[q] & BD_MASK));
+        if (e[q] != BD_HOLE) cp_async_scalar(xl + base + q * NT, a.x + (e[q] & BD_MASK));
     }
   };
 
@@ -634,20 +633,20 @@ stiff_brick_persistent(const BrickArgs<T> a, const PersistArgs pa, const DMat<T,
       uint32_t e[U];
       T v[U], sc[U];
 #pragma unroll
-      for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? __ldg(a.bdofs + d0 + base + q * NT) : BD_FIRST;
+      for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? __ldg(a.bdofs + d0 + base + q * NT) : BD_HOLE;
 #pragma unroll
       for (int q = 0; q < U; ++q)
-        sc[q] = (base + q * NT < nloc && (e[q] & BD_LAST) && a.scale) ? __ldg(a.scale + (e[q] & BD_MASK)) : T(1);
+        sc[q] = (e[q] != BD_HOLE && (e[q] & BD_LAST) && a.scale) ? __ldg(a.scale + (e[q] & BD_MASK)) : T(1);
 #pragma unroll
       for (int q = 0; q < U; ++q)
       {
-        const bool ok = base + q * NT < nloc;
+        const bool ok = e[q] != BD_HOLE;
         // y is written by other SMs inside this launch: bypass L1
         v[q] = (ok && (!(e[q] & BD_FIRST) || a.beta)) ? __ldcg(a.y + (e[q] & BD_MASK)) : T(0);
       }
 #pragma unroll
       for (int q = 0; q < U; ++q)
-        if (base + q * NT < nloc)
+        if (e[q] != BD_HOLE)
         {
           a.y[e[q] & BD_MASK] = (v[q] + yl[base + q * NT]) * sc[q];
           yl[base + q * NT] = T(0);
@@ -1030,7 +1029,7 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
       BrickPlan bp;
       build_brick_plan(op->P, op->ncells, ndofs, tdm.data(),
                        geom->centroid.empty() ? nullptr : geom->centroid.data(), be, lc.W, nloc_cap, bp,
-                       shared.empty() ? nullptr : shared.data());
+                       shared.empty() ? nullptr : shared.data(), (int)esz);
       op->ncolours = bp.ncolours;
       op->part_split = bp.part_split;
       op->colour_off = bp.colour_off;
