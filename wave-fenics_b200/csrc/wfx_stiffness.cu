@@ -55,6 +55,17 @@ __device__ __forceinline__ void cp_async_scalar(float* dst_smem, const float* sr
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// fire-and-forget prefetches into L2: a contiguous block (bytes multiple of 16, one request), or
+// the line holding one address
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#ifndef WFX_PF_DIST
+#define WFX_PF_DIST 1 // measured at 64^3 P4 fp64: 1 -> 0.604 ms, 2 -> 0.619, 3 -> 0.631, 4 -> 0.650, none -> 0.695
+#endif
+constexpr int PF_DIST = WFX_PF_DIST; // rounds the L2 prefetch of G runs ahead of the register loads
 // one-shot TMA bulk copy global -> shared with mbarrier completion (bytes multiple of 16)
 __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar)
 {
@@ -333,6 +344,7 @@ struct BrickArgs
   int beta;       // 0: FIRST touch overwrites y; 1: accumulates into y
   int nloc_pad;   // capacity of the shared dof arrays (even)
   int rounds_max; // capacity (rounds) of the shared local-dofmap staging area
+  int pf_stride;  // CTAs resident on the GPU at once (for the cross-CTA L2 prefetch)
 };
 
 // Shared memory of one CTA:  xl[nloc_pad] | yl[nloc_pad] | tiles[W][slot_elems] | sldm[rounds_max*W*NDP] (u16)
@@ -370,12 +382,19 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
 
   // the batch's local dofmap: one TMA bulk copy, waited for after the dofs are staged
   if (tid == 0 && nr > 0) bulk_copy_g2s(sldm, a.ldm + (int64_t)r0 * W * NDP, (uint32_t)(nr * W * NDP * 2), bar);
-  // G of the first cell is requested before anything else is staged
+  // The G of the first 1 + PF_DIST rounds goes to L2 by bulk prefetch (one request per cell): the
+  // register loads issued later are then L2 hits and leave the SM's load queue quickly.  The
+  // register load of the first cell itself is issued after the dof gather below, so that the
+  // latency-critical index loads of the staging are not queued behind it.
   V2 g[N][3];
-  {
-    const int c0 = nr > 0 ? __ldg(a.slot_cell + (int64_t)r0 * W + slot) : -1;
-    if (lane_ok && c0 >= 0) load_G<T, N>(a.G6 + (int64_t)c0 * (6 * ND), col, g);
-  }
+  const int c0 = nr > 0 ? __ldg(a.slot_cell + (int64_t)r0 * W + slot) : -1;
+  if constexpr ((6 * ND * sizeof(T)) % 16 == 0)
+    if (col == 0)
+      for (int q = 0; q <= PF_DIST && q < nr; ++q)
+      {
+        const int cq = q == 0 ? c0 : __ldg(a.slot_cell + (int64_t)(r0 + q) * W + slot);
+        if (cq >= 0) l2_prefetch_bulk(a.G6 + (int64_t)cq * (6 * ND), (uint32_t)(6 * ND * sizeof(T)));
+      }
   for (int v = tid; v < nr * W; v += NT) scell[v] = __ldg(a.slot_cell + (int64_t)r0 * W + v);
   // stage the batch's dofs: U independent index loads, then U asynchronous gathers into xl
   for (int base = tid; base < nloc; base += NT * U)
@@ -389,7 +408,18 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
       if (e[q] != BD_HOLE) cp_async_scalar(xl + base + q * NT, a.x + (e[q] & BD_MASK));
       if (base + q * NT < nloc) yl[base + q * NT] = T(0);
     }
+#ifdef WFX_PF_WRITEBACK
+    // what the write-back will read (y of non-FIRST dofs, the scaling of LAST dofs): into L2 now
+#pragma unroll
+    for (int q = 0; q < U; ++q)
+      if (e[q] != BD_HOLE)
+      {
+        if (!(e[q] & BD_FIRST) || a.beta) l2_prefetch(a.y + (e[q] & BD_MASK));
+        if ((e[q] & BD_LAST) && a.scale) l2_prefetch(a.scale + (e[q] & BD_MASK));
+      }
+#endif
   }
+  if (lane_ok && c0 >= 0) load_G<T, N>(a.G6 + (int64_t)c0 * (6 * ND), col, g);
   cp_async_wait_all();
   if (nr > 0) mbar_wait(bar, 0);
   __syncthreads();
@@ -417,6 +447,36 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
     {
       const int cn = r + 1 < nr ? scell[(r + 1) * W + slot] : -1;
       if (lane_ok && cn >= 0) load_G<T, N>(a.G6 + (int64_t)cn * (6 * ND), col, g);
+      // keep the L2 prefetch PF_DIST rounds ahead of the register loads
+      if constexpr ((6 * ND * sizeof(T)) % 16 == 0)
+        if (col == 0 && r + 1 + PF_DIST < nr)
+        {
+          const int c2 = scell[(r + 1 + PF_DIST) * W + slot];
+          if (c2 >= 0) l2_prefetch_bulk(a.G6 + (int64_t)c2 * (6 * ND), (uint32_t)(6 * ND * sizeof(T)));
+        }
+#ifndef WFX_NO_PF_NEXT_CTA
+      // In the last round, warm L2 for the CTA that will take this one's place on the SM
+      // (blocks are dispatched in index order, a.pf_stride of them are resident): the first
+      // cells' G, the batch's dof list and its local dofmap -- what that CTA waits for first.
+      if (r == nr - 1 && col == 0 && (int)blockIdx.x + a.pf_stride < (int)gridDim.x)
+      {
+        const int bn = b + a.pf_stride;
+        const int r0n = __ldg(a.round_off + bn);
+        if constexpr ((6 * ND * sizeof(T)) % 16 == 0)
+        {
+          const int cq = __ldg(a.slot_cell + (int64_t)r0n * W + slot);
+          if (cq >= 0) l2_prefetch_bulk(a.G6 + (int64_t)cq * (6 * ND), (uint32_t)(6 * ND * sizeof(T)));
+        }
+        if (slot == 0)
+        {
+          const int64_t dn = __ldg(a.dof_off + bn);
+          const uint32_t nbytes = ((uint32_t)(__ldg(a.dof_off + bn + 1) - dn) * 4u) & ~15u;
+          if (nbytes && (dn % 4) == 0) l2_prefetch_bulk(a.bdofs + dn, nbytes);
+          const uint32_t lbytes = (uint32_t)((__ldg(a.round_off + bn + 1) - r0n) * W * NDP * 2);
+          if (lbytes) l2_prefetch_bulk(a.ldm + (int64_t)r0n * W * NDP, lbytes);
+        }
+      }
+#endif
     }
     tm.mark(4);
     if constexpr (SLOT <= 32) cell_part2<T, N>(f2, tiles, ro, Dm, active, WarpSync(), yv, tm);
@@ -793,6 +853,7 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   a.beta = beta;
   a.nloc_pad = op->nloc_pad;
   a.rounds_max = op->rounds_max;
+  a.pf_stride = C::MINB * op->ctx->num_sms;
   if (!beta && op->d_untouched.n && op->cur_part != 1)
   {
     const int n = (int)op->d_untouched.n;
