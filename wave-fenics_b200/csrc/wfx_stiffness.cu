@@ -345,6 +345,8 @@ struct BrickArgs
   int nloc_pad;   // capacity of the shared dof arrays (even)
   int rounds_max; // capacity (rounds) of the shared local-dofmap staging area
   int pf_stride;  // CTAs resident on the GPU at once (for the cross-CTA L2 prefetch)
+  const int64_t* run_off; // per batch: runs of consecutive dofs (nullable)
+  const uint32_t* runs;   // (first dof, length) pairs
 };
 
 // Shared memory of one CTA:  xl[nloc_pad] | yl[nloc_pad] | tiles[W][slot_elems] | sldm[rounds_max*W*NDP] (u16)
@@ -474,6 +476,29 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
           if (nbytes && (dn % 4) == 0) l2_prefetch_bulk(a.bdofs + dn, nbytes);
           const uint32_t lbytes = (uint32_t)((__ldg(a.round_off + bn + 1) - r0n) * W * NDP * 2);
           if (lbytes) l2_prefetch_bulk(a.ldm + (int64_t)r0n * W * NDP, lbytes);
+        }
+      }
+#endif
+#ifdef WFX_PF_RUNS // measured neutral-to-slower in round 1 (0.619 vs 0.609 ms): off by default
+      // Runs of consecutive dofs: bulk L2 prefetch of what will be gathered / read element-wise.
+      // Last round: the x entries of the CTA that follows this one on the SM.  Half-way: the
+      // scaling (1/m) entries this CTA's own write-back will read.
+      if (a.runs)
+      {
+        const bool for_next = r == nr - 1 && (int)blockIdx.x + a.pf_stride < (int)gridDim.x;
+        const bool for_own = a.scale && r == nr / 2;
+        if (for_next || for_own)
+        {
+          const int bb = for_next ? b + a.pf_stride : b;
+          const T* vec = for_next ? a.x : a.scale;
+          const int64_t q1 = __ldg(a.run_off + bb + 1);
+          for (int64_t q = __ldg(a.run_off + bb) + tid; q < q1; q += NT)
+          {
+            const uint32_t s = __ldg(a.runs + 2 * q), len = __ldg(a.runs + 2 * q + 1);
+            const uintptr_t lo = reinterpret_cast<uintptr_t>(vec + s) & ~(uintptr_t)15;
+            const uintptr_t hi = (reinterpret_cast<uintptr_t>(vec + s + len) + 15) & ~(uintptr_t)15;
+            l2_prefetch_bulk(reinterpret_cast<const void*>(lo), (uint32_t)(hi - lo));
+          }
         }
       }
 #endif
@@ -799,6 +824,8 @@ struct wfx_stiffness
   DevBuf<uint32_t> d_bdofs;
   DevBuf<int32_t> d_round_off, d_slot_cell, d_untouched;
   DevBuf<uint16_t> d_ldm;
+  DevBuf<int64_t> d_run_off;
+  DevBuf<uint32_t> d_runs;
   // persistent (single cooperative launch) form: experimental, WFX_PERSISTENT=1.  Measured slower
   // than the chained colour launches in round 1 (0.91 vs 0.70 ms at 64^3 P4: the write-back
   // phase runs 4x longer while the next batch's staging traffic is in flight), so it is off.
@@ -854,6 +881,8 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   a.nloc_pad = op->nloc_pad;
   a.rounds_max = op->rounds_max;
   a.pf_stride = C::MINB * op->ctx->num_sms;
+  a.run_off = op->d_runs.n ? op->d_run_off.p : nullptr;
+  a.runs = op->d_runs.n ? op->d_runs.p : nullptr;
   if (!beta && op->d_untouched.n && op->cur_part != 1)
   {
     const int n = (int)op->d_untouched.n;
@@ -1105,6 +1134,11 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
       op->d_round_off.upload(bp.round_off);
       op->d_slot_cell.upload(bp.slot_cell);
       op->d_ldm.upload(bp.ldm);
+      if (!bp.runs.empty())
+      {
+        op->d_run_off.upload(bp.run_off);
+        op->d_runs.upload(bp.runs);
+      }
       op->nbatches = bp.nbatches;
       {
         std::vector<uint8_t> bc((size_t)bp.nbatches);
