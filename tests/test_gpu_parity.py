@@ -327,3 +327,64 @@ def test_multi_gpu_halo_and_rk4(torch):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "mgpu_check ok" in r.stdout
+
+
+def test_planar3d_demo_full_run_matches_oracle(wfx, orc, torch):
+    """BASELINE config 1 (cpu_planar3d in miniature): the whole run to t_f = L/c0 + 8/f0 -- 1 000+
+    RK4 steps with source ramp, propagation and absorption -- against the oracle's time stepper."""
+    P, c0, f0, p0, Lx = 4, 1500.0, 0.5e6, 6e4, 0.1
+    nx = 24
+    side = Lx / nx
+    mesh = wfx.create_box_hex((nx, 1, 1), P, (Lx, side, side))
+    Go, detJ = orc.precompute_geometric_data(mesh, P)
+    m = np.zeros(mesh.ndofs)
+    orc.mass_apply(mesh, P, detJ, np.ones(mesh.ndofs), m)
+    m1, m2 = orc.boundary_facet_mass(mesh, P)
+    dt = wfx.cfl_timestep(mesh.h_min, c0, P, f0)
+    tf = Lx / c0 + 8.0 / f0
+    uo, vo = np.zeros(mesh.ndofs), np.zeros(mesh.ndofs)
+    so, to = orc.rk4(mesh, P, Go, m, m1, m2, c0, f0, p0, 0.0, tf, dt, uo, vo, sumfact=True,
+                     nthreads=orc.max_threads())
+    eqn = wfx.LinearGLLOpt(mesh, None, P, c0, f0, p0)
+    eqn.init()
+    s, t = eqn.rk4(0.0, tf, dt)
+    u, v = eqn.get_state()
+    assert s == so and s > 300 and t == to
+    assert np.abs(uo).max() > 1e3  # the wave (kPa scale) has crossed the domain
+    assert rel_l2(u, uo) < TOL64 and rel_l2(v, vo) < TOL64
+
+
+def test_stiffness_interface_interior_split(wfx, orc, torch):
+    """The distributed-mesh schedule on one GPU: with an (artificial) set of rank-shared dofs the
+    interface part followed by the interior part equals the plain apply, and the fused scaling
+    skips exactly the shared dofs."""
+    import copy
+    P = 4
+    mesh = copy.copy(_mesh(wfx, 6, P))
+    M = P * 6 + 1
+    shared = (np.arange(M * M) + (M // 2) * M * M).astype(np.int32)  # the lattice plane x = L/2
+    mesh.halo = {"send_indices": shared, "recv_indices": np.zeros(0, dtype=np.int32)}
+    geo = wfx.Geometry(mesh, P)
+    op = wfx.StiffnessOperator(mesh, P, geometry=geo)
+    assert op.nshared == len(shared) and op.info()["ncolours"] == 16
+    mass = wfx.MassOperator(mesh, P, geometry=geo)
+    Go, _ = orc.precompute_geometric_data(mesh, P)
+    x = np.random.default_rng(5).standard_normal(mesh.ndofs)
+    kx = np.zeros(mesh.ndofs)
+    orc.stiffness_apply(mesh, P, Go, x, kx, dense=False)
+    xd = dev(torch, x)
+    y = torch.full((mesh.ndofs,), float("nan"), dtype=torch.float64, device="cuda")
+    op.apply_part(xd, y, 0)
+    got0 = y.cpu().numpy()
+    # after the interface part every shared dof is complete, interior-only dofs are untouched
+    assert rel_l2(got0[shared], kx[shared]) < TOL64
+    op.apply_part(xd, y, 1)
+    assert rel_l2(y.cpu().numpy(), kx) < TOL64
+    y2 = torch.full_like(y, float("nan"))
+    op.apply(xd, y2, beta=0)  # both parts in one call
+    assert torch.equal(y, y2)
+    y3 = torch.full_like(y, float("nan"))
+    op.apply_scaled(xd, mass.inverse_diagonal_ptr(), y3)
+    want = kx / mass.diagonal()
+    want[shared] = kx[shared]  # shared dofs are left for the ghost reduction to scale
+    assert rel_l2(y3.cpu().numpy(), want) < TOL64
