@@ -5,16 +5,19 @@
 // scatter chain of the hackathon GPU operators (common/cuda/mass.hpp:76-95,
 // common/cuda/scatter.cu:38-45), which becomes one kernel with an atomic-free scatter.
 //
-// Thread mapping: one thread per (i,j) column of a cell, the n values along k live in
-// registers.  The k-direction contraction is register-only, the i- and j-direction
-// contractions exchange data through a per-cell shared-memory tile.  G (symmetric, 6
-// entries per point) streams from HBM exactly once as 128-bit loads.
+// Thread mapping: the N^2 threads of a cell each own one grid line per direction ("three
+// roles", see cell_part1); a 1-D contraction is register-only with the derivative matrix in the
+// kernel-parameter constant bank, lines are exchanged through two shared tiles transformed in
+// place.  G (symmetric, 6 entries per point) streams from HBM exactly once as 128-bit loads,
+// software-prefetched into registers one cell ahead and into L2 (bulk prefetch) one more.
 //
-// Two kernels:
-//   stiff_cell_kernel   simple: cells coloured, global gather / read-modify-write scatter
-//   stiff_brick_kernel  product path: one CTA per batch of cells (wfx_plan.h); batch dofs
-//                       staged in shared memory, each written back once; optional fused
-//                       diagonal scaling (the lumped-mass inverse) on the LAST touch.
+// Kernels:
+//   stiff_cell_kernel       simple: cells coloured, global gather / read-modify-write scatter
+//   stiff_brick_kernel      product path: one CTA per batch of cells (wfx_plan.h); batch dofs
+//                           staged in shared memory, each written back once; optional fused
+//                           diagonal scaling (the lumped-mass inverse) on the LAST touch; colours
+//                           are consecutive launches chained by programmatic dependent launch.
+//   stiff_brick_persistent  experimental single cooperative launch (off: measured slower).
 #include "wfx_internal.h"
 #include "wfx_plan.h"
 
