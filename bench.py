@@ -164,7 +164,8 @@ def run_b200(args):
 
     import ctypes as C
 
-    comm_stream = torch.cuda.Stream(device=dev) if halo is not None else None
+    # high priority: the small pack / NCCL / unpack kernels must not queue behind the interior batches
+    comm_stream = torch.cuda.Stream(device=dev, priority=-1) if halo is not None else None
 
     def step():
         if halo is None:

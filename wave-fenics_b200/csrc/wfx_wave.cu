@@ -136,7 +136,10 @@ extern "C" int wfx_wave_create(wfx_ctx* ctx, wfx_stiffness* stiff, wfx_mass* mas
       if (wfx_mass_assemble(mass, halo)) fail("%s", wfx_last_error());
       if (bnd && wfx_boundary_assemble(bnd, halo)) fail("%s", wfx_last_error());
     }
-    WFX_CUDA(cudaStreamCreateWithFlags(&w->comm_stream, cudaStreamNonBlocking));
+    // highest priority: the small pack / NCCL / unpack kernels must not queue behind the interior batches
+    int prio_lo = 0, prio_hi = 0;
+    WFX_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    WFX_CUDA(cudaStreamCreateWithPriority(&w->comm_stream, cudaStreamNonBlocking, prio_hi));
     WFX_CUDA(cudaEventCreateWithFlags(&w->ev_iface, cudaEventDisableTiming));
     WFX_CUDA(cudaEventCreateWithFlags(&w->ev_halo, cudaEventDisableTiming));
   }
