@@ -397,7 +397,9 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
         place.assign(nloc, -1);
       }
       else plan.n_regular++;
+      plan.batch_regular.push_back(regular ? 1 : 0);
     }
+    else plan.batch_regular.push_back(0);
     if (place.empty() || (nloc > 0 && place[0] < 0))
       for (int l = 0; l < nloc; ++l) place[l] = l;
     plan.nloc_max = std::max(plan.nloc_max, nslots);
@@ -456,6 +458,7 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
         if (filled == 0)
         {
           plan.slot_cell.resize(plan.slot_cell.size() + W, -1);
+          plan.slot_base.resize(plan.slot_base.size() + W, 0);
           plan.ldm.resize(plan.ldm.size() + (size_t)W * plan.ndp, 0);
           ++nrounds;
         }
@@ -464,6 +467,9 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
         plan.slot_cell[slot] = cell;
         const int32_t* d = tdm + (int64_t)cell * nd;
         for (int t = 0; t < nd; ++t) plan.ldm[slot * plan.ndp + t] = (uint16_t)g2l[d[t]];
+        // position of the cell's origin corner (point i=j=k=0): for a regular brick every other
+        // point of the cell is at a fixed offset from it (ascpos(i)*Sx + ascpos(j)*Sy + ascpos(k))
+        plan.slot_base[slot] = (uint16_t)g2l[d[0]];
         filled = (filled + 1) % W;
       }
     }
@@ -530,6 +536,17 @@ void verify_brick_plan(const BrickPlan& plan, const int32_t* tdm, const uint8_t*
             if (round_stamp[l] == r) fail("brick plan: two cells of one round share a dof");
           }
           for (int t = 0; t < nd; ++t) round_stamp[plan.ldm[slot * plan.ndp + t]] = r;
+          // regular bricks: the kernels compute positions arithmetically from the cell's base
+          if (!plan.batch_regular.empty() && plan.batch_regular[b])
+          {
+            const int n1 = plan.P + 1;
+            for (int k = 0; k < n1; ++k)
+              for (int i = 0; i < n1; ++i)
+                for (int j = 0; j < n1; ++j)
+                  if (plan.ldm[slot * plan.ndp + (k * n1 + i) * n1 + j]
+                      != plan.slot_base[slot] + ascpos(i, plan.P) * plan.Sx + ascpos(j, plan.P) * plan.Sy + ascpos(k, plan.P))
+                    fail("brick plan: regular batch with a non-arithmetic position");
+          }
         }
     }
   if (cells_total != ncells) fail("brick plan: %lld of %lld cells covered", (long long)cells_total, (long long)ncells);

@@ -48,6 +48,7 @@ struct BrickPlan
   std::vector<uint32_t> bdofs;     // global dof | BD_FIRST | BD_LAST, ascending per batch
   std::vector<int32_t> round_off;  // [nbatches+1] into rounds
   std::vector<int32_t> slot_cell;  // [nrounds_total*W] cell id or -1
+  std::vector<uint16_t> slot_base; // [nrounds_total*W] position of the cell's origin corner in the batch arrays
   std::vector<uint16_t> ldm;       // [nrounds_total*W][ndp] batch-local dof, k-major point order
   std::vector<int32_t> untouched;  // vector entries no cell references
   std::vector<int64_t> run_off;    // [nbatches+1] into runs (pairs)
@@ -56,6 +57,7 @@ struct BrickPlan
   int64_t n_slots_padded = 0;
   int64_t n_private = 0;           // bdofs entries that are FIRST and LAST
   int n_regular = 0;               // batches placed as regular bricks (bank-conflict-free layout)
+  std::vector<uint8_t> batch_regular; // [nbatches] 1 if the batch is a regular brick
   int Sx = 0, Sy = 0;              // strides of that placement
 };
 

@@ -264,6 +264,57 @@ __device__ __forceinline__ void cell_part1(const T (&u)[N], const typename Vec2<
   tm.mark(3);
 }
 
+// Part 1 when all three roles already hold their input line (regular bricks: the lines are
+// read straight from the batch's staged dofs): no tile round trip for u and one barrier less.
+template <typename T, int N, typename Sync>
+__device__ __forceinline__ void cell_part1_reg(const T (&u)[N], const T (&lj)[N], const T (&lI)[N],
+                                               const typename Vec2<T>::type (&g)[N][3],
+                                               T* __restrict__ tiles, const RoleOff& ro,
+                                               const DMat<T, N>& Dm, T coeff, bool active, Sync sync,
+                                               T (&f2)[N], PhaseTimer& tm)
+{
+  constexpr int PS_A = Tiles<N>::PS_A, PS_T = Tiles<N>::PS_T;
+  T* A = tiles;
+  T* AT = tiles + tile_a_elems<N>();
+  tm.mark(1);
+  if (active)
+  {
+#pragma unroll
+    for (int n = 0; n < N; ++n)
+    {
+      T s1 = 0, s0 = 0;
+#pragma unroll
+      for (int m = 0; m < N; ++m)
+      {
+        s1 += Dm.d[n * N + m] * lj[m];
+        s0 += Dm.d[n * N + m] * lI[m];
+      }
+      A[ro.rA + n] = s1;  // w1(i, n, k)
+      AT[ro.rT + n] = s0; // w0(n, j, k)
+    }
+  }
+  sync();
+  tm.mark(2);
+  if (active)
+  {
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+    {
+      T w2 = 0;
+#pragma unroll
+      for (int m = 0; m < N; ++m) w2 += Dm.d[k * N + m] * u[m];
+      const T w0 = AT[k * PS_T + ro.kT];
+      const T w1 = A[k * PS_A + ro.kA];
+      const T g00 = g[k][0].x, g01 = g[k][0].y, g02 = g[k][1].x;
+      const T g11 = g[k][1].y, g12 = g[k][2].x, g22 = g[k][2].y;
+      AT[k * PS_T + ro.kT] = coeff * (g00 * w0 + g01 * w1 + g02 * w2); // f0
+      A[k * PS_A + ro.kA] = coeff * (g01 * w0 + g11 * w1 + g12 * w2);  // f1
+      f2[k] = coeff * (g02 * w0 + g12 * w1 + g22 * w2);
+    }
+  }
+  tm.mark(3);
+}
+
 template <typename T, int N, typename Sync>
 __device__ __forceinline__ void cell_part2(const T (&f2)[N], T* __restrict__ tiles, const RoleOff& ro,
                                            const DMat<T, N>& Dm, bool active, Sync sync, T (&yv)[N],
@@ -350,11 +401,16 @@ struct BrickArgs
   int pf_stride;  // CTAs resident on the GPU at once (for the cross-CTA L2 prefetch)
   const int64_t* run_off; // per batch: runs of consecutive dofs (nullable)
   const uint32_t* runs;   // (first dof, length) pairs
+  const uint16_t* slot_base; // REG kernels: position of each slot's origin corner
+  int Sx, Sy;                // REG kernels: strides of the brick lattice in the shared arrays
 };
 
 // Shared memory of one CTA:  xl[nloc_pad] | yl[nloc_pad] | tiles[W][slot_elems] | sldm[rounds_max*W*NDP] (u16)
 //                            | scell[rounds_max*W] (i32) | mbarrier (u64)
-template <typename T, int N, int SLOT, int W, int MINB>
+// REG: every batch of the launch is a regular brick (wfx_plan): the positions of a cell's points
+// in the shared arrays are base + ascpos(i)*Sx + ascpos(j)*Sy + ascpos(k), so no local dofmap is
+// staged and all three roles read their input lines straight from xl (no tile round trip for u).
+template <typename T, int N, int SLOT, int W, int MINB, bool REG>
 __global__ void __launch_bounds__(SLOT* W, MINB)
 stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
 {
@@ -369,8 +425,11 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   T* work = yl + a.nloc_pad;
   // 16-byte aligned for the bulk copy below
   const size_t meta_off = ((size_t)(2 * a.nloc_pad + W * slot_elems<N>()) * sizeof(T) + 15) & ~(size_t)15;
+  // generic: sldm | scell | mbarrier.   REG: scell | sbase (u16)
   uint16_t* sldm = reinterpret_cast<uint16_t*>(smem_raw + meta_off);
-  int32_t* scell = reinterpret_cast<int32_t*>(sldm + (size_t)a.rounds_max * W * NDP);
+  int32_t* scell = REG ? reinterpret_cast<int32_t*>(smem_raw + meta_off)
+                       : reinterpret_cast<int32_t*>(sldm + (size_t)a.rounds_max * W * NDP);
+  uint16_t* sbase = reinterpret_cast<uint16_t*>(scell + (size_t)a.rounds_max * W);
   uint64_t* bar = reinterpret_cast<uint64_t*>(
       smem_raw + ((meta_off + (size_t)a.rounds_max * W * (NDP * 2 + 4) + 7) & ~(size_t)7));
   pdl_launch_dependents(); // the next colour may start staging; it waits before touching y
@@ -386,7 +445,21 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   const int r0 = __ldg(a.round_off + b), nr = __ldg(a.round_off + b + 1) - r0;
 
   // the batch's local dofmap: one TMA bulk copy, waited for after the dofs are staged
-  if (tid == 0 && nr > 0) bulk_copy_g2s(sldm, a.ldm + (int64_t)r0 * W * NDP, (uint32_t)(nr * W * NDP * 2), bar);
+  if constexpr (!REG)
+  {
+    if (tid == 0 && nr > 0) bulk_copy_g2s(sldm, a.ldm + (int64_t)r0 * W * NDP, (uint32_t)(nr * W * NDP * 2), bar);
+  }
+  else
+  {
+    for (int v = tid; v < nr * W; v += NT) sbase[v] = __ldg(a.slot_base + (int64_t)r0 * W + v);
+  }
+  // REG: offsets of this thread's three lines relative to the cell's base position
+  const int P1 = N - 1;
+  auto apos = [P1](int q) { return q == 0 ? 0 : (q == 1 ? P1 : q - 1); };
+  const int hi = (lane_ok ? col : 0) / N, lo = (lane_ok ? col : 0) % N;
+  const int offK = apos(hi) * a.Sx + apos(lo) * a.Sy; // role K: i = hi, j = lo, line over k (stride 1)
+  const int offJ = apos(lo) * a.Sx + apos(hi);        // role J: k = hi, i = lo, line over j (stride Sy)
+  const int offI = apos(lo) * a.Sy + apos(hi);        // role I: k = hi, j = lo, line over i (stride Sx)
   // The G of the first 1 + PF_DIST rounds goes to L2 by bulk prefetch (one request per cell): the
   // register loads issued later are then L2 hits and leave the SM's load queue quickly.  The
   // register load of the first cell itself is issued after the dof gather below, so that the
@@ -426,7 +499,8 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   }
   if (lane_ok && c0 >= 0) load_G<T, N>(a.G6 + (int64_t)c0 * (6 * ND), col, g);
   cp_async_wait_all();
-  if (nr > 0) mbar_wait(bar, 0);
+  if constexpr (!REG)
+    if (nr > 0) mbar_wait(bar, 0);
   __syncthreads();
   tm.mark(0);
 
@@ -435,18 +509,39 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   {
     const int cell = scell[r * W + slot];
     const bool active = lane_ok && cell >= 0;
-    const uint16_t* lrow = sldm + (r * W + slot) * NDP + col;
     int li[N];
     T u[N], yv[N], f2[N];
-#pragma unroll
-    for (int k = 0; k < N; ++k)
+    if constexpr (REG)
     {
-      li[k] = active ? (int)lrow[k * N2] : 0;
-      u[k] = active ? xl[li[k]] : T(0);
-      yv[k] = 0;
+      const int base = active ? (int)sbase[r * W + slot] : 0;
+      T lj[N], lI[N];
+#pragma unroll
+      for (int m = 0; m < N; ++m)
+      {
+        constexpr int P0 = N - 1;
+        const int am = m == 0 ? 0 : (m == 1 ? P0 : m - 1); // ascpos(m), compile-time after unrolling
+        li[m] = base + offK + am;
+        u[m] = active ? xl[li[m]] : T(0);
+        lj[m] = active ? xl[base + offJ + am * a.Sy] : T(0);
+        lI[m] = active ? xl[base + offI + am * a.Sx] : T(0);
+        yv[m] = 0;
+      }
+      if constexpr (SLOT <= 32) cell_part1_reg<T, N>(u, lj, lI, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2, tm);
+      else cell_part1_reg<T, N>(u, lj, lI, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2, tm);
     }
-    if constexpr (SLOT <= 32) cell_part1<T, N>(u, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2, tm);
-    else cell_part1<T, N>(u, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2, tm);
+    else
+    {
+      const uint16_t* lrow = sldm + (r * W + slot) * NDP + col;
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+      {
+        li[k] = active ? (int)lrow[k * N2] : 0;
+        u[k] = active ? xl[li[k]] : T(0);
+        yv[k] = 0;
+      }
+      if constexpr (SLOT <= 32) cell_part1<T, N>(u, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2, tm);
+      else cell_part1<T, N>(u, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2, tm);
+    }
     // G of this cell is consumed: request the next cell's G into the same registers so
     // that the loads fly during part 2 and the next gather
     {
@@ -477,8 +572,11 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
           const int64_t dn = __ldg(a.dof_off + bn);
           const uint32_t nbytes = ((uint32_t)(__ldg(a.dof_off + bn + 1) - dn) * 4u) & ~15u;
           if (nbytes && (dn % 4) == 0) l2_prefetch_bulk(a.bdofs + dn, nbytes);
-          const uint32_t lbytes = (uint32_t)((__ldg(a.round_off + bn + 1) - r0n) * W * NDP * 2);
-          if (lbytes) l2_prefetch_bulk(a.ldm + (int64_t)r0n * W * NDP, lbytes);
+          if constexpr (!REG)
+          {
+            const uint32_t lbytes = (uint32_t)((__ldg(a.round_off + bn + 1) - r0n) * W * NDP * 2);
+            if (lbytes) l2_prefetch_bulk(a.ldm + (int64_t)r0n * W * NDP, lbytes);
+          }
         }
       }
 #endif
@@ -827,6 +925,11 @@ struct wfx_stiffness
   DevBuf<uint32_t> d_bdofs;
   DevBuf<int32_t> d_round_off, d_slot_cell, d_untouched;
   DevBuf<uint16_t> d_ldm;
+  // regular-brick form (every batch a lattice brick): arithmetic positions, no staged dofmap
+  bool regular = false;
+  int Sx = 0, Sy = 0;
+  size_t smem_bytes_reg = 0;
+  DevBuf<uint16_t> d_slot_base;
   DevBuf<int64_t> d_run_off;
   DevBuf<uint32_t> d_runs;
   // persistent (single cooperative launch) form: experimental, WFX_PERSISTENT=1.  Measured slower
@@ -866,7 +969,10 @@ template <typename T, int N>
 void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta, cudaStream_t st)
 {
   using C = Cfg<N>;
-  auto kern = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB>;
+  const bool reg = op->regular && !op->persistent;
+  auto kern = reg ? stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true>
+                  : stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false>;
+  const size_t smem = reg ? op->smem_bytes_reg : op->smem_bytes;
   DMat<T, N> Dm;
   for (int q = 0; q < N * N; ++q) Dm.d[q] = (T)op->Dhost[q];
   BrickArgs<T> a;
@@ -886,6 +992,9 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   a.pf_stride = C::MINB * op->ctx->num_sms;
   a.run_off = op->d_runs.n ? op->d_run_off.p : nullptr;
   a.runs = op->d_runs.n ? op->d_runs.p : nullptr;
+  a.slot_base = op->d_slot_base.p;
+  a.Sx = op->Sx;
+  a.Sy = op->Sy;
   if (!beta && op->d_untouched.n && op->cur_part != 1)
   {
     const int n = (int)op->d_untouched.n;
@@ -923,7 +1032,7 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nb);
     cfg.blockDim = dim3(C::SLOT * C::W);
-    cfg.dynamicSmemBytes = op->smem_bytes;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -942,7 +1051,9 @@ template <typename T, int N>
 void configure_brick(wfx_stiffness* op)
 {
   using C = Cfg<N>;
-  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB>,
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->ctx->smem_optin));
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->ctx->smem_optin));
   WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persistent<T, N, C::SLOT, C::W, C::MINB>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->ctx->smem_optin));
@@ -1137,6 +1248,13 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
       op->d_round_off.upload(bp.round_off);
       op->d_slot_cell.upload(bp.slot_cell);
       op->d_ldm.upload(bp.ldm);
+      op->d_slot_base.upload(bp.slot_base);
+      op->Sx = bp.Sx;
+      op->Sy = bp.Sy;
+      op->regular = bp.nbatches > 0 && bp.n_regular == bp.nbatches;
+      if (const char* e = std::getenv("WFX_REGULAR")) op->regular = op->regular && std::atoi(e) != 0;
+      op->smem_bytes_reg = (((size_t)op->nloc_pad * 2 * esz + tiles_bytes + 15) & ~(size_t)15)
+                           + (size_t)bp.rounds_max * lc.W * 6 + 16;
       if (!bp.runs.empty())
       {
         op->d_run_off.upload(bp.run_off);
