@@ -103,7 +103,7 @@ def test_brick_plan_structured(wfx, P, N, be, W):
     assert s["cell_colours"] == 8
     # regular bricks are placed on a padded lattice (bank-conflict-free strides): a few holes
     full = (P * min(be, N) + 1) ** 3
-    assert full <= s["nloc_max"] <= 1.03 * (P * be + 1) ** 3
+    assert full <= s["nloc_max"] <= 1.07 * (P * be + 1) ** 3
     assert s["regular_batches"] == s["batches"]
     assert s["untouched"] == 0
     if N % be == 0 and be ** 3 // 8 >= W:

@@ -28,8 +28,8 @@ for _ in range(3):
 torch.cuda.synchronize()
 t = buf.cpu().numpy().reshape(nb * W, 12).astype(np.float64)
 names = ["0 staging", "1 gather+sync", "2 transform1+sync", "3 Gmult(+G wait)", "4 G prefetch issue",
-         "5 sync+transform2+sync", "6 combine+scatter", "7 round barrier", "8 pdl wait", "9 writeback"]
-tot = t[:, :10].sum(axis=1)
+         "5 sync+transform2+sync", "6 combine+scatter", "7 round barrier", "8 pdl wait", "9 writeback", "10 staging: issue", "11 staging: copies landed"]
+tot = t[:, :12].sum(axis=1)
 print(f"per-warp total cycles: mean {tot.mean():.0f}")
 for i, n in enumerate(names):
     print(f"  {n:26s} mean {t[:, i].mean():9.0f} cyc  {100 * t[:, i].mean() / tot.mean():5.1f}%   per cell {t[:, i].mean() / 8:7.0f}")

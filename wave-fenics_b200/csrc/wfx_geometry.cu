@@ -271,7 +271,7 @@ extern "C" int wfx_geometry_get(wfx_geom* g, double* G_host, double* detJ_host)
         for (int j = 0; j < n; ++j)
           for (int k = 0; k < n; ++k)
           {
-            const int col = i * n + j;
+            const int col = g->g_colpos.empty() ? i * n + j : g->g_colpos[i * n + j];
             double* dst = G_host + (c * nq + (i * n + j) * n + k) * 9;
             for (int a = 0; a < 3; ++a)
               for (int b = 0; b < 3; ++b)

@@ -127,7 +127,9 @@ struct wfx_ctx
 //   nq = n^3 points per cell, n = P+1, n2 = n^2.
 //   point index inside a cell is "k-major": r = k*n2 + (i*n + j) for tensor node (i,j,k)
 //   (i <-> x, slowest in the reference's tensor order; k <-> z).
-//   G6  [ncells][6][nq]  components (00,01,02,11,12,22), dtype T
+//   G6  [ncells][n][3][n2][2]  per k-plane three pairs (00,01) (02,11) (12,22) per column, dtype T;
+//       column of point (i,j) is i*n+j unless g_colpos is set (a stiffness operator may reorder
+//       the columns once, in place, to the lane order of its kernel: wfx_stiffness.cu)
 //   dJw [ncells][nq]     detJ * w, fp64 (setup-only consumers)
 struct wfx_geom
 {
@@ -135,6 +137,7 @@ struct wfx_geom
   int P = 0, n = 0, nq = 0, dtype = WFX_F64;
   int64_t ncells = 0;
   void* G6 = nullptr;     // T
+  std::vector<uint8_t> g_colpos; // empty: identity; else column of point (i,j) = g_colpos[i*n+j]
   double* dJw = nullptr;  // fp64
   // cell centroids (host) for the locality-preserving batch plan
   std::vector<float> centroid; // [ncells][3]

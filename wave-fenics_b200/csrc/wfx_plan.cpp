@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -26,14 +27,26 @@ inline int ascpos(int a, int P) { return a == 0 ? 0 : (a == 1 ? P : a - 1); }
 // access one k-plane.  word_bytes = 8: 16 banks of 8 bytes per half-warp; 4: 32 banks per warp.
 struct Strides
 {
-  bool ok = false;
+  bool ok = false, tuned = false;
   int Sx = 0, Sy = 0;
 };
-Strides find_strides(int P, int be, int word_bytes)
+Strides find_strides(int P, int be, int word_bytes, bool tuned)
 {
   const int n = P + 1, E = P * be + 1;
   const int banks = word_bytes == 8 ? 16 : 32;
   Strides best;
+  // Degree 4, 64-bit words: the kernel has a layout in which ALL of a cell's shared-memory
+  // accesses (three roles, dof arrays and tiles) are conflict-free; it needs Sx = 5, Sy = 2
+  // (mod 16), see tools/bank_layout_search.py.  Costs 7 % padding of the dof arrays.
+  if (tuned && P == 4 && word_bytes == 8)
+  {
+    best.Sy = E;
+    while (best.Sy % 16 != 2) ++best.Sy;
+    best.Sx = (E - 1) * best.Sy + E;
+    while (best.Sx % 16 != 5) ++best.Sx;
+    best.ok = best.tuned = true;
+    return best;
+  }
   int best_conf = 1 << 30, best_cap = 1 << 30;
   for (int Sy = E; Sy < E + 32; ++Sy)
     for (int Sx = (E - 1) * Sy + E; Sx < (E - 1) * Sy + E + 32; ++Sx)
@@ -113,7 +126,7 @@ void verify_cell_colour_plan(const CellColourPlan& plan, int nd, int64_t ncells,
 
 void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
                       const float* centroid, int brick_edge, int W, int nloc_cap,
-                      BrickPlan& plan, const uint8_t* dof_shared, int word_bytes)
+                      BrickPlan& plan, const uint8_t* dof_shared, int word_bytes, bool allow_tuned)
 {
   const int n = P + 1, nd = n * n * n;
   if (ndofs > (int64_t)BD_MASK) fail("brick plan: more than 2^30 local dofs");
@@ -321,7 +334,12 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
   std::vector<int> ccol, place;
   std::vector<uint8_t> slot_used;
   const bool have_coords = !cell_ijk.empty();
-  const Strides lay = have_coords ? find_strides(P, brick_edge, word_bytes) : Strides();
+  // Off by default: the 7 % padding pushes two resident CTAs over the 196 KB shared-memory
+  // carve-out step, L1 shrinks from 60 to 28 KB and the kernel loses 20 % (measured, round 1) --
+  // far more than the conflict-free layout gains.  WFX_TUNED_STRIDES=1 enables it for experiments.
+  bool want_tuned = false;
+  if (const char* ev = std::getenv("WFX_TUNED_STRIDES")) want_tuned = allow_tuned && std::atoi(ev) != 0;
+  const Strides lay = have_coords ? find_strides(P, brick_edge, word_bytes, want_tuned) : Strides();
   plan.Sx = lay.Sx;
   plan.Sy = lay.Sy;
   for (int i = 0; i < nb; ++i)
@@ -479,6 +497,14 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
   }
   plan.nrounds_total = plan.round_off[nb];
   plan.n_slots_padded = plan.nrounds_total * W - ncells;
+  // the tuned strides only pay off when every batch runs the regular-brick kernel; otherwise
+  // their padding just costs shared memory: plan again with the compact strides
+  if (lay.tuned && plan.n_regular != nb)
+  {
+    BrickPlan compact;
+    build_brick_plan(P, ncells, ndofs, tdm, centroid, brick_edge, W, nloc_cap, compact, dof_shared, word_bytes, false);
+    plan = std::move(compact);
+  }
 }
 
 void verify_brick_plan(const BrickPlan& plan, const int32_t* tdm, const uint8_t* dof_shared)

@@ -70,7 +70,8 @@ void build_cell_colour_plan(int nd, int64_t ncells, int64_t ndofs, const int32_t
 // shared-memory dof arrays.
 void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
                       const float* centroid, int brick_edge, int W, int nloc_cap,
-                      BrickPlan& plan, const uint8_t* dof_shared = nullptr, int word_bytes = 8);
+                      BrickPlan& plan, const uint8_t* dof_shared = nullptr, int word_bytes = 8,
+                      bool allow_tuned = true);
 
 // Checks every invariant the kernels rely on; throws wfx::Error on violation.
 void verify_brick_plan(const BrickPlan& plan, const int32_t* tdm, const uint8_t* dof_shared = nullptr);

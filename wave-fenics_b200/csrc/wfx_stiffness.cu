@@ -20,6 +20,7 @@
 //   stiff_brick_persistent  experimental single cooperative launch (off: measured slower).
 #include "wfx_internal.h"
 #include "wfx_plan.h"
+#include <type_traits>
 
 #include <algorithm>
 #include <cstdlib>
@@ -44,6 +45,27 @@ __device__ __forceinline__ float2 ld_stream(const float2* p)
 {
   float2 r;
   asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+
+// read-once scalar loads that leave L1 to the loads in flight (L1 is the landing buffer of the
+// G stream: its capacity bounds the bytes in flight per SM)
+__device__ __forceinline__ uint32_t ld_once(const uint32_t* p)
+{
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double ld_once(const double* p)
+{
+  double r;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ld_once(const float* p)
+{
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
   return r;
 }
 
@@ -158,6 +180,8 @@ struct RoleOff
 {
   int kA, kT; // role K: element (k) of this thread's column is A[k*PS_A + kA], AT[k*PS_T + kT]
   int rA, rT; // roles J / I: this thread's row starts at A[rA], AT[rT]
+  int colK;   // role K: i*N + j (column of G6 and of the local dofmap)
+  int iK, jK, kJ, iJ, kI, jI; // the lines this thread owns in the three roles
 };
 template <int N>
 __device__ __forceinline__ RoleOff role_offsets(int lane)
@@ -168,7 +192,75 @@ __device__ __forceinline__ RoleOff role_offsets(int lane)
   o.kT = Tiles<N>::boff(lo) + hi;
   o.rA = hi * Tiles<N>::PS_A + lo * N;      // role J: k = hi, i = lo, row over j
   o.rT = hi * Tiles<N>::PS_T + Tiles<N>::boff(lo); // role I: k = hi, j = lo, row over i
+  o.colK = lane;
+  o.iK = hi, o.jK = lo, o.kJ = hi, o.iJ = lo, o.kI = hi, o.jI = lo;
   return o;
+}
+
+// Layout policies: tile geometry + the lane -> line maps of the three roles.
+// LayoutStd: lane = hi*N + lo in all roles, rows stored in index order.
+template <int N>
+struct LayoutStd
+{
+  static constexpr int PS_A = Tiles<N>::PS_A, PS_T = Tiles<N>::PS_T;
+  static constexpr int AT_OFF = N * PS_A, SLOT_ELEMS = N * (PS_A + PS_T);
+  __host__ __device__ static constexpr int eA(int n) { return n; } // offset of element j = n in a row of A
+  __host__ __device__ static constexpr int eT(int n) { return n; } // offset of element i = n in a row of AT
+  __device__ static __forceinline__ RoleOff offsets(int lane) { return role_offsets<N>(lane); }
+};
+
+// LayoutP4D: degree 4, 64-bit words, regular bricks whose lattice strides are Sx = 5, Sy = 2
+// (mod 16).  Found by tools/bank_layout_search.py: with these lane maps every shared-memory
+// access of a cell -- the dof lines of roles K and J, the y accumulation, all tile rows and
+// columns -- is free of bank conflicts; role I's dof line costs 3 wavefronts instead of 2 (no
+// stride triple makes all three roles conflict-free).  Rows are 5 words at 5*a(.) inside a
+// 33-word plane, a() = ascending lattice position; row elements are permuted (eA / eT).
+__device__ __constant__ uint8_t c_p4d_lanes[6][25] = {
+    // role K lane -> i, j
+    {2, 2, 2, 3, 4, 4, 4, 3, 3, 0, 0, 1, 2, 2, 3, 3, 0, 0, 1, 1, 0, 4, 4, 1, 1},
+    {3, 4, 1, 3, 0, 2, 3, 4, 1, 3, 4, 3, 0, 2, 0, 2, 0, 2, 0, 2, 1, 4, 1, 4, 1},
+    // role J lane -> k, i
+    {0, 2, 3, 4, 1, 0, 2, 3, 4, 1, 0, 2, 3, 4, 1, 0, 2, 3, 4, 1, 0, 2, 3, 4, 1},
+    {0, 0, 0, 0, 0, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 1, 1, 1, 1, 1},
+    // role I lane -> k, j
+    {4, 0, 2, 3, 4, 1, 0, 1, 3, 3, 4, 2, 0, 2, 3, 2, 0, 2, 4, 0, 1, 1, 3, 4, 1},
+    {2, 3, 3, 3, 3, 3, 4, 4, 4, 0, 0, 4, 2, 2, 2, 1, 0, 0, 4, 1, 0, 1, 1, 1, 2}};
+struct LayoutP4D
+{
+  static constexpr int N = 5, PS_A = 33, PS_T = 33;
+  static constexpr int AT_OFF = N * PS_A, SLOT_ELEMS = N * (PS_A + PS_T);
+  static constexpr int SX_MOD = 5, SY_MOD = 2; // required lattice strides modulo 16
+  __host__ __device__ static constexpr int eA(int n) { return n == 0 ? 3 : n == 1 ? 2 : n == 2 ? 4 : n == 3 ? 0 : 1; }
+  __host__ __device__ static constexpr int eT(int n) { return n == 0 ? 0 : n == 1 ? 2 : n == 2 ? 1 : n; }
+  __host__ __device__ static constexpr int a(int q) { return q == 0 ? 0 : (q == 1 ? N - 1 : q - 1); }
+  __device__ static __forceinline__ RoleOff offsets(int lane)
+  {
+    RoleOff o;
+    o.iK = c_p4d_lanes[0][lane], o.jK = c_p4d_lanes[1][lane];
+    o.kJ = c_p4d_lanes[2][lane], o.iJ = c_p4d_lanes[3][lane];
+    o.kI = c_p4d_lanes[4][lane], o.jI = c_p4d_lanes[5][lane];
+    o.colK = o.iK * N + o.jK;
+    o.kA = 5 * a(o.iK) + eA(o.jK);
+    o.kT = 5 * a(o.jK) + eT(o.iK);
+    o.rA = o.kJ * PS_A + 5 * a(o.iJ);
+    o.rT = o.kI * PS_T + 5 * a(o.jI);
+    return o;
+  }
+};
+// column position of point (i,j) in a G6 whose columns were reordered to LayoutP4D's role K lanes
+__device__ __constant__ uint8_t c_p4d_colpos[25] = {16, 20, 17, 9, 10, 18, 24, 19, 11, 23, 12, 2, 13,
+                                                    0,  1,  14, 8, 15, 3,  7,  4,  22, 5,  6, 21};
+const uint8_t h_p4d_colpos[25] = {16, 20, 17, 9, 10, 18, 24, 19, 11, 23, 12, 2, 13,
+                                  0,  1,  14, 8, 15, 3,  7,  4,  22, 5,  6, 21};
+// G6 column this thread loads in role K (g_order: 0 = columns by i*N+j, 1 = LayoutP4D lane order)
+template <typename L, int N>
+__device__ __forceinline__ int g_column(const RoleOff& ro, int lane, int g_order)
+{
+  if constexpr (N == 5)
+  {
+    if (g_order) return std::is_same<L, LayoutP4D>::value ? lane : (int)c_p4d_colpos[ro.colK];
+  }
+  return ro.colK;
 }
 
 // G of one cell for this thread's column: [k][pair] 2-vectors, streamed once from HBM.
@@ -199,12 +291,13 @@ __device__ __forceinline__ void load_G(const T* __restrict__ Gc, int col,
 //          f = coeff * G w   (SURVEY.md App. A.9); f0 -> AT, f1 -> A, f2 stays in registers.
 // Part 2:  y(i,j,k) = sum_m D[m][i] f0(m,j,k) + D[m][j] f1(i,m,k) + D[m][k] f2(i,j,m).
 // Inactive threads (padding lanes / empty slots) only take part in the synchronisation.
-template <typename T, int N, bool TRANSPOSE>
+// L: layout policy; ROW_A: the row belongs to tile A (elements by j) or AT (elements by i)
+template <typename T, int N, bool TRANSPOSE, typename L, bool ROW_A>
 __device__ __forceinline__ void line_transform(T* __restrict__ row, const DMat<T, N>& Dm)
 {
   T l[N], o[N];
 #pragma unroll
-  for (int m = 0; m < N; ++m) l[m] = row[m];
+  for (int m = 0; m < N; ++m) l[m] = row[ROW_A ? L::eA(m) : L::eT(m)];
 #pragma unroll
   for (int n = 0; n < N; ++n)
   {
@@ -214,68 +307,82 @@ __device__ __forceinline__ void line_transform(T* __restrict__ row, const DMat<T
     o[n] = s;
   }
 #pragma unroll
-  for (int n = 0; n < N; ++n) row[n] = o[n];
+  for (int n = 0; n < N; ++n) row[ROW_A ? L::eA(n) : L::eT(n)] = o[n];
 }
 
-template <typename T, int N, typename Sync>
-__device__ __forceinline__ void cell_part1(const T (&u)[N], const typename Vec2<T>::type (&g)[N][3],
+// second half of part 1: w2 from the register line, w0 / w1 from the tiles, f = coeff * G w
+// gnext (nullable): this thread's column of the NEXT cell's G; plane k of it is requested into
+// g[k] as soon as plane k of the current cell is consumed, so the 3*N loads of a cell are spread
+// over the phase instead of hitting the load pipe (and L1, their landing buffer) in one burst.
+template <typename T, int N, typename L>
+__device__ __forceinline__ void g_multiply(const T (&u)[N], typename Vec2<T>::type (&g)[N][3],
+                                           T* __restrict__ A, T* __restrict__ AT, const RoleOff& ro,
+                                           const DMat<T, N>& Dm, T coeff, T (&f2)[N],
+                                           const typename Vec2<T>::type* gnext = nullptr)
+{
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+  {
+    T w2 = 0;
+#pragma unroll
+    for (int m = 0; m < N; ++m) w2 += Dm.d[k * N + m] * u[m];
+    const T w0 = AT[k * L::PS_T + ro.kT];
+    const T w1 = A[k * L::PS_A + ro.kA];
+    const T g00 = g[k][0].x, g01 = g[k][0].y, g02 = g[k][1].x;
+    const T g11 = g[k][1].y, g12 = g[k][2].x, g22 = g[k][2].y;
+    AT[k * L::PS_T + ro.kT] = coeff * (g00 * w0 + g01 * w1 + g02 * w2); // f0
+    A[k * L::PS_A + ro.kA] = coeff * (g01 * w0 + g11 * w1 + g12 * w2);  // f1
+    f2[k] = coeff * (g02 * w0 + g12 * w1 + g22 * w2);
+    if (gnext)
+    {
+#pragma unroll
+      for (int p = 0; p < 3; ++p) g[k][p] = ld_stream(gnext + (k * 3 + p) * (N * N));
+    }
+  }
+}
+
+template <typename T, int N, typename L, typename Sync>
+__device__ __forceinline__ void cell_part1(const T (&u)[N], typename Vec2<T>::type (&g)[N][3],
                                            T* __restrict__ tiles, const RoleOff& ro,
                                            const DMat<T, N>& Dm, T coeff, bool active, Sync sync,
                                            T (&f2)[N], PhaseTimer& tm)
 {
-  constexpr int PS_A = Tiles<N>::PS_A, PS_T = Tiles<N>::PS_T;
   T* A = tiles;
-  T* AT = tiles + tile_a_elems<N>();
+  T* AT = tiles + L::AT_OFF;
   if (active)
   {
 #pragma unroll
     for (int k = 0; k < N; ++k)
     {
-      A[k * PS_A + ro.kA] = u[k];
-      AT[k * PS_T + ro.kT] = u[k];
+      A[k * L::PS_A + ro.kA] = u[k];
+      AT[k * L::PS_T + ro.kT] = u[k];
     }
   }
   sync();
   tm.mark(1);
   if (active)
   {
-    line_transform<T, N, false>(A + ro.rA, Dm);  // u(i, ., k) -> w1(i, ., k)
-    line_transform<T, N, false>(AT + ro.rT, Dm); // u(., j, k) -> w0(., j, k)
+    line_transform<T, N, false, L, true>(A + ro.rA, Dm);   // u(i, ., k) -> w1(i, ., k)
+    line_transform<T, N, false, L, false>(AT + ro.rT, Dm); // u(., j, k) -> w0(., j, k)
   }
   sync();
   tm.mark(2);
-  if (active)
-  {
-#pragma unroll
-    for (int k = 0; k < N; ++k)
-    {
-      T w2 = 0;
-#pragma unroll
-      for (int m = 0; m < N; ++m) w2 += Dm.d[k * N + m] * u[m];
-      const T w0 = AT[k * PS_T + ro.kT];
-      const T w1 = A[k * PS_A + ro.kA];
-      const T g00 = g[k][0].x, g01 = g[k][0].y, g02 = g[k][1].x;
-      const T g11 = g[k][1].y, g12 = g[k][2].x, g22 = g[k][2].y;
-      AT[k * PS_T + ro.kT] = coeff * (g00 * w0 + g01 * w1 + g02 * w2); // f0
-      A[k * PS_A + ro.kA] = coeff * (g01 * w0 + g11 * w1 + g12 * w2);  // f1
-      f2[k] = coeff * (g02 * w0 + g12 * w1 + g22 * w2);
-    }
-  }
+  if (active) g_multiply<T, N, L>(u, g, A, AT, ro, Dm, coeff, f2);
   tm.mark(3);
 }
 
 // Part 1 when all three roles already hold their input line (regular bricks: the lines are
 // read straight from the batch's staged dofs): no tile round trip for u and one barrier less.
-template <typename T, int N, typename Sync>
+template <typename T, int N, typename L, typename Sync>
 __device__ __forceinline__ void cell_part1_reg(const T (&u)[N], const T (&lj)[N], const T (&lI)[N],
-                                               const typename Vec2<T>::type (&g)[N][3],
+                                               typename Vec2<T>::type (&g)[N][3],
                                                T* __restrict__ tiles, const RoleOff& ro,
                                                const DMat<T, N>& Dm, T coeff, bool active, Sync sync,
-                                               T (&f2)[N], PhaseTimer& tm)
+                                               T (&f2)[N], PhaseTimer& tm,
+                                               const typename Vec2<T>::type* gnext = nullptr)
 {
-  constexpr int PS_A = Tiles<N>::PS_A, PS_T = Tiles<N>::PS_T;
   T* A = tiles;
-  T* AT = tiles + tile_a_elems<N>();
+  T* AT = tiles + L::AT_OFF;
   tm.mark(1);
   if (active)
   {
@@ -289,45 +396,28 @@ __device__ __forceinline__ void cell_part1_reg(const T (&u)[N], const T (&lj)[N]
         s1 += Dm.d[n * N + m] * lj[m];
         s0 += Dm.d[n * N + m] * lI[m];
       }
-      A[ro.rA + n] = s1;  // w1(i, n, k)
-      AT[ro.rT + n] = s0; // w0(n, j, k)
+      A[ro.rA + L::eA(n)] = s1;  // w1(i, n, k)
+      AT[ro.rT + L::eT(n)] = s0; // w0(n, j, k)
     }
   }
   sync();
   tm.mark(2);
-  if (active)
-  {
-#pragma unroll
-    for (int k = 0; k < N; ++k)
-    {
-      T w2 = 0;
-#pragma unroll
-      for (int m = 0; m < N; ++m) w2 += Dm.d[k * N + m] * u[m];
-      const T w0 = AT[k * PS_T + ro.kT];
-      const T w1 = A[k * PS_A + ro.kA];
-      const T g00 = g[k][0].x, g01 = g[k][0].y, g02 = g[k][1].x;
-      const T g11 = g[k][1].y, g12 = g[k][2].x, g22 = g[k][2].y;
-      AT[k * PS_T + ro.kT] = coeff * (g00 * w0 + g01 * w1 + g02 * w2); // f0
-      A[k * PS_A + ro.kA] = coeff * (g01 * w0 + g11 * w1 + g12 * w2);  // f1
-      f2[k] = coeff * (g02 * w0 + g12 * w1 + g22 * w2);
-    }
-  }
+  if (active) g_multiply<T, N, L>(u, g, A, AT, ro, Dm, coeff, f2, gnext);
   tm.mark(3);
 }
 
-template <typename T, int N, typename Sync>
+template <typename T, int N, typename L, typename Sync>
 __device__ __forceinline__ void cell_part2(const T (&f2)[N], T* __restrict__ tiles, const RoleOff& ro,
                                            const DMat<T, N>& Dm, bool active, Sync sync, T (&yv)[N],
                                            PhaseTimer& tm)
 {
-  constexpr int PS_A = Tiles<N>::PS_A, PS_T = Tiles<N>::PS_T;
   T* A = tiles;
-  T* AT = tiles + tile_a_elems<N>();
+  T* AT = tiles + L::AT_OFF;
   sync(); // f0 / f1 visible
   if (active)
   {
-    line_transform<T, N, true>(A + ro.rA, Dm);  // f1(i, ., k) -> sum_m D[m][.] f1(i,m,k)
-    line_transform<T, N, true>(AT + ro.rT, Dm); // f0(., j, k) -> sum_m D[m][.] f0(m,j,k)
+    line_transform<T, N, true, L, true>(A + ro.rA, Dm);   // f1(i, ., k) -> sum_m D[m][.] f1(i,m,k)
+    line_transform<T, N, true, L, false>(AT + ro.rT, Dm); // f0(., j, k) -> sum_m D[m][.] f0(m,j,k)
   }
   sync();
   tm.mark(5);
@@ -336,7 +426,7 @@ __device__ __forceinline__ void cell_part2(const T (&f2)[N], T* __restrict__ til
 #pragma unroll
     for (int k = 0; k < N; ++k)
     {
-      T s = AT[k * PS_T + ro.kT] + A[k * PS_A + ro.kA];
+      T s = AT[k * L::PS_T + ro.kT] + A[k * L::PS_A + ro.kA];
 #pragma unroll
       for (int m = 0; m < N; ++m) s += Dm.d[m * N + k] * f2[m];
       yv[k] = s;
@@ -349,7 +439,7 @@ template <typename T, int N, int SLOT, int CPB>
 __global__ void __launch_bounds__(SLOT* CPB)
 stiff_cell_kernel(const int32_t* __restrict__ cells, int ncl, const int32_t* __restrict__ tdm,
                   const T* __restrict__ G6, const T* __restrict__ x, T* __restrict__ y,
-                  const DMat<T, N> Dm, T coeff)
+                  const DMat<T, N> Dm, T coeff, int g_order)
 {
   constexpr int N2 = N * N, ND = N2 * N;
   using V2 = typename Vec2<T>::type;
@@ -369,11 +459,11 @@ stiff_cell_kernel(const int32_t* __restrict__ cells, int ncl, const int32_t* __r
     u[k] = active ? x[dof[k]] : T(0);
     yv[k] = 0;
   }
-  if (active) load_G<T, N>(G6 + cell * (int64_t)(6 * ND), col, g);
+  if (active) load_G<T, N>(G6 + cell * (int64_t)(6 * ND), g_column<LayoutStd<N>, N>(ro, col, g_order), g);
   PhaseTimer tm;
   tm.start(false);
-  cell_part1<T, N>(u, g, s_w[slot], ro, Dm, coeff, active, BlockSync(), f2, tm);
-  cell_part2<T, N>(f2, s_w[slot], ro, Dm, active, BlockSync(), yv, tm);
+  cell_part1<T, N, LayoutStd<N>>(u, g, s_w[slot], ro, Dm, coeff, active, BlockSync(), f2, tm);
+  cell_part2<T, N, LayoutStd<N>>(f2, s_w[slot], ro, Dm, active, BlockSync(), yv, tm);
   if (active)
   {
 #pragma unroll
@@ -403,6 +493,7 @@ struct BrickArgs
   const uint32_t* runs;   // (first dof, length) pairs
   const uint16_t* slot_base; // REG kernels: position of each slot's origin corner
   int Sx, Sy;                // REG kernels: strides of the brick lattice in the shared arrays
+  int g_order;               // column order of G6 (see g_column)
 };
 
 // Shared memory of one CTA:  xl[nloc_pad] | yl[nloc_pad] | tiles[W][slot_elems] | sldm[rounds_max*W*NDP] (u16)
@@ -410,21 +501,21 @@ struct BrickArgs
 // REG: every batch of the launch is a regular brick (wfx_plan): the positions of a cell's points
 // in the shared arrays are base + ascpos(i)*Sx + ascpos(j)*Sy + ascpos(k), so no local dofmap is
 // staged and all three roles read their input lines straight from xl (no tile round trip for u).
-template <typename T, int N, int SLOT, int W, int MINB, bool REG>
+template <typename T, int N, int SLOT, int W, int MINB, bool REG, typename L>
 __global__ void __launch_bounds__(SLOT* W, MINB)
 stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
 {
   // U: batch dofs handled per thread in one pass of the staging / write-back loops; all their
   // loads are issued before the first is consumed (two dependent memory round trips per pass)
   constexpr int N2 = N * N, ND = N2 * N, NT = SLOT * W, NDP = ndp_of<N>();
-  constexpr int U = 20;
+  constexpr int U = 21;
   using V2 = typename Vec2<T>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* xl = reinterpret_cast<T*>(smem_raw);
   T* yl = xl + a.nloc_pad;
   T* work = yl + a.nloc_pad;
   // 16-byte aligned for the bulk copy below
-  const size_t meta_off = ((size_t)(2 * a.nloc_pad + W * slot_elems<N>()) * sizeof(T) + 15) & ~(size_t)15;
+  const size_t meta_off = ((size_t)(2 * a.nloc_pad + W * L::SLOT_ELEMS) * sizeof(T) + 15) & ~(size_t)15;
   // generic: sldm | scell | mbarrier.   REG: scell | sbase (u16)
   uint16_t* sldm = reinterpret_cast<uint16_t*>(smem_raw + meta_off);
   int32_t* scell = REG ? reinterpret_cast<int32_t*>(smem_raw + meta_off)
@@ -441,78 +532,100 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   const int tid = threadIdx.x;
   const int slot = tid / SLOT, col = tid % SLOT;
   const bool lane_ok = col < N2;
-  const RoleOff ro = role_offsets<N>(lane_ok ? col : 0);
+  const RoleOff ro = L::offsets(lane_ok ? col : 0);
+  const int gcol = g_column<L, N>(ro, lane_ok ? col : 0, a.g_order);
   const int r0 = __ldg(a.round_off + b), nr = __ldg(a.round_off + b + 1) - r0;
 
   // the batch's local dofmap: one TMA bulk copy, waited for after the dofs are staged
   if constexpr (!REG)
-  {
     if (tid == 0 && nr > 0) bulk_copy_g2s(sldm, a.ldm + (int64_t)r0 * W * NDP, (uint32_t)(nr * W * NDP * 2), bar);
-  }
-  else
-  {
-    for (int v = tid; v < nr * W; v += NT) sbase[v] = __ldg(a.slot_base + (int64_t)r0 * W + v);
-  }
   // REG: offsets of this thread's three lines relative to the cell's base position
   const int P1 = N - 1;
   auto apos = [P1](int q) { return q == 0 ? 0 : (q == 1 ? P1 : q - 1); };
-  const int hi = (lane_ok ? col : 0) / N, lo = (lane_ok ? col : 0) % N;
-  const int offK = apos(hi) * a.Sx + apos(lo) * a.Sy; // role K: i = hi, j = lo, line over k (stride 1)
-  const int offJ = apos(lo) * a.Sx + apos(hi);        // role J: k = hi, i = lo, line over j (stride Sy)
-  const int offI = apos(lo) * a.Sy + apos(hi);        // role I: k = hi, j = lo, line over i (stride Sx)
-  // The G of the first 1 + PF_DIST rounds goes to L2 by bulk prefetch (one request per cell): the
-  // register loads issued later are then L2 hits and leave the SM's load queue quickly.  The
-  // register load of the first cell itself is issued after the dof gather below, so that the
-  // latency-critical index loads of the staging are not queued behind it.
+  const int offK = apos(ro.iK) * a.Sx + apos(ro.jK) * a.Sy; // role K: line over k (stride 1)
+  const int offJ = apos(ro.iJ) * a.Sx + apos(ro.kJ);        // role J: line over j (stride Sy)
+  const int offI = apos(ro.jI) * a.Sy + apos(ro.kI);        // role I: line over i (stride Sx)
+
+  // Staging.  A warp issues in order, so a load followed by its use costs a full memory round
+  // trip before anything else can be issued: ALL loads that depend only on the batch header (the
+  // dof indices of the first pass, the slot tables, the first cells) are issued back to back
+  // into registers first and consumed afterwards -- two round trips instead of six.
   V2 g[N][3];
+  uint32_t e[U];
+#pragma unroll
+  for (int q = 0; q < U; ++q) e[q] = tid + q * NT < nloc ? ld_once(a.bdofs + d0 + tid + q * NT) : BD_HOLE;
+  const int nslots = nr * W;
+  const int sc_v = tid < nslots ? __ldg(a.slot_cell + (int64_t)r0 * W + tid) : -1;
+  uint16_t sb_v = 0;
+  if constexpr (REG) sb_v = tid < nslots ? __ldg(a.slot_base + (int64_t)r0 * W + tid) : (uint16_t)0;
   const int c0 = nr > 0 ? __ldg(a.slot_cell + (int64_t)r0 * W + slot) : -1;
+  int cpf[PF_DIST > 0 ? PF_DIST : 1];
+#pragma unroll
+  for (int q = 1; q <= PF_DIST; ++q) cpf[q - 1] = q < nr ? __ldg(a.slot_cell + (int64_t)(r0 + q) * W + slot) : -1;
+  // The G of the first 1 + PF_DIST rounds goes to L2 by bulk prefetch (one request per cell): the
+  // register loads issued later are then L2 hits and leave the SM's load queue quickly.
   if constexpr ((6 * ND * sizeof(T)) % 16 == 0)
     if (col == 0)
-      for (int q = 0; q <= PF_DIST && q < nr; ++q)
-      {
-        const int cq = q == 0 ? c0 : __ldg(a.slot_cell + (int64_t)(r0 + q) * W + slot);
-        if (cq >= 0) l2_prefetch_bulk(a.G6 + (int64_t)cq * (6 * ND), (uint32_t)(6 * ND * sizeof(T)));
-      }
-  for (int v = tid; v < nr * W; v += NT) scell[v] = __ldg(a.slot_cell + (int64_t)r0 * W + v);
-  // stage the batch's dofs: U independent index loads, then U asynchronous gathers into xl
-  for (int base = tid; base < nloc; base += NT * U)
-  {
-    uint32_t e[U];
+    {
+      if (c0 >= 0) l2_prefetch_bulk(a.G6 + (int64_t)c0 * (6 * ND), (uint32_t)(6 * ND * sizeof(T)));
 #pragma unroll
-    for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? __ldg(a.bdofs + d0 + base + q * NT) : BD_HOLE;
+      for (int q = 1; q <= PF_DIST; ++q)
+        if (cpf[q - 1] >= 0) l2_prefetch_bulk(a.G6 + (int64_t)cpf[q - 1] * (6 * ND), (uint32_t)(6 * ND * sizeof(T)));
+    }
+  if (tid < nslots)
+  {
+    scell[tid] = sc_v;
+    if constexpr (REG) sbase[tid] = sb_v;
+  }
+  for (int v = tid + NT; v < nslots; v += NT)
+  {
+    scell[v] = __ldg(a.slot_cell + (int64_t)r0 * W + v);
+    if constexpr (REG) sbase[v] = __ldg(a.slot_base + (int64_t)r0 * W + v);
+  }
+  // the batch's dofs: asynchronous gathers into xl (first pass from the indices loaded above)
+#pragma unroll
+  for (int q = 0; q < U; ++q)
+  {
+    if (e[q] != BD_HOLE) cp_async_scalar(xl + tid + q * NT, a.x + (e[q] & BD_MASK));
+    if (tid + q * NT < nloc) yl[tid + q * NT] = T(0);
+  }
+  for (int base = tid + NT * U; base < nloc; base += NT * U)
+  {
+#pragma unroll
+    for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? ld_once(a.bdofs + d0 + base + q * NT) : BD_HOLE;
 #pragma unroll
     for (int q = 0; q < U; ++q)
     {
       if (e[q] != BD_HOLE) cp_async_scalar(xl + base + q * NT, a.x + (e[q] & BD_MASK));
       if (base + q * NT < nloc) yl[base + q * NT] = T(0);
     }
-#ifdef WFX_PF_WRITEBACK
-    // what the write-back will read (y of non-FIRST dofs, the scaling of LAST dofs): into L2 now
-#pragma unroll
-    for (int q = 0; q < U; ++q)
-      if (e[q] != BD_HOLE)
-      {
-        if (!(e[q] & BD_FIRST) || a.beta) l2_prefetch(a.y + (e[q] & BD_MASK));
-        if ((e[q] & BD_LAST) && a.scale) l2_prefetch(a.scale + (e[q] & BD_MASK));
-      }
-#endif
   }
-  if (lane_ok && c0 >= 0) load_G<T, N>(a.G6 + (int64_t)c0 * (6 * ND), col, g);
+  tm.mark(10);
+  if (lane_ok && c0 >= 0) load_G<T, N>(a.G6 + (int64_t)c0 * (6 * ND), gcol, g);
   cp_async_wait_all();
+  tm.mark(11);
   if constexpr (!REG)
     if (nr > 0) mbar_wait(bar, 0);
   __syncthreads();
   tm.mark(0);
 
-  T* tiles = work + slot * slot_elems<N>();
+  T* tiles = work + slot * L::SLOT_ELEMS;
   for (int r = 0; r < nr; ++r)
   {
     const int cell = scell[r * W + slot];
     const bool active = lane_ok && cell >= 0;
+    const int cn = r + 1 < nr ? scell[(r + 1) * W + slot] : -1;
+    bool g_requested = false; // next cell's G already requested inside part 1
     int li[N];
     T u[N], yv[N], f2[N];
     if constexpr (REG)
     {
+#ifndef WFX_NO_G_ROTATE
+      const V2* gnext = cn >= 0 ? reinterpret_cast<const V2*>(a.G6 + (int64_t)cn * (6 * ND)) + gcol : nullptr;
+      g_requested = active;
+#else
+      const V2* gnext = nullptr;
+#endif
       const int base = active ? (int)sbase[r * W + slot] : 0;
       T lj[N], lI[N];
 #pragma unroll
@@ -526,12 +639,12 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
         lI[m] = active ? xl[base + offI + am * a.Sx] : T(0);
         yv[m] = 0;
       }
-      if constexpr (SLOT <= 32) cell_part1_reg<T, N>(u, lj, lI, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2, tm);
-      else cell_part1_reg<T, N>(u, lj, lI, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2, tm);
+      if constexpr (SLOT <= 32) cell_part1_reg<T, N, L>(u, lj, lI, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2, tm, gnext);
+      else cell_part1_reg<T, N, L>(u, lj, lI, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2, tm, gnext);
     }
     else
     {
-      const uint16_t* lrow = sldm + (r * W + slot) * NDP + col;
+      const uint16_t* lrow = sldm + (r * W + slot) * NDP + ro.colK;
 #pragma unroll
       for (int k = 0; k < N; ++k)
       {
@@ -539,14 +652,13 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
         u[k] = active ? xl[li[k]] : T(0);
         yv[k] = 0;
       }
-      if constexpr (SLOT <= 32) cell_part1<T, N>(u, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2, tm);
-      else cell_part1<T, N>(u, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2, tm);
+      if constexpr (SLOT <= 32) cell_part1<T, N, L>(u, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2, tm);
+      else cell_part1<T, N, L>(u, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2, tm);
     }
     // G of this cell is consumed: request the next cell's G into the same registers so
     // that the loads fly during part 2 and the next gather
     {
-      const int cn = r + 1 < nr ? scell[(r + 1) * W + slot] : -1;
-      if (lane_ok && cn >= 0) load_G<T, N>(a.G6 + (int64_t)cn * (6 * ND), col, g);
+      if (lane_ok && cn >= 0 && !g_requested) load_G<T, N>(a.G6 + (int64_t)cn * (6 * ND), gcol, g);
       // keep the L2 prefetch PF_DIST rounds ahead of the register loads
       if constexpr ((6 * ND * sizeof(T)) % 16 == 0)
         if (col == 0 && r + 1 + PF_DIST < nr)
@@ -605,8 +717,8 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
 #endif
     }
     tm.mark(4);
-    if constexpr (SLOT <= 32) cell_part2<T, N>(f2, tiles, ro, Dm, active, WarpSync(), yv, tm);
-    else cell_part2<T, N>(f2, tiles, ro, Dm, active, BlockSync(), yv, tm);
+    if constexpr (SLOT <= 32) cell_part2<T, N, L>(f2, tiles, ro, Dm, active, WarpSync(), yv, tm);
+    else cell_part2<T, N, L>(f2, tiles, ro, Dm, active, BlockSync(), yv, tm);
     if (active)
     {
 #pragma unroll
@@ -623,7 +735,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
     uint32_t e[U];
     T v[U], sc[U];
 #pragma unroll
-    for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? __ldg(a.bdofs + d0 + base + q * NT) : BD_HOLE;
+    for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? ld_once(a.bdofs + d0 + base + q * NT) : BD_HOLE;
     if (base == tid)
     {
       pdl_wait(); // earlier colours have finished their writes to y
@@ -634,8 +746,8 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
     {
       const bool ok = e[q] != BD_HOLE; // in range and a real dof (regular bricks have unused positions)
       const uint32_t dof = e[q] & BD_MASK;
-      v[q] = (ok && (!(e[q] & BD_FIRST) || a.beta)) ? a.y[dof] : T(0);
-      sc[q] = (ok && (e[q] & BD_LAST) && a.scale) ? __ldg(a.scale + dof) : T(1);
+      v[q] = (ok && (!(e[q] & BD_FIRST) || a.beta)) ? __ldcg(a.y + dof) : T(0);
+      sc[q] = (ok && (e[q] & BD_LAST) && a.scale) ? ld_once(a.scale + dof) : T(1);
     }
 #pragma unroll
     for (int q = 0; q < U; ++q)
@@ -694,6 +806,7 @@ stiff_brick_persistent(const BrickArgs<T> a, const PersistArgs pa, const DMat<T,
   const int slot = tid / SLOT, col = tid % SLOT;
   const bool lane_ok = col < N2;
   const RoleOff ro = role_offsets<N>(lane_ok ? col : 0);
+  const int gcol = g_column<LayoutStd<N>, N>(ro, lane_ok ? col : 0, a.g_order);
   T* tiles = work + slot * slot_elems<N>();
   PhaseTimer tm;
   tm.start(tid % 32 == 0);
@@ -748,7 +861,7 @@ stiff_brick_persistent(const BrickArgs<T> a, const PersistArgs pa, const DMat<T,
   if (t < pa.nbatches)
   {
     const int c0 = __ldg(a.slot_cell + (int64_t)__ldg(a.round_off + t) * W + slot);
-    if (lane_ok && c0 >= 0) load_G<T, N>(a.G6 + (int64_t)c0 * (6 * ND), col, g);
+    if (lane_ok && c0 >= 0) load_G<T, N>(a.G6 + (int64_t)c0 * (6 * ND), gcol, g);
     stage(t);
   }
   for (; t < pa.nbatches; t += gridDim.x)
@@ -779,18 +892,18 @@ stiff_brick_persistent(const BrickArgs<T> a, const PersistArgs pa, const DMat<T,
         u[k] = active ? xl[li[k]] : T(0);
         yv[k] = 0;
       }
-      if constexpr (SLOT <= 32) cell_part1<T, N>(u, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2, tm);
-      else cell_part1<T, N>(u, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2, tm);
+      if constexpr (SLOT <= 32) cell_part1<T, N, LayoutStd<N>>(u, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2, tm);
+      else cell_part1<T, N, LayoutStd<N>>(u, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2, tm);
       {
         // next cell of this batch, or the first cell of this CTA's next batch
         int cn = -1;
         if (r + 1 < nr) cn = scell[(r + 1) * W + slot];
         else cn = cn_first;
-        if (lane_ok && cn >= 0) load_G<T, N>(a.G6 + (int64_t)cn * (6 * ND), col, g);
+        if (lane_ok && cn >= 0) load_G<T, N>(a.G6 + (int64_t)cn * (6 * ND), gcol, g);
       }
       tm.mark(4);
-      if constexpr (SLOT <= 32) cell_part2<T, N>(f2, tiles, ro, Dm, active, WarpSync(), yv, tm);
-      else cell_part2<T, N>(f2, tiles, ro, Dm, active, BlockSync(), yv, tm);
+      if constexpr (SLOT <= 32) cell_part2<T, N, LayoutStd<N>>(f2, tiles, ro, Dm, active, WarpSync(), yv, tm);
+      else cell_part2<T, N, LayoutStd<N>>(f2, tiles, ro, Dm, active, BlockSync(), yv, tm);
       if (active)
       {
 #pragma unroll
@@ -854,6 +967,23 @@ __global__ void zero_entries_kernel(const int32_t* __restrict__ idx, int n, T* _
 {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) y[idx[t]] = T(0);
+}
+
+// One-time in-place reordering of the columns of a degree-4 G6 (rows of 25 2-vectors, one warp
+// per row): the row's column q moves to position c_p4d_colpos[q].
+template <typename T>
+__global__ void permute_g_columns_kernel(T* __restrict__ G6, int64_t nrows)
+{
+  constexpr int NC = 25;
+  using V2 = typename Vec2<T>::type;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= nrows) return;
+  V2* r = reinterpret_cast<V2*>(G6) + row * NC;
+  V2 v{};
+  if (lane < NC) v = r[lane];
+  __syncwarp();
+  if (lane < NC) r[c_p4d_colpos[lane]] = v;
 }
 
 // per-degree launch configuration
@@ -926,7 +1056,7 @@ struct wfx_stiffness
   DevBuf<int32_t> d_round_off, d_slot_cell, d_untouched;
   DevBuf<uint16_t> d_ldm;
   // regular-brick form (every batch a lattice brick): arithmetic positions, no staged dofmap
-  bool regular = false;
+  int variant = 0; // 0 generic, 1 regular bricks, 2 regular bricks + the P4 fp64 conflict-free layout
   int Sx = 0, Sy = 0;
   size_t smem_bytes_reg = 0;
   DevBuf<uint16_t> d_slot_base;
@@ -960,7 +1090,8 @@ void launch_simple(wfx_stiffness* op, const T* x, T* y, cudaStream_t st)
     if (ncl == 0) continue;
     const int grid = (ncl + C::CPB - 1) / C::CPB;
     stiff_cell_kernel<T, N, C::SLOT, C::CPB><<<grid, C::SLOT * C::CPB, 0, st>>>(
-        op->d_cells.p + beg, ncl, op->d_tdm.p, (const T*)op->geom->G6, x, y, Dm, coeff);
+        op->d_cells.p + beg, ncl, op->d_tdm.p, (const T*)op->geom->G6, x, y, Dm, coeff,
+        op->geom->g_colpos.empty() ? 0 : 1);
   }
   WFX_CUDA(cudaGetLastError());
 }
@@ -969,10 +1100,15 @@ template <typename T, int N>
 void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta, cudaStream_t st)
 {
   using C = Cfg<N>;
-  const bool reg = op->regular && !op->persistent;
-  auto kern = reg ? stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true>
-                  : stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false>;
-  const size_t smem = reg ? op->smem_bytes_reg : op->smem_bytes;
+  using KernPtr = void (*)(BrickArgs<T>, DMat<T, N>, int);
+  const int variant = op->persistent ? 0 : op->variant;
+  KernPtr kern = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N>>;
+  size_t smem = op->smem_bytes;
+  if (variant == 1) kern = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>>, smem = op->smem_bytes_reg;
+  if constexpr (N == 5 && sizeof(T) == 8)
+    if (variant == 2) kern = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutP4D>, smem = op->smem_bytes_reg;
+  static const size_t smem_pad = std::getenv("WFX_SMEM_PAD") ? (size_t)std::atoi(std::getenv("WFX_SMEM_PAD")) : 0;
+  smem += smem_pad;
   DMat<T, N> Dm;
   for (int q = 0; q < N * N; ++q) Dm.d[q] = (T)op->Dhost[q];
   BrickArgs<T> a;
@@ -995,6 +1131,7 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   a.slot_base = op->d_slot_base.p;
   a.Sx = op->Sx;
   a.Sy = op->Sy;
+  a.g_order = op->geom->g_colpos.empty() ? 0 : 1;
   if (!beta && op->d_untouched.n && op->cur_part != 1)
   {
     const int n = (int)op->d_untouched.n;
@@ -1051,10 +1188,14 @@ template <typename T, int N>
 void configure_brick(wfx_stiffness* op)
 {
   using C = Cfg<N>;
-  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->ctx->smem_optin));
-  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->ctx->smem_optin));
+  const int optin = (int)op->ctx->smem_optin;
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N>>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  if constexpr (N == 5 && sizeof(T) == 8)
+    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutP4D>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persistent<T, N, C::SLOT, C::W, C::MINB>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->ctx->smem_optin));
 }
@@ -1251,10 +1392,28 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
       op->d_slot_base.upload(bp.slot_base);
       op->Sx = bp.Sx;
       op->Sy = bp.Sy;
-      op->regular = bp.nbatches > 0 && bp.n_regular == bp.nbatches;
-      if (const char* e = std::getenv("WFX_REGULAR")) op->regular = op->regular && std::atoi(e) != 0;
-      op->smem_bytes_reg = (((size_t)op->nloc_pad * 2 * esz + tiles_bytes + 15) & ~(size_t)15)
+      bool regular = bp.nbatches > 0 && bp.n_regular == bp.nbatches;
+      if (const char* e = std::getenv("WFX_REGULAR")) regular = regular && std::atoi(e) != 0;
+      size_t tiles_reg = tiles_bytes;
+      op->variant = regular ? 1 : 0;
+      if (regular && op->N == 5 && esz == 8 && bp.Sx % 16 == LayoutP4D::SX_MOD && bp.Sy % 16 == LayoutP4D::SY_MOD)
+      {
+        op->variant = 2;
+        tiles_reg = (size_t)lc.W * LayoutP4D::SLOT_ELEMS * esz;
+      }
+      op->smem_bytes_reg = (((size_t)op->nloc_pad * 2 * esz + tiles_reg + 15) & ~(size_t)15)
                            + (size_t)bp.rounds_max * lc.W * 6 + 16;
+      if (op->variant && op->smem_bytes_reg > ctx->smem_optin) op->variant = 0;
+      // variant 2 reads G in the lane order of its role K: reorder the geometry's columns once
+      // (in place; every other consumer honours geom->g_colpos)
+      if (op->variant == 2 && geom->g_colpos.empty())
+      {
+        const int64_t nrows = op->ncells * op->N * 3;
+        permute_g_columns_kernel<double><<<(unsigned)((nrows + 7) / 8), 256>>>((double*)geom->G6, nrows);
+        WFX_CUDA(cudaGetLastError());
+        WFX_CUDA(cudaDeviceSynchronize());
+        geom->g_colpos.assign(h_p4d_colpos, h_p4d_colpos + 25);
+      }
       if (!bp.runs.empty())
       {
         op->d_run_off.upload(bp.run_off);

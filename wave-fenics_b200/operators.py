@@ -73,7 +73,7 @@ class Geometry:
         return G, detJ
 
     def __del__(self):
-        if getattr(self, "handle", None):
+        if getattr(self, "handle", None) and getattr(capi, "lib", None) is not None:
             capi.lib.wfx_geometry_destroy(self.handle)
             self.handle = None
 
@@ -184,7 +184,7 @@ class StiffnessOperator(_Operator):
                     bytes=by.value, ncolours=ncol.value, nlaunches=nl.value)
 
     def __del__(self):
-        if getattr(self, "handle", None):
+        if getattr(self, "handle", None) and getattr(capi, "lib", None) is not None:
             capi.lib.wfx_stiffness_destroy(self.handle)
             self.handle = None
 
@@ -247,7 +247,7 @@ class MassOperator(_Operator):
         return self._download(self.inverse_diagonal_ptr())
 
     def __del__(self):
-        if getattr(self, "handle", None):
+        if getattr(self, "handle", None) and getattr(capi, "lib", None) is not None:
             capi.lib.wfx_mass_destroy(self.handle)
             self.handle = None
 
@@ -286,7 +286,7 @@ class BoundaryOperator(_Operator):
         return m1, m2
 
     def __del__(self):
-        if getattr(self, "handle", None):
+        if getattr(self, "handle", None) and getattr(capi, "lib", None) is not None:
             capi.lib.wfx_boundary_destroy(self.handle)
             self.handle = None
 
@@ -343,6 +343,6 @@ class LinearGLLOpt:
         return steps.value, t_end.value
 
     def __del__(self):
-        if getattr(self, "handle", None):
+        if getattr(self, "handle", None) and getattr(capi, "lib", None) is not None:
             capi.lib.wfx_wave_destroy(self.handle)
             self.handle = None

@@ -184,7 +184,7 @@ class Halo:
                   C.c_void_p(scale_ptr), C.c_void_p(st))
 
     def __del__(self):
-        if getattr(self, "handle", None):
+        if getattr(self, "handle", None) and getattr(capi, "lib", None) is not None:
             capi.lib.wfx_halo_destroy(self.handle)
             capi.lib.wfx_comm_destroy(self.comm)
             self.handle = None
