@@ -494,6 +494,7 @@ struct BrickArgs
   const uint16_t* slot_base; // REG kernels: position of each slot's origin corner
   int Sx, Sy;                // REG kernels: strides of the brick lattice in the shared arrays
   int g_order;               // column order of G6 (see g_column)
+  int uni_nloc, uni_nr;      // > 0: every batch has this many dof positions / rounds (no header loads)
 };
 
 // Shared memory of one CTA:  xl[nloc_pad] | yl[nloc_pad] | tiles[W][slot_elems] | sldm[rounds_max*W*NDP] (u16)
@@ -527,14 +528,16 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   PhaseTimer tm;
   tm.start(threadIdx.x % 32 == 0);
   const int b = batch0 + blockIdx.x;
-  const int64_t d0 = __ldg(a.dof_off + b);
-  const int nloc = (int)(__ldg(a.dof_off + b + 1) - d0);
+  // batch header: arithmetic when the plan is uniform (saves a memory round trip), else loaded
+  const int64_t d0 = a.uni_nloc ? (int64_t)b * a.uni_nloc : __ldg(a.dof_off + b);
+  const int nloc = a.uni_nloc ? a.uni_nloc : (int)(__ldg(a.dof_off + b + 1) - d0);
   const int tid = threadIdx.x;
   const int slot = tid / SLOT, col = tid % SLOT;
   const bool lane_ok = col < N2;
   const RoleOff ro = L::offsets(lane_ok ? col : 0);
   const int gcol = g_column<L, N>(ro, lane_ok ? col : 0, a.g_order);
-  const int r0 = __ldg(a.round_off + b), nr = __ldg(a.round_off + b + 1) - r0;
+  const int r0 = a.uni_nr ? b * a.uni_nr : __ldg(a.round_off + b);
+  const int nr = a.uni_nr ? a.uni_nr : __ldg(a.round_off + b + 1) - r0;
 
   // the batch's local dofmap: one TMA bulk copy, waited for after the dofs are staged
   if constexpr (!REG)
@@ -666,6 +669,14 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
           const int c2 = scell[(r + 1 + PF_DIST) * W + slot];
           if (c2 >= 0) l2_prefetch_bulk(a.G6 + (int64_t)c2 * (6 * ND), (uint32_t)(6 * ND * sizeof(T)));
         }
+#ifndef WFX_NO_PF_OWN_BDOFS
+      // the write-back walks the batch's dof list again: keep it in L2 (it was read ~30 us ago)
+      if (r == nr - 1 && tid == SLOT * (W > 1 ? 1 : 0))
+      {
+        const int64_t dn = d0 & ~(int64_t)3;
+        l2_prefetch_bulk(a.bdofs + dn, (uint32_t)(((d0 + nloc + 3) & ~(int64_t)3) - dn) * 4u);
+      }
+#endif
 #ifndef WFX_NO_PF_NEXT_CTA
       // In the last round, warm L2 for the CTA that will take this one's place on the SM
       // (blocks are dispatched in index order, a.pf_stride of them are resident): the first
@@ -673,7 +684,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
       if (r == nr - 1 && col == 0 && (int)blockIdx.x + a.pf_stride < (int)gridDim.x)
       {
         const int bn = b + a.pf_stride;
-        const int r0n = __ldg(a.round_off + bn);
+        const int r0n = a.uni_nr ? bn * a.uni_nr : __ldg(a.round_off + bn);
         if constexpr ((6 * ND * sizeof(T)) % 16 == 0)
         {
           const int cq = __ldg(a.slot_cell + (int64_t)r0n * W + slot);
@@ -681,12 +692,16 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
         }
         if (slot == 0)
         {
-          const int64_t dn = __ldg(a.dof_off + bn);
-          const uint32_t nbytes = ((uint32_t)(__ldg(a.dof_off + bn + 1) - dn) * 4u) & ~15u;
-          if (nbytes && (dn % 4) == 0) l2_prefetch_bulk(a.bdofs + dn, nbytes);
+          // (16-byte granules: the list is padded by 4 entries on the device)
+          const int64_t dn0 = a.uni_nloc ? (int64_t)bn * a.uni_nloc : __ldg(a.dof_off + bn);
+          const int64_t dn1 = a.uni_nloc ? dn0 + a.uni_nloc : __ldg(a.dof_off + bn + 1);
+          const int64_t dn = dn0 & ~(int64_t)3;
+          const uint32_t nbytes = (uint32_t)(((dn1 + 3) & ~(int64_t)3) - dn) * 4u;
+          if (nbytes) l2_prefetch_bulk(a.bdofs + dn, nbytes);
           if constexpr (!REG)
           {
-            const uint32_t lbytes = (uint32_t)((__ldg(a.round_off + bn + 1) - r0n) * W * NDP * 2);
+            const int nrn = a.uni_nr ? a.uni_nr : __ldg(a.round_off + bn + 1) - r0n;
+            const uint32_t lbytes = (uint32_t)(nrn * W * NDP * 2);
             if (lbytes) l2_prefetch_bulk(a.ldm + (int64_t)r0n * W * NDP, lbytes);
           }
         }
@@ -1056,6 +1071,7 @@ struct wfx_stiffness
   DevBuf<int32_t> d_round_off, d_slot_cell, d_untouched;
   DevBuf<uint16_t> d_ldm;
   // regular-brick form (every batch a lattice brick): arithmetic positions, no staged dofmap
+  int uni_nloc = 0, uni_nr = 0; // uniform plans: dof positions / rounds of every batch (else 0)
   int variant = 0; // 0 generic, 1 regular bricks, 2 regular bricks + the P4 fp64 conflict-free layout
   int Sx = 0, Sy = 0;
   size_t smem_bytes_reg = 0;
@@ -1132,6 +1148,8 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   a.Sx = op->Sx;
   a.Sy = op->Sy;
   a.g_order = op->geom->g_colpos.empty() ? 0 : 1;
+  a.uni_nloc = op->uni_nloc;
+  a.uni_nr = op->uni_nr;
   if (!beta && op->d_untouched.n && op->cur_part != 1)
   {
     const int n = (int)op->d_untouched.n;
@@ -1385,6 +1403,18 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
                        + meta_bytes(bp.rounds_max) + 16; // + mbarrier
       if (op->smem_bytes > ctx->smem_optin) fail("stiffness: batch needs %zu B shared memory", op->smem_bytes);
       op->d_dof_off.upload(bp.dof_off);
+      {
+        bool un = bp.nbatches > 0, ur = bp.nbatches > 0;
+        for (int b = 0; b < bp.nbatches; ++b)
+        {
+          un = un && bp.dof_off[b + 1] - bp.dof_off[b] == bp.dof_off[1];
+          ur = ur && bp.round_off[b + 1] - bp.round_off[b] == bp.round_off[1];
+        }
+        if (std::getenv("WFX_NO_UNIFORM")) un = ur = false;
+        op->uni_nloc = un ? (int)bp.dof_off[1] : 0;
+        op->uni_nr = ur ? bp.round_off[1] : 0;
+      }
+      bp.bdofs.resize(bp.bdofs.size() + 4, BD_HOLE); // slack for the 16-byte granules of the L2 prefetches
       op->d_bdofs.upload(bp.bdofs);
       op->d_round_off.upload(bp.round_off);
       op->d_slot_cell.upload(bp.slot_cell);
