@@ -112,6 +112,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
                  : "memory");
 }
 
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -523,7 +533,18 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
                        : reinterpret_cast<int32_t*>(sldm + (size_t)a.rounds_max * W * NDP);
   uint16_t* sbase = reinterpret_cast<uint16_t*>(scell + (size_t)a.rounds_max * W);
   uint64_t* bar = reinterpret_cast<uint64_t*>(
-      smem_raw + ((meta_off + (size_t)a.rounds_max * W * (NDP * 2 + 4) + 7) & ~(size_t)7));
+      smem_raw + ((meta_off + (size_t)a.rounds_max * W * (REG ? 6 : NDP * 2 + 4) + 7) & ~(size_t)7));
+  // Round barrier, split into arrive / wait when a cell is one warp's business (SLOT <= 32): only
+  // the accumulation into yl has to wait for the previous round, everything before it (reads of
+  // xl, the contractions in the warp's own tiles) runs ahead, and the warps drift apart instead of
+  // hitting the same pipe in lock step.
+#ifndef WFX_NO_SPLIT_BARRIER
+  constexpr bool SPLIT = SLOT <= 32 && (SLOT * W) % 32 == 0 && SLOT * W > 32;
+#else
+  constexpr bool SPLIT = false;
+#endif
+  uint64_t* rbar = bar + 1;
+  if (SPLIT && threadIdx.x == 0) mbar_init(rbar, NT / 32); // one arrival per warp and round
   pdl_launch_dependents(); // the next colour may start staging; it waits before touching y
   PhaseTimer tm;
   tm.start(threadIdx.x % 32 == 0);
@@ -734,15 +755,23 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
     tm.mark(4);
     if constexpr (SLOT <= 32) cell_part2<T, N, L>(f2, tiles, ro, Dm, active, WarpSync(), yv, tm);
     else cell_part2<T, N, L>(f2, tiles, ro, Dm, active, BlockSync(), yv, tm);
+    if constexpr (SPLIT)
+      if (r > 0) mbar_wait(rbar, (r - 1) & 1); // every warp has finished round r-1's accumulation
     if (active)
     {
 #pragma unroll
       for (int k = 0; k < N; ++k) yl[li[k]] += yv[k]; // cells of one round share no dof
     }
     tm.mark(6);
-    __syncthreads();
+    if constexpr (SPLIT)
+    {
+      __syncwarp();
+      if (r + 1 < nr && tid % 32 == 0) mbar_arrive(rbar);
+    }
+    else __syncthreads();
     tm.mark(7);
   }
+  if constexpr (SPLIT) __syncthreads();
   // write-back: every batch dof exactly once.  Index loads first, then (after the earlier
   // colours have finished) all y / scale loads of the pass, then the stores.
   for (int base = tid; base < nloc; base += NT * U)
@@ -1400,7 +1429,7 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
       op->nloc_pad = (bp.nloc_max + 1) & ~1;
       op->rounds_max = bp.rounds_max;
       op->smem_bytes = (((size_t)op->nloc_pad * 2 * esz + tiles_bytes + 15) & ~(size_t)15)
-                       + meta_bytes(bp.rounds_max) + 16; // + mbarrier
+                       + meta_bytes(bp.rounds_max) + 32; // + mbarriers
       if (op->smem_bytes > ctx->smem_optin) fail("stiffness: batch needs %zu B shared memory", op->smem_bytes);
       op->d_dof_off.upload(bp.dof_off);
       {
@@ -1432,7 +1461,7 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
         tiles_reg = (size_t)lc.W * LayoutP4D::SLOT_ELEMS * esz;
       }
       op->smem_bytes_reg = (((size_t)op->nloc_pad * 2 * esz + tiles_reg + 15) & ~(size_t)15)
-                           + (size_t)bp.rounds_max * lc.W * 6 + 16;
+                           + (size_t)bp.rounds_max * lc.W * 6 + 32;
       if (op->variant && op->smem_bytes_reg > ctx->smem_optin) op->variant = 0;
       // variant 2 reads G in the lane order of its role K: reorder the geometry's columns once
       // (in place; every other consumer honours geom->g_colpos)
