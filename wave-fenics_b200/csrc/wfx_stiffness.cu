@@ -80,13 +80,11 @@ __device__ __forceinline__ void cp_async_scalar(float* dst_smem, const float* sr
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-// fire-and-forget prefetches into L2: a contiguous block (bytes multiple of 16, one request), or
-// the line holding one address
+// fire-and-forget prefetch of a contiguous block into L2 (bytes multiple of 16, one request)
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes)
 {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #ifndef WFX_PF_DIST
 #define WFX_PF_DIST 1 // measured at 64^3 P4 fp64: 1 -> 0.604 ms, 2 -> 0.619, 3 -> 0.631, 4 -> 0.650, none -> 0.695
 #endif
