@@ -328,7 +328,6 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
 
   // ---- 4. per-batch dof lists, rounds and local dofmaps ---------------------------
   plan.dof_off.assign(nb + 1, 0);
-  plan.run_off.assign(nb + 1, 0);
   plan.round_off.assign(nb + 1, 0);
   std::vector<uint64_t> lmask;
   std::vector<int> ccol, place;
@@ -433,21 +432,6 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
       if ((e & BD_FIRST) && (e & BD_LAST)) plan.n_private++;
       plan.bdofs[base + place[l]] = e;
       g2l[d] = place[l]; // local index used by the cells = position in the shared arrays
-    }
-    // maximal runs of consecutive global dofs (uniq is ascending): targets of bulk L2 prefetches.
-    // Kept only when the numbering gives the batch real runs (average length >= 4).
-    {
-      const size_t r_begin = plan.runs.size();
-      for (int l = 0; l < (int)uniq.size();)
-      {
-        int e = l + 1;
-        while (e < (int)uniq.size() && uniq[e] == uniq[e - 1] + 1) ++e;
-        plan.runs.push_back((uint32_t)uniq[l]);
-        plan.runs.push_back((uint32_t)(e - l));
-        l = e;
-      }
-      if ((plan.runs.size() - r_begin) / 2 * 4 > uniq.size()) plan.runs.resize(r_begin);
-      plan.run_off[i + 1] = (int64_t)plan.runs.size() / 2;
     }
     nloc = nslots;
     plan.dof_off[i + 1] = (int64_t)plan.bdofs.size();

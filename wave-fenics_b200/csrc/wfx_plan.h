@@ -51,8 +51,6 @@ struct BrickPlan
   std::vector<uint16_t> slot_base; // [nrounds_total*W] position of the cell's origin corner in the batch arrays
   std::vector<uint16_t> ldm;       // [nrounds_total*W][ndp] batch-local dof, k-major point order
   std::vector<int32_t> untouched;  // vector entries no cell references
-  std::vector<int64_t> run_off;    // [nbatches+1] into runs (pairs)
-  std::vector<uint32_t> runs;      // (first dof, length) of the batch's runs of consecutive dofs
   // statistics
   int64_t n_slots_padded = 0;
   int64_t n_private = 0;           // bdofs entries that are FIRST and LAST

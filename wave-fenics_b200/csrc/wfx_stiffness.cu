@@ -17,12 +17,15 @@
 //                           staged in shared memory, each written back once; optional fused
 //                           diagonal scaling (the lumped-mass inverse) on the LAST touch; colours
 //                           are consecutive launches chained by programmatic dependent launch.
-//   stiff_brick_persistent  experimental single cooperative launch (off: measured slower).
+//                           REG = every batch is a lattice brick: arithmetic shared-memory
+//                           positions, no staged local dofmap.
+// (A persistent single-launch form of the brick kernel was measured slower and removed:
+//  DESIGN.md section 6.)
 #include "wfx_internal.h"
 #include "wfx_plan.h"
-#include <type_traits>
 
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 #include <cstring>
 
@@ -497,8 +500,6 @@ struct BrickArgs
   int nloc_pad;   // capacity of the shared dof arrays (even)
   int rounds_max; // capacity (rounds) of the shared local-dofmap staging area
   int pf_stride;  // CTAs resident on the GPU at once (for the cross-CTA L2 prefetch)
-  const int64_t* run_off; // per batch: runs of consecutive dofs (nullable)
-  const uint32_t* runs;   // (first dof, length) pairs
   const uint16_t* slot_base; // REG kernels: position of each slot's origin corner
   int Sx, Sy;                // REG kernels: strides of the brick lattice in the shared arrays
   int g_order;               // column order of G6 (see g_column)
@@ -726,29 +727,6 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
         }
       }
 #endif
-#ifdef WFX_PF_RUNS // measured neutral-to-slower in round 1 (0.619 vs 0.609 ms): off by default
-      // Runs of consecutive dofs: bulk L2 prefetch of what will be gathered / read element-wise.
-      // Last round: the x entries of the CTA that follows this one on the SM.  Half-way: the
-      // scaling (1/m) entries this CTA's own write-back will read.
-      if (a.runs)
-      {
-        const bool for_next = r == nr - 1 && (int)blockIdx.x + a.pf_stride < (int)gridDim.x;
-        const bool for_own = a.scale && r == nr / 2;
-        if (for_next || for_own)
-        {
-          const int bb = for_next ? b + a.pf_stride : b;
-          const T* vec = for_next ? a.x : a.scale;
-          const int64_t q1 = __ldg(a.run_off + bb + 1);
-          for (int64_t q = __ldg(a.run_off + bb) + tid; q < q1; q += NT)
-          {
-            const uint32_t s = __ldg(a.runs + 2 * q), len = __ldg(a.runs + 2 * q + 1);
-            const uintptr_t lo = reinterpret_cast<uintptr_t>(vec + s) & ~(uintptr_t)15;
-            const uintptr_t hi = (reinterpret_cast<uintptr_t>(vec + s + len) + 15) & ~(uintptr_t)15;
-            l2_prefetch_bulk(reinterpret_cast<const void*>(lo), (uint32_t)(hi - lo));
-          }
-        }
-      }
-#endif
     }
     tm.mark(4);
     if constexpr (SLOT <= 32) cell_part2<T, N, L>(f2, tiles, ro, Dm, active, WarpSync(), yv, tm);
@@ -798,210 +776,6 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   if (nloc <= tid) pdl_wait(); // threads without a batch dof still honour the dependency
   tm.mark(9);
   tm.flush((batch0 + blockIdx.x) * W + slot);
-}
-
-// ---- product kernel, persistent form: ONE cooperative launch per apply ---------------------
-// Every CTA walks the colour-sorted batch list with stride gridDim.x.  What the multi-launch
-// kernel pays around the rounds of each batch (two dependent memory round trips to stage the
-// dofs, two more to write back, at ~3 us loaded latency) is overlapped here:
-//  * after the last round of batch t the shared x array is dead, so the dof list of batch t+g is
-//    loaded and its gather (cp.async), local dofmap (TMA bulk copy) and cell list are issued
-//    BEFORE batch t is written back; they land while the write-back runs;
-//  * the G prefetch rotation carries across batches (the last round requests the first cell of
-//    the next batch).
-// Colour order is enforced inside the launch: a batch of colour c is written back only after all
-// batches of colour c-1 are (a per-colour completion counter, monotonic across applies so it never
-// needs resetting).  All CTAs are co-resident (cooperative launch), and every CTA finishes its
-// colour c-1 batches before it touches colour c, so the wait cannot deadlock.
-struct PersistArgs
-{
-  const uint8_t* batch_colour;   // [nbatches]
-  const int32_t* colour_count;   // [ncolours] batches per colour
-  unsigned long long* done;      // [ncolours] completed batches, accumulated over applies
-  unsigned long long epoch;      // 1-based apply counter of this operator
-  int nbatches;
-};
-
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p)
-{
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
-template <typename T, int N, int SLOT, int W, int MINB>
-__global__ void __launch_bounds__(SLOT* W, MINB)
-stiff_brick_persistent(const BrickArgs<T> a, const PersistArgs pa, const DMat<T, N> Dm)
-{
-  constexpr int N2 = N * N, ND = N2 * N, NT = SLOT * W, NDP = ndp_of<N>(), U = 20;
-  using V2 = typename Vec2<T>::type;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* xl = reinterpret_cast<T*>(smem_raw);
-  T* yl = xl + a.nloc_pad;
-  T* work = yl + a.nloc_pad;
-  const size_t meta_off = ((size_t)(2 * a.nloc_pad + W * slot_elems<N>()) * sizeof(T) + 15) & ~(size_t)15;
-  uint16_t* sldm = reinterpret_cast<uint16_t*>(smem_raw + meta_off);
-  int32_t* scell = reinterpret_cast<int32_t*>(sldm + (size_t)a.rounds_max * W * NDP);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(
-      smem_raw + ((meta_off + (size_t)a.rounds_max * W * (NDP * 2 + 4) + 7) & ~(size_t)7));
-  const int tid = threadIdx.x;
-  const int slot = tid / SLOT, col = tid % SLOT;
-  const bool lane_ok = col < N2;
-  const RoleOff ro = role_offsets<N>(lane_ok ? col : 0);
-  const int gcol = g_column<LayoutStd<N>, N>(ro, lane_ok ? col : 0, a.g_order);
-  T* tiles = work + slot * slot_elems<N>();
-  PhaseTimer tm;
-  tm.start(tid % 32 == 0);
-
-  if (tid == 0)
-  {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int l = tid; l < a.nloc_pad; l += NT) yl[l] = T(0);
-  __syncthreads();
-  uint32_t bar_parity = 0;
-
-  // issue the staging of batch tb: dof list -> registers -> asynchronous gather into xl; local
-  // dofmap by TMA; cell list.  Completion is awaited by wait_staged().
-  auto stage = [&](int tb) {
-    const int64_t d0 = __ldg(a.dof_off + tb);
-    const int nloc = (int)(__ldg(a.dof_off + tb + 1) - d0);
-    const int r0 = __ldg(a.round_off + tb), nr = __ldg(a.round_off + tb + 1) - r0;
-    if (tid == 0)
-    {
-      const uint32_t bytes = (uint32_t)(nr * W * NDP * 2);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       smem_u32(sldm)),
-                   "l"(a.ldm + (int64_t)r0 * W * NDP), "r"(bytes), "r"(smem_u32(bar))
-                   : "memory");
-    }
-    for (int v = tid; v < nr * W; v += NT) scell[v] = __ldg(a.slot_cell + (int64_t)r0 * W + v);
-    for (int base = tid; base < nloc; base += NT * U)
-    {
-      uint32_t e[U];
-#pragma unroll
-      for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? __ldg(a.bdofs + d0 + base + q * NT) : BD_HOLE;
-#pragma unroll
-      for (int q = 0; q < U; ++q)
-        if (e[q] != BD_HOLE) cp_async_scalar(xl + base + q * NT, a.x + (e[q] & BD_MASK));
-    }
-  };
-
-  int t = blockIdx.x;
-  V2 g[N][3];
-#ifdef WFX_STAGGER_NS
-  // de-synchronise the CTAs: without it all of them reach their latency-bound write-back /
-  // staging phases at the same moment, wave after wave
-  {
-    const unsigned h = (blockIdx.x * 2654435761u) >> 22; // 0..1023
-    const unsigned ns = (unsigned)((unsigned long long)h * WFX_STAGGER_NS >> 10);
-    for (unsigned w = 0; w < ns; w += 1000) __nanosleep(1000);
-  }
-#endif
-  if (t < pa.nbatches)
-  {
-    const int c0 = __ldg(a.slot_cell + (int64_t)__ldg(a.round_off + t) * W + slot);
-    if (lane_ok && c0 >= 0) load_G<T, N>(a.G6 + (int64_t)c0 * (6 * ND), gcol, g);
-    stage(t);
-  }
-  for (; t < pa.nbatches; t += gridDim.x)
-  {
-    const int tn = t + gridDim.x;
-    const int64_t d0 = __ldg(a.dof_off + t);
-    const int nloc = (int)(__ldg(a.dof_off + t + 1) - d0);
-    const int nr = __ldg(a.round_off + t + 1) - __ldg(a.round_off + t);
-    const int cn_first = tn < pa.nbatches ? __ldg(a.slot_cell + (int64_t)__ldg(a.round_off + tn) * W + slot) : -1;
-    // staged data of this batch has landed
-    cp_async_wait_all();
-    mbar_wait(bar, bar_parity);
-    bar_parity ^= 1;
-    __syncthreads();
-    tm.mark(0);
-
-    for (int r = 0; r < nr; ++r)
-    {
-      const int cell = scell[r * W + slot];
-      const bool active = lane_ok && cell >= 0;
-      const uint16_t* lrow = sldm + (r * W + slot) * NDP + col;
-      int li[N];
-      T u[N], yv[N], f2[N];
-#pragma unroll
-      for (int k = 0; k < N; ++k)
-      {
-        li[k] = active ? (int)lrow[k * N2] : 0;
-        u[k] = active ? xl[li[k]] : T(0);
-        yv[k] = 0;
-      }
-      if constexpr (SLOT <= 32) cell_part1<T, N, LayoutStd<N>>(u, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2, tm);
-      else cell_part1<T, N, LayoutStd<N>>(u, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2, tm);
-      {
-        // next cell of this batch, or the first cell of this CTA's next batch
-        int cn = -1;
-        if (r + 1 < nr) cn = scell[(r + 1) * W + slot];
-        else cn = cn_first;
-        if (lane_ok && cn >= 0) load_G<T, N>(a.G6 + (int64_t)cn * (6 * ND), gcol, g);
-      }
-      tm.mark(4);
-      if constexpr (SLOT <= 32) cell_part2<T, N, LayoutStd<N>>(f2, tiles, ro, Dm, active, WarpSync(), yv, tm);
-      else cell_part2<T, N, LayoutStd<N>>(f2, tiles, ro, Dm, active, BlockSync(), yv, tm);
-      if (active)
-      {
-#pragma unroll
-        for (int k = 0; k < N; ++k) yl[li[k]] += yv[k]; // cells of one round share no dof
-      }
-      tm.mark(6);
-      __syncthreads();
-      tm.mark(7);
-    }
-    // xl, sldm and scell are dead: start staging the next batch, then write this one back
-    if (tn < pa.nbatches) stage(tn);
-    const int colour = pa.batch_colour[t];
-    if (colour > 0)
-    {
-      if (tid == 0)
-      {
-        // all batches of the previous colour have been written back
-        const unsigned long long target = pa.epoch * (unsigned long long)pa.colour_count[colour - 1];
-        while (ld_acquire_u64(pa.done + colour - 1) < target) __nanosleep(100);
-      }
-      __syncthreads();
-    }
-    tm.mark(8);
-    for (int base = tid; base < nloc; base += NT * U)
-    {
-      uint32_t e[U];
-      T v[U], sc[U];
-#pragma unroll
-      for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? __ldg(a.bdofs + d0 + base + q * NT) : BD_HOLE;
-#pragma unroll
-      for (int q = 0; q < U; ++q)
-        sc[q] = (e[q] != BD_HOLE && (e[q] & BD_LAST) && a.scale) ? __ldg(a.scale + (e[q] & BD_MASK)) : T(1);
-#pragma unroll
-      for (int q = 0; q < U; ++q)
-      {
-        const bool ok = e[q] != BD_HOLE;
-        // y is written by other SMs inside this launch: bypass L1
-        v[q] = (ok && (!(e[q] & BD_FIRST) || a.beta)) ? __ldcg(a.y + (e[q] & BD_MASK)) : T(0);
-      }
-#pragma unroll
-      for (int q = 0; q < U; ++q)
-        if (e[q] != BD_HOLE)
-        {
-          a.y[e[q] & BD_MASK] = (v[q] + yl[base + q * NT]) * sc[q];
-          yl[base + q * NT] = T(0);
-        }
-    }
-    __syncthreads();
-    tm.mark(9);
-    if (tid == 0)
-    {
-      __threadfence();
-      atomicAdd(pa.done + colour, 1ull);
-    }
-  }
-  tm.flush(blockIdx.x * W + slot);
 }
 
 template <typename T>
@@ -1103,17 +877,6 @@ struct wfx_stiffness
   int Sx = 0, Sy = 0;
   size_t smem_bytes_reg = 0;
   DevBuf<uint16_t> d_slot_base;
-  DevBuf<int64_t> d_run_off;
-  DevBuf<uint32_t> d_runs;
-  // persistent (single cooperative launch) form: experimental, WFX_PERSISTENT=1.  Measured slower
-  // than the chained colour launches in round 1 (0.91 vs 0.70 ms at 64^3 P4: the write-back
-  // phase runs 4x longer while the next batch's staging traffic is in flight), so it is off.
-  bool persistent = false;
-  int nbatches = 0, persist_grid = 0;
-  unsigned long long epoch = 0;
-  DevBuf<uint8_t> d_batch_colour;
-  DevBuf<int32_t> d_colour_count;
-  DevBuf<unsigned long long> d_done;
   // host-call staging
   DevBuf<unsigned char> d_hx, d_hy;
 };
@@ -1144,7 +907,7 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
 {
   using C = Cfg<N>;
   using KernPtr = void (*)(BrickArgs<T>, DMat<T, N>, int);
-  const int variant = op->persistent ? 0 : op->variant;
+  const int variant = op->variant;
   KernPtr kern = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N>>;
   size_t smem = op->smem_bytes;
   if (variant == 1) kern = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>>, smem = op->smem_bytes_reg;
@@ -1169,8 +932,6 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   a.nloc_pad = op->nloc_pad;
   a.rounds_max = op->rounds_max;
   a.pf_stride = C::MINB * op->ctx->num_sms;
-  a.run_off = op->d_runs.n ? op->d_run_off.p : nullptr;
-  a.runs = op->d_runs.n ? op->d_runs.p : nullptr;
   a.slot_base = op->d_slot_base.p;
   a.Sx = op->Sx;
   a.Sy = op->Sy;
@@ -1181,27 +942,6 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   {
     const int n = (int)op->d_untouched.n;
     zero_entries_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(op->d_untouched.p, n, y);
-  }
-  if (op->persistent && op->cur_part < 0)
-  {
-    auto pk = stiff_brick_persistent<T, N, C::SLOT, C::W, C::MINB>;
-    if (op->persist_grid == 0)
-    {
-      int occ = 0;
-      WFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pk, C::SLOT * C::W, op->smem_bytes));
-      if (occ < 1) fail("stiffness: persistent kernel does not fit on an SM");
-      op->persist_grid = std::min(op->nbatches, occ * op->ctx->num_sms);
-    }
-    PersistArgs pa;
-    pa.batch_colour = op->d_batch_colour.p;
-    pa.colour_count = op->d_colour_count.p;
-    pa.done = op->d_done.p;
-    pa.epoch = ++op->epoch;
-    pa.nbatches = op->nbatches;
-    void* args[] = {(void*)&a, (void*)&pa, (void*)&Dm};
-    WFX_CUDA(cudaLaunchCooperativeKernel((void*)pk, dim3(op->persist_grid), dim3(C::SLOT * C::W), args,
-                                         op->smem_bytes, st));
-    return;
   }
   bool first = true;
   // execution colours of the requested part: interface batches [0, part_split), interior the rest
@@ -1241,8 +981,6 @@ void configure_brick(wfx_stiffness* op)
   if constexpr (N == 5 && sizeof(T) == 8)
     WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutP4D>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persistent<T, N, C::SLOT, C::W, C::MINB>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->ctx->smem_optin));
 }
 template <typename T>
 void configure_any(wfx_stiffness* op)
@@ -1471,26 +1209,6 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
         WFX_CUDA(cudaDeviceSynchronize());
         geom->g_colpos.assign(h_p4d_colpos, h_p4d_colpos + 25);
       }
-      if (!bp.runs.empty())
-      {
-        op->d_run_off.upload(bp.run_off);
-        op->d_runs.upload(bp.runs);
-      }
-      op->nbatches = bp.nbatches;
-      {
-        std::vector<uint8_t> bc((size_t)bp.nbatches);
-        std::vector<int32_t> cc((size_t)bp.ncolours);
-        for (int c = 0; c < bp.ncolours; ++c)
-        {
-          cc[c] = bp.colour_off[c + 1] - bp.colour_off[c];
-          for (int b = bp.colour_off[c]; b < bp.colour_off[c + 1]; ++b) bc[b] = (uint8_t)c;
-        }
-        op->d_batch_colour.upload(bc);
-        op->d_colour_count.upload(cc);
-        op->d_done.alloc((size_t)bp.ncolours);
-        WFX_CUDA(cudaMemset(op->d_done.p, 0, (size_t)bp.ncolours * sizeof(unsigned long long)));
-      }
-      if (const char* e = std::getenv("WFX_PERSISTENT")) op->persistent = std::atoi(e) != 0;
       if (!bp.untouched.empty()) op->d_untouched.upload(bp.untouched);
       if (op->dtype == WFX_F64) configure_any<double>(op.get());
       else configure_any<float>(op.get());
