@@ -17,6 +17,7 @@
 
 #include "wavefx.h"
 
+#include <array>
 #include <cstdint>
 #include <map>
 #include <memory>
@@ -104,13 +105,17 @@ class StiffnessOperator
 public:
   // `params` is accepted and -- exactly like the reference (common/operators.hpp:113-115) --
   // not used for the speed of sound: c0 = 1500 is hard-coded there.
+  // shared_dofs (distributed meshes): the local dofs that also live on another rank (the union of
+  // HaloSpec::send_indices and recv_indices).  Cells touching them are scheduled first so that the
+  // ghost exchange overlaps the interior cells.
   StiffnessOperator(std::shared_ptr<Geometry<T>> geom, const SpaceView& V, int bdegree,
-                    std::map<std::string, double>& params)
+                    std::map<std::string, double>& params, const std::vector<std::int32_t>& shared_dofs = {})
       : _geom(std::move(geom)), _ndofs(V.ndofs), _params(params)
   {
     if (bdegree != V.degree) throw std::runtime_error("wavefx: degree mismatch");
-    check(wfx_stiffness_create(_geom->context()->get(), _geom->get(), V.ndofs, V.dofmap, 1500.0,
-                               WFX_STIFF_AUTO, &_h));
+    check(wfx_stiffness_create_partitioned(_geom->context()->get(), _geom->get(), V.ndofs, V.dofmap, 1500.0,
+                                           WFX_STIFF_AUTO, (std::int64_t)shared_dofs.size(),
+                                           shared_dofs.empty() ? nullptr : shared_dofs.data(), &_h));
   }
   ~StiffnessOperator() { wfx_stiffness_destroy(_h); }
   StiffnessOperator(const StiffnessOperator&) = delete;
@@ -195,21 +200,96 @@ private:
 template <typename T>
 using MassOperatorCPU = MassOperator<T>;
 
+// Index data of a ghost exchange, as VectorUpdater reads it from the IndexMap
+// (demo/gpu_scatter_mpi/VectorUpdater.hpp:31-59 and the neighbour ranks of :69-80).
+struct HaloSpec
+{
+  std::vector<std::int32_t> send_ranks;   // destination ranks of the forward scatter
+  std::vector<std::int32_t> send_offsets; // scatter_fwd_indices().offsets()
+  std::vector<std::int32_t> send_indices; // scatter_fwd_indices().array(): owned local indices
+  std::vector<std::int32_t> recv_ranks;   // source ranks of the forward scatter
+  std::vector<std::int32_t> recv_offsets; // scatter_fwd_receive_offsets()
+  std::vector<std::int32_t> recv_indices; // size_local + scatter_fwd_ghost_positions()[i]: local ghost slots
+};
+
+// The NCCL communicator that takes the place of the IndexMap's MPI neighbourhood communicators.
+// `id` comes from Comm::unique_id() on rank 0 and is distributed by the caller
+// (MPI_Bcast(id.data(), 128, MPI_BYTE, 0, comm)).
+class Comm
+{
+public:
+  static std::array<char, 128> unique_id()
+  {
+    std::array<char, 128> id{};
+    check(wfx_comm_unique_id(id.data()));
+    return id;
+  }
+  Comm(std::shared_ptr<Context> ctx, const std::array<char, 128>& id, int nranks, int rank) : _ctx(std::move(ctx))
+  {
+    check(wfx_comm_create(_ctx->get(), id.data(), nranks, rank, &_h));
+  }
+  ~Comm() { wfx_comm_destroy(_h); }
+  Comm(const Comm&) = delete;
+  Comm& operator=(const Comm&) = delete;
+  wfx_comm* get() const { return _h; }
+  const std::shared_ptr<Context>& context() const { return _ctx; }
+
+private:
+  std::shared_ptr<Context> _ctx;
+  wfx_comm* _h = nullptr;
+};
+
+// VectorUpdater<T> (demo/gpu_scatter_mpi/VectorUpdater.hpp:21-215): owner -> ghost copy and
+// ghost -> owner add on DEVICE arrays laid out [owned | ghosts].  The begin/end pairs of the
+// reference collapse to one asynchronous call on the given stream.
+template <typename T>
+class VectorUpdater
+{
+public:
+  VectorUpdater(std::shared_ptr<Comm> comm, const HaloSpec& s) : _comm(std::move(comm))
+  {
+    check(wfx_halo_create(_comm->context()->get(), _comm->get(), std::is_same<T, double>::value ? WFX_F64 : WFX_F32,
+                          (int)s.send_ranks.size(), s.send_ranks.data(), s.send_offsets.data(), s.send_indices.data(),
+                          (int)s.recv_ranks.size(), s.recv_ranks.data(), s.recv_offsets.data(), s.recv_indices.data(),
+                          &_h));
+  }
+  ~VectorUpdater() { wfx_halo_destroy(_h); }
+  VectorUpdater(const VectorUpdater&) = delete;
+  VectorUpdater& operator=(const VectorUpdater&) = delete;
+  void update_fwd(T* x_dev, void* stream = nullptr) { check(wfx_halo_update_fwd(_h, x_dev, stream)); }          // :148
+  void update_rev(T* x_dev, void* stream = nullptr) { check(wfx_halo_update_rev(_h, x_dev, stream)); }          // :204
+  // reverse add then forward copy in one call: every copy of a shared dof ends bitwise identical
+  void update_rev_fwd(T* x_dev, void* stream = nullptr) { check(wfx_halo_update_rev_fwd(_h, x_dev, stream)); }
+  wfx_halo* get() const { return _h; }
+
+private:
+  std::shared_ptr<Comm> _comm;
+  wfx_halo* _h = nullptr;
+};
+
 // The wave model and its RK4 driver (common/LinearGLL.hpp:37-287), fp64 like the reference.
 class LinearGLLOpt
 {
 public:
+  // halo: the fp64 ghost exchange of a distributed mesh (nullptr on one rank); it must outlive the model
   LinearGLLOpt(std::shared_ptr<Context> ctx, const SpaceView& V, int& degreeOfBasis, double& speedOfSound,
-               double& sourceFrequency, double& pressureAmplitude)
-      : _ctx(std::move(ctx)), _ndofs(V.ndofs)
+               double& sourceFrequency, double& pressureAmplitude,
+               std::shared_ptr<VectorUpdater<double>> halo = nullptr, const HaloSpec* spec = nullptr)
+      : _ctx(std::move(ctx)), _halo(std::move(halo)), _ndofs(V.ndofs)
   {
+    std::vector<std::int32_t> shared;
+    if (spec)
+    {
+      shared = spec->send_indices;
+      shared.insert(shared.end(), spec->recv_indices.begin(), spec->recv_indices.end());
+    }
     _geom = std::make_shared<Geometry<double>>(_ctx, V);
     mass_op = std::make_shared<MassOperator<double>>(_geom, V, degreeOfBasis);                 // :105
     std::map<std::string, double> params{{"c0", speedOfSound}};
-    stiff_op = std::make_shared<StiffnessOperator<double>>(_geom, V, degreeOfBasis, params);    // :120
+    stiff_op = std::make_shared<StiffnessOperator<double>>(_geom, V, degreeOfBasis, params, shared);  // :120
     check(wfx_boundary_create(_ctx->get(), V.degree, WFX_F64, V.nfacets, V.facet_cell, V.facet_local,
                               V.facet_tag, V.npoints, V.x, V.xdofs, V.ndofs, V.dofmap, &_bnd));  // :113-115
-    check(wfx_wave_create(_ctx->get(), stiff_op->get(), mass_op->get(), _bnd, nullptr, V.size_local,
+    check(wfx_wave_create(_ctx->get(), stiff_op->get(), mass_op->get(), _bnd, _halo ? _halo->get() : nullptr, V.size_local,
                           speedOfSound, sourceFrequency, pressureAmplitude, &_wave));
   }
   ~LinearGLLOpt()
@@ -243,6 +323,7 @@ public:
 
 private:
   std::shared_ptr<Context> _ctx;
+  std::shared_ptr<VectorUpdater<double>> _halo;
   std::shared_ptr<Geometry<double>> _geom;
   std::int64_t _ndofs;
   wfx_boundary* _bnd = nullptr;
