@@ -24,13 +24,17 @@ struct wfx_boundary
 
 namespace
 {
+// g_dev (nullable): the source amplitude g in device memory; then c02g holds c0^2 and the product
+// c0^2 * g is formed here with the same single rounding as on the host.
 template <typename T>
 __global__ void boundary_kernel(int64_t nb, const int32_t* __restrict__ idx,
                                 const double* __restrict__ m1, const double* __restrict__ m2,
-                                double c02g, double c0, const T* __restrict__ vn, T* __restrict__ b)
+                                double c02g, double c0, const T* __restrict__ vn, T* __restrict__ b,
+                                const double* __restrict__ g_dev)
 {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= nb) return;
+  if (g_dev) c02g = __dmul_rn(c02g, *g_dev);
   const int32_t i = idx[t];
   b[i] = (T)((double)b[i] + c02g * m1[t] - c0 * m2[t] * (double)vn[i]);
 }
@@ -141,12 +145,27 @@ extern "C" int wfx_boundary_apply(wfx_boundary* op, double c0, double g, const v
   const double c02g = c0 * c0 * g;
   if (op->dtype == WFX_F64)
     boundary_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        op->nb, op->d_idx.p, op->d_m1.p, op->d_m2.p, c02g, c0, (const double*)vn, (double*)b);
+        op->nb, op->d_idx.p, op->d_m1.p, op->d_m2.p, c02g, c0, (const double*)vn, (double*)b, nullptr);
   else
     boundary_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        op->nb, op->d_idx.p, op->d_m1.p, op->d_m2.p, c02g, c0, (const float*)vn, (float*)b);
+        op->nb, op->d_idx.p, op->d_m1.p, op->d_m2.p, c02g, c0, (const float*)vn, (float*)b, nullptr);
   WFX_CUDA(cudaGetLastError());
   WFX_API_END
+}
+
+void wfx::boundary_apply_dev(wfx_boundary* op, double c0, const double* g_dev, const void* vn, void* b,
+                             cudaStream_t stream)
+{
+  if (!op || op->nb == 0) return;
+  const unsigned grid = (unsigned)((op->nb + 255) / 256);
+  const double c02 = c0 * c0;
+  if (op->dtype == WFX_F64)
+    boundary_kernel<double><<<grid, 256, 0, stream>>>(op->nb, op->d_idx.p, op->d_m1.p, op->d_m2.p, c02, c0,
+                                                       (const double*)vn, (double*)b, g_dev);
+  else
+    boundary_kernel<float><<<grid, 256, 0, stream>>>(op->nb, op->d_idx.p, op->d_m1.p, op->d_m2.p, c02, c0,
+                                                      (const float*)vn, (float*)b, g_dev);
+  WFX_CUDA(cudaGetLastError());
 }
 
 extern "C" int wfx_boundary_get(wfx_boundary* op, double* m1, double* m2)

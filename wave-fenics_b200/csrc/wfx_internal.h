@@ -103,6 +103,10 @@ double clamp_m101(double v);                              // xt::isclose clamp t
 int stiffness_dtype(const struct ::wfx_stiffness* op);    // wfx_stiffness.cu
 bool stiffness_has_split(const struct ::wfx_stiffness* op); // interface/interior parts present
 int halo_dtype(const struct ::wfx_halo* h);                // wfx_halo.cu
+// wfx_boundary_apply with the source amplitude g read from device memory at run time (CUDA-graph
+// replays of a time step change g without touching the graph), wfx_boundary.cu
+void boundary_apply_dev(struct ::wfx_boundary* op, double c0, const double* g_dev, const void* vn, void* b,
+                        cudaStream_t stream);
 
 struct ScopedDevice
 {

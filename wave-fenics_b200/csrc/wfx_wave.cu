@@ -32,8 +32,20 @@ struct wfx_wave
   // distributed runs: the ghost reduction runs on its own stream, ordered by events
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_iface = nullptr, ev_halo = nullptr;
+  // one-rank runs: a full time step (4 stages, ~40 launches) is captured once per step size
+  // into a CUDA graph and replayed; the four source amplitudes of the step live in g_dev
+  bool use_graph = true;
+  cudaGraphExec_t step_graph = nullptr;
+  double graph_dt = 0;
+  DevBuf<double> g_dev;
+  cudaStream_t own_stream = nullptr; // capture needs a non-legacy stream
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   ~wfx_wave()
   {
+    if (step_graph) cudaGraphExecDestroy(step_graph);
+    if (own_stream) cudaStreamDestroy(own_stream);
+    if (ev_in) cudaEventDestroy(ev_in);
+    if (ev_out) cudaEventDestroy(ev_out);
     if (ev_iface) cudaEventDestroy(ev_iface);
     if (ev_halo) cudaEventDestroy(ev_halo);
     if (comm_stream) cudaStreamDestroy(comm_stream);
@@ -103,6 +115,59 @@ void launch_stage(int stage, int64_t n, const void* b, const void* minv, void* u
 #undef WFX_STAGE
   WFX_CUDA(cudaGetLastError());
 }
+__global__ void set_source_kernel(double* g_dev, double g0, double g1, double g2, double g3)
+{
+  g_dev[0] = g0, g_dev[1] = g1, g_dev[2] = g2, g_dev[3] = g3;
+}
+
+// One time step of size dt on stream st: the four stages of LinearGLL.hpp:244-270.  g[i] is the
+// source amplitude of stage i; with g_from_dev the boundary kernels read it from w->g_dev
+// instead (graph capture).
+void enqueue_step(wfx_wave* w, double dt, const double* g, bool g_from_dev, cudaStream_t st)
+{
+  const double a_runge[5] = {0.0, 0.5, 0.5, 1.0, 0.0};
+  const double b_runge[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};
+  auto boundary = [&](int i, const void* vn) {
+    if (!w->bnd) return;
+    if (g_from_dev) boundary_apply_dev(w->bnd, w->c0, w->g_dev.p + i, vn, w->b.p, st);
+    else if (wfx_boundary_apply(w->bnd, w->c0, g[i], vn, w->b.p, st)) fail("%s", wfx_last_error()); // :175
+  };
+  for (int i = 0; i < 4; ++i)
+  {
+    // stage state: the solution itself at stage 0 (a_0 = 0), else un/vn
+    const void* un = i == 0 ? w->u_.p : w->un.p;
+    const void* vn = i == 0 ? w->v_.p : w->vn.p;
+    // f1 (:151-192)
+    if (!w->halo)
+    {
+      if (wfx_stiffness_apply(w->stiff, un, w->b.p, 0, st)) fail("%s", wfx_last_error()); // :173-174
+      boundary(i, vn);
+    }
+    else
+    {
+      // distributed: interface cells first, their ghost reduction (:176, which also stands
+      // for the scatter_fwd of the next stage, :164,167) on the comm stream while the interior
+      // cells run; the boundary term (facet masses assembled over the ranks) is added by
+      // every copy of a dof after the reduction.
+      static const bool overlap = [] { const char* e = std::getenv("WFX_WAVE_OVERLAP"); return !e || std::atoi(e) != 0; }();
+      const bool split = overlap && stiffness_has_split(w->stiff);
+      if (wfx_stiffness_apply_part(w->stiff, un, nullptr, w->b.p, 0, split ? 0 : -1, st)) fail("%s", wfx_last_error());
+      WFX_CUDA(cudaEventRecord(w->ev_iface, st));
+      WFX_CUDA(cudaStreamWaitEvent(w->comm_stream, w->ev_iface, 0));
+      if (wfx_halo_update_rev_fwd(w->halo, w->b.p, w->comm_stream)) fail("%s", wfx_last_error());
+      WFX_CUDA(cudaEventRecord(w->ev_halo, w->comm_stream));
+      if (split && wfx_stiffness_apply_part(w->stiff, un, nullptr, w->b.p, 0, 1, st)) fail("%s", wfx_last_error());
+      WFX_CUDA(cudaStreamWaitEvent(st, w->ev_halo, 0));
+      boundary(i, vn);
+    }
+    if (w->dtype == WFX_F64)
+      launch_stage<double>(i, w->n, w->b.p, w->minv, w->u_.p, w->v_.p, w->u0.p, w->v0.p, w->un.p,
+                           w->vn.p, dt * b_runge[i], dt * a_runge[i + 1], st);
+    else
+      launch_stage<float>(i, w->n, w->b.p, w->minv, w->u_.p, w->v_.p, w->u0.p, w->v0.p, w->un.p,
+                          w->vn.p, dt * b_runge[i], dt * a_runge[i + 1], st);
+  }
+}
 } // namespace
 
 extern "C" int wfx_wave_create(wfx_ctx* ctx, wfx_stiffness* stiff, wfx_mass* mass,
@@ -142,6 +207,14 @@ extern "C" int wfx_wave_create(wfx_ctx* ctx, wfx_stiffness* stiff, wfx_mass* mas
     WFX_CUDA(cudaStreamCreateWithPriority(&w->comm_stream, cudaStreamNonBlocking, prio_hi));
     WFX_CUDA(cudaEventCreateWithFlags(&w->ev_iface, cudaEventDisableTiming));
     WFX_CUDA(cudaEventCreateWithFlags(&w->ev_halo, cudaEventDisableTiming));
+  }
+  if (const char* e = std::getenv("WFX_WAVE_GRAPH")) w->use_graph = std::atoi(e) != 0;
+  if (!halo)
+  {
+    w->g_dev.alloc(4);
+    WFX_CUDA(cudaStreamCreateWithFlags(&w->own_stream, cudaStreamNonBlocking));
+    WFX_CUDA(cudaEventCreateWithFlags(&w->ev_in, cudaEventDisableTiming));
+    WFX_CUDA(cudaEventCreateWithFlags(&w->ev_out, cudaEventDisableTiming));
   }
   if (wfx_mass_inverse_diagonal(mass, &w->minv)) fail("%s", wfx_last_error());
   const size_t nb = (size_t)ndofs * (w->dtype == WFX_F64 ? 8 : 4);
@@ -204,55 +277,67 @@ extern "C" int wfx_wave_rk4(wfx_wave* w, double t0, double tf, double dt, int64_
   ScopedDevice sd(w->ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
   const double w0 = 2.0 * M_PI * w->f0, T = 1.0 / w->f0, alpha = 4.0; // LinearGLL.hpp:96-99
-  const double a_runge[5] = {0.0, 0.5, 0.5, 1.0, 0.0};
-  const double b_runge[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};
   const double c_runge[4] = {0.0, 0.5, 0.5, 1.0};
+  // Graph replay (one rank only: the distributed step spans two streams and NCCL).  A capture
+  // cannot run on the legacy default stream: such callers are moved to an internal stream that
+  // is ordered after and before the caller's stream by events.
+  const bool graph_ok = w->use_graph && !w->halo;
+  cudaStream_t ws = st;
+  if (graph_ok && (st == nullptr || st == cudaStreamLegacy))
+  {
+    ws = w->own_stream;
+    WFX_CUDA(cudaEventRecord(w->ev_in, st));
+    WFX_CUDA(cudaStreamWaitEvent(ws, w->ev_in, 0));
+  }
   double t = t0;
   int64_t step = 0;
+  const double dt_nominal = dt;
   while (t < tf) // :241
   {
     if (max_steps > 0 && step >= max_steps) break;
     dt = std::min(dt, tf - t); // :242
+    double g[4];
     for (int i = 0; i < 4; ++i)
     {
       const double tn = t + c_runge[i] * dt; // :257
-      // stage state: the solution itself at stage 0 (a_0 = 0), else un/vn
-      const void* un = i == 0 ? w->u_.p : w->un.p;
-      const void* vn = i == 0 ? w->v_.p : w->vn.p;
-      // f1 (:151-192)
       const double window = tn < T * alpha ? 0.5 * (1.0 - std::cos(w->f0 * M_PI * tn / alpha)) : 1.0;
-      const double g = window * w->p0 * w0 / w->c0 * std::cos(w0 * tn); // :162
-      if (!w->halo)
-      {
-        if (wfx_stiffness_apply(w->stiff, un, w->b.p, 0, st)) fail("%s", wfx_last_error()); // :173-174
-        if (w->bnd && wfx_boundary_apply(w->bnd, w->c0, g, vn, w->b.p, st)) fail("%s", wfx_last_error()); // :175
-      }
-      else
-      {
-        // distributed: interface cells first, their ghost reduction (:176, which also stands
-        // for the scatter_fwd of the next stage, :164,167) on the comm stream while the interior
-        // cells run; the boundary term (facet masses assembled over the ranks) is added by
-        // every copy of a dof after the reduction.
-        static const bool overlap = [] { const char* e = std::getenv("WFX_WAVE_OVERLAP"); return !e || std::atoi(e) != 0; }();
-        const bool split = overlap && stiffness_has_split(w->stiff);
-        if (wfx_stiffness_apply_part(w->stiff, un, nullptr, w->b.p, 0, split ? 0 : -1, st)) fail("%s", wfx_last_error());
-        WFX_CUDA(cudaEventRecord(w->ev_iface, st));
-        WFX_CUDA(cudaStreamWaitEvent(w->comm_stream, w->ev_iface, 0));
-        if (wfx_halo_update_rev_fwd(w->halo, w->b.p, w->comm_stream)) fail("%s", wfx_last_error());
-        WFX_CUDA(cudaEventRecord(w->ev_halo, w->comm_stream));
-        if (split && wfx_stiffness_apply_part(w->stiff, un, nullptr, w->b.p, 0, 1, st)) fail("%s", wfx_last_error());
-        WFX_CUDA(cudaStreamWaitEvent(st, w->ev_halo, 0));
-        if (w->bnd && wfx_boundary_apply(w->bnd, w->c0, g, vn, w->b.p, st)) fail("%s", wfx_last_error());
-      }
-      if (w->dtype == WFX_F64)
-        launch_stage<double>(i, w->n, w->b.p, w->minv, w->u_.p, w->v_.p, w->u0.p, w->v0.p, w->un.p,
-                             w->vn.p, dt * b_runge[i], dt * a_runge[i + 1], st);
-      else
-        launch_stage<float>(i, w->n, w->b.p, w->minv, w->u_.p, w->v_.p, w->u0.p, w->v0.p, w->un.p,
-                            w->vn.p, dt * b_runge[i], dt * a_runge[i + 1], st);
+      g[i] = window * w->p0 * w0 / w->c0 * std::cos(w0 * tn); // :162
     }
+    if (graph_ok && dt == dt_nominal)
+    {
+      if (!w->step_graph || w->graph_dt != dt)
+      {
+        if (w->step_graph) WFX_CUDA(cudaGraphExecDestroy(w->step_graph));
+        w->step_graph = nullptr;
+        cudaGraph_t graph = nullptr;
+        WFX_CUDA(cudaStreamBeginCapture(ws, cudaStreamCaptureModeThreadLocal));
+        try
+        {
+          enqueue_step(w, dt, nullptr, true, ws);
+        }
+        catch (...)
+        {
+          cudaStreamEndCapture(ws, &graph);
+          if (graph) cudaGraphDestroy(graph);
+          throw;
+        }
+        WFX_CUDA(cudaStreamEndCapture(ws, &graph));
+        const cudaError_t ie = cudaGraphInstantiate(&w->step_graph, graph, 0);
+        cudaGraphDestroy(graph);
+        WFX_CUDA(ie);
+        w->graph_dt = dt;
+      }
+      set_source_kernel<<<1, 1, 0, ws>>>(w->g_dev.p, g[0], g[1], g[2], g[3]);
+      WFX_CUDA(cudaGraphLaunch(w->step_graph, ws));
+    }
+    else enqueue_step(w, dt, g, false, ws);
     t += dt;
     step += 1;
+  }
+  if (ws != st)
+  {
+    WFX_CUDA(cudaEventRecord(w->ev_out, ws));
+    WFX_CUDA(cudaStreamWaitEvent(st, w->ev_out, 0));
   }
   if (steps_out) *steps_out = step;
   if (t_end) *t_end = t;
