@@ -388,3 +388,43 @@ def test_stiffness_interface_interior_split(wfx, orc, torch):
     want = kx / mass.diagonal()
     want[shared] = kx[shared]  # shared dofs are left for the ghost reduction to scale
     assert rel_l2(y3.cpu().numpy(), want) < TOL64
+
+
+# ---- kernel variants behind environment switches stay correct -----------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"WFX_REGULAR": "0"}, {"WFX_TUNED_STRIDES": "1"}, {"WFX_NO_UNIFORM": "1"}])
+def test_stiffness_kernel_variants(wfx, orc, torch, monkeypatch, env):
+    """The generic (staged local dofmap) kernel, the conflict-free P4 layout with reordered G columns
+    and the loaded batch headers are not the default on structured meshes: force each and compare
+    with the default kernel (bitwise for the generic kernel: same arithmetic, same order) and the
+    oracle."""
+    P, N = 4, 6
+    mesh = _mesh(wfx, N, P, 0.15, renumber=11)
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(mesh.ndofs)
+    ref = wfx.StiffnessOperator(mesh, P, {"c0": 1500.0})
+    y_ref = torch.empty(mesh.ndofs, dtype=torch.float64, device="cuda")
+    ref.apply(dev(torch, x), y_ref, beta=0)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    geo = wfx.Geometry(mesh, P)
+    op = wfx.StiffnessOperator(mesh, P, {"c0": 1500.0}, geometry=geo)
+    y = torch.full_like(y_ref, float("nan"))
+    op.apply(dev(torch, x), y, beta=0)
+    if "WFX_TUNED_STRIDES" in env:
+        assert rel_l2(y.cpu().numpy(), y_ref.cpu().numpy()) < 1e-14
+        # the geometry's columns were reordered in place: the exported G must not change
+        Go, _ = orc.precompute_geometric_data(mesh, P)
+        iu = np.triu_indices(3)
+        assert np.array_equal(geo.get()[0][:, :, iu[0], iu[1]], Go[:, :, iu[0], iu[1]])
+        # and a second operator on the same (reordered) geometry with the simple kernel agrees
+        op2 = wfx.StiffnessOperator(mesh, P, {"c0": 1500.0}, mode=wfx.capi.STIFF_CELL_COLOUR, geometry=geo)
+        y2 = torch.zeros_like(y_ref)
+        op2.apply(dev(torch, x), y2, beta=0)
+        assert rel_l2(y2.cpu().numpy(), y_ref.cpu().numpy()) < 1e-14
+    else:
+        assert torch.equal(y, y_ref)
+    Go, _ = orc.precompute_geometric_data(mesh, P)
+    yo = np.zeros(mesh.ndofs)
+    orc.stiffness_apply(mesh, P, Go, x, yo, dense=True)
+    assert rel_l2(y.cpu().numpy(), yo) < TOL64
