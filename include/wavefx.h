@@ -131,7 +131,9 @@ int wfx_stiffness_apply(wfx_stiffness* op, const void* x_dev, void* y_dev, int b
  * part 0's result can overlap part 1:  apply_part(.., 0) ; halo on another stream ;
  * apply_part(.., 1).  The fused scaling of wfx_stiffness_apply_scaled is then applied to
  * non-shared dofs only; shared dofs are scaled by wfx_halo_update_rev_fwd_scaled after
- * their sum is complete.  part = -1 runs both parts. */
+ * their sum is complete.  part = -1 runs both parts.  Part 1 continues the apply that the
+ * preceding part-0 call on the same stream started: same x_dev / y_dev, x unchanged in between
+ * (its first kernel may start while part 0 is still draining). */
 int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, int64_t ndofs,
                                      const int32_t* dofmap_host, double c0, int flags,
                                      int64_t nshared, const int32_t* shared_dofs_host,

@@ -865,6 +865,7 @@ struct wfx_stiffness
   int ncolours = 0, nloc_pad = 0, W = 0, rounds_max = 0;
   int part_split = 0; // first execution colour of the interior part (distributed meshes)
   int cur_part = -1;  // part selected by the running apply: -1 all, 0 interface, 1 interior
+  bool part0_launched = false; // the last apply was an interface part that launched kernels
   size_t smem_bytes = 0;
   std::vector<int32_t> colour_off;
   DevBuf<int64_t> d_dof_off;
@@ -943,7 +944,11 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
     const int n = (int)op->d_untouched.n;
     zero_entries_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(op->d_untouched.p, n, y);
   }
-  bool first = true;
+  // The interior part continues the apply its interface part started (same x, earlier in this
+  // stream): its first launch may overlap that part's tail like any later colour.  Only if the
+  // interface part really launched something -- otherwise the kernel in front of us is x's producer.
+  bool first = !(op->cur_part == 1 && op->part0_launched);
+  if (op->cur_part != 1) op->part0_launched = false;
   // execution colours of the requested part: interface batches [0, part_split), interior the rest
   const int k0 = op->cur_part == 1 ? op->part_split : 0;
   const int k1 = op->cur_part == 0 ? op->part_split : op->ncolours;
@@ -965,7 +970,9 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
     cfg.numAttrs = (op->use_pdl && !first) ? 1 : 0;
     WFX_CUDA(cudaLaunchKernelEx(&cfg, kern, a, Dm, beg));
     first = false;
+    if (op->cur_part == 0) op->part0_launched = true;
   }
+  if (op->cur_part == 1) op->part0_launched = false;
 }
 
 // opt in to the large dynamic shared-memory carve-out once per operator (per device)
