@@ -643,12 +643,8 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
     T u[N], yv[N], f2[N];
     if constexpr (REG)
     {
-#ifndef WFX_NO_G_ROTATE
       const V2* gnext = cn >= 0 ? reinterpret_cast<const V2*>(a.G6 + (int64_t)cn * (6 * ND)) + gcol : nullptr;
       g_requested = active;
-#else
-      const V2* gnext = nullptr;
-#endif
       const int base = active ? (int)sbase[r * W + slot] : 0;
       T lj[N], lI[N];
 #pragma unroll
@@ -689,15 +685,12 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
           const int c2 = scell[(r + 1 + PF_DIST) * W + slot];
           if (c2 >= 0) l2_prefetch_bulk(a.G6 + (int64_t)c2 * (6 * ND), (uint32_t)(6 * ND * sizeof(T)));
         }
-#ifndef WFX_NO_PF_OWN_BDOFS
       // the write-back walks the batch's dof list again: keep it in L2 (it was read ~30 us ago)
       if (r == nr - 1 && tid == SLOT * (W > 1 ? 1 : 0))
       {
         const int64_t dn = d0 & ~(int64_t)3;
         l2_prefetch_bulk(a.bdofs + dn, (uint32_t)(((d0 + nloc + 3) & ~(int64_t)3) - dn) * 4u);
       }
-#endif
-#ifndef WFX_NO_PF_NEXT_CTA
       // In the last round, warm L2 for the CTA that will take this one's place on the SM
       // (blocks are dispatched in index order, a.pf_stride of them are resident): the first
       // cells' G, the batch's dof list and its local dofmap -- what that CTA waits for first.
@@ -726,7 +719,6 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
           }
         }
       }
-#endif
     }
     tm.mark(4);
     if constexpr (SLOT <= 32) cell_part2<T, N, L>(f2, tiles, ro, Dm, active, WarpSync(), yv, tm);
@@ -914,6 +906,7 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   if (variant == 1) kern = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>>, smem = op->smem_bytes_reg;
   if constexpr (N == 5 && sizeof(T) == 8)
     if (variant == 2) kern = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutP4D>, smem = op->smem_bytes_reg;
+  // experiment knob ("L1 is part of the budget"): extra dynamic shared memory per CTA
   static const size_t smem_pad = std::getenv("WFX_SMEM_PAD") ? (size_t)std::atoi(std::getenv("WFX_SMEM_PAD")) : 0;
   smem += smem_pad;
   DMat<T, N> Dm;
