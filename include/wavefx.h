@@ -69,6 +69,12 @@ int wfx_deriv_1d(int P, double* D);
  * = second member of tabulate_basis_and_permutation (common/operators.hpp:24). perm[(P+1)^3]. */
 int wfx_compute_permutations(int P, int32_t* perm);
 
+/* tabulate_basis_and_permutation (common/operators.hpp:13-32): table[4][nq][nd] (basis, d/dX0,
+ * d/dX1, d/dX2 at the GLL points; dofs in DOLFINx order, points in the quadrature's tensor order,
+ * entries clamped as at :26-29) and perm[nd].  Either output may be NULL.  The GPU operators never
+ * form this dense table; it is exported for callers of the reference function. */
+int wfx_tabulate_basis_and_permutation(int P, double* table, int32_t* perm);
+
 /* reorder_dofmap (common/permute.hpp:10-28): out[c*nd+t] = in[c*nd+perm[t]]. */
 int wfx_reorder_dofmap(int P, int64_t ncells, const int32_t* in_host, int32_t* out_host);
 

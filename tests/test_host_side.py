@@ -143,3 +143,16 @@ def test_cfl_timestep_matches_reference_formula(wfx):
     raw = 0.5 * np.sqrt(3) * side / (1500.0 * 16)
     spp = int(2e-6 / raw + 1)
     assert dt == 2e-6 / spp and dt <= raw
+
+
+@pytest.mark.parametrize("P", [1, 2, 4, 6])
+def test_tabulate_basis_and_permutation_matches_oracle(wfx, orc, P):
+    # a2: the dense table of common/operators.hpp:13-32 (exported for callers of that function)
+    table, perm = wfx.capi.tabulate_basis_and_permutation(P)
+    nd = (P + 1) ** 3
+    assert np.array_equal(perm, orc.perm(P))
+    np.testing.assert_allclose(table[1:], orc.tabulate_dphi(P).reshape(3, nd, nd), rtol=1e-13, atol=1e-13)
+    # collocation: phi_i(x_q) = delta in DOLFINx dof order
+    ident = np.zeros((nd, nd))
+    ident[np.arange(nd), perm] = 1.0
+    assert np.array_equal(table[0], ident)

@@ -40,6 +40,7 @@ _SIG = {
     "wfx_gll": [C.c_int, _c_f64p, _c_f64p],
     "wfx_deriv_1d": [C.c_int, _c_f64p],
     "wfx_compute_permutations": [C.c_int, _c_i32p],
+    "wfx_tabulate_basis_and_permutation": [C.c_int, _c_f64p, _c_i32p],
     "wfx_reorder_dofmap": [C.c_int, C.c_int64, _c_i32p, _c_i32p],
     "wfx_tabulate_1d": [C.c_int, C.c_int, C.c_int, _c_f64p, C.POINTER(C.c_int)],
     "wfx_ctx_create": [C.c_int, _vpp],
@@ -164,6 +165,15 @@ def compute_permutations(P):
     perm = np.empty((P + 1) ** 3, dtype=np.int32)
     call("wfx_compute_permutations", P, i32p(perm))
     return perm
+
+
+def tabulate_basis_and_permutation(P):
+    """(table [4, nq, nd], perm [nd]) as common/operators.hpp:13-32 returns them."""
+    nd = (P + 1) ** 3
+    table = np.empty((4, nd, nd))
+    perm = np.empty(nd, dtype=np.int32)
+    call("wfx_tabulate_basis_and_permutation", P, f64p(table.reshape(-1)), i32p(perm))
+    return table, perm
 
 
 def reorder_dofmap(dofmap, P):

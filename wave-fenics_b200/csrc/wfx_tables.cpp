@@ -4,6 +4,7 @@
 // common/precompute.hpp:179-199); Basix itself is not a dependency.
 #include "wfx_internal.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -209,6 +210,39 @@ extern "C" int wfx_compute_permutations(int P, int32_t* perm)
 {
   WFX_API_BEGIN
   tensor_perm(P, perm);
+  WFX_API_END
+}
+
+// tabulate_basis_and_permutation (common/operators.hpp:13-32): table[4][nq][nd], the basis and its
+// three reference derivatives at the GLL points (= the nodes: collocated), dof axis in DOLFINx order,
+// point axis in the tensor order of the quadrature, every entry clamped as at :26-29.
+extern "C" int wfx_tabulate_basis_and_permutation(int P, double* table, int32_t* perm_out)
+{
+  WFX_API_BEGIN
+  const int n = P + 1, nd = n * n * n;
+  std::vector<int32_t> perm(nd);
+  tensor_perm(P, perm.data());
+  if (perm_out) std::copy(perm.begin(), perm.end(), perm_out);
+  if (table)
+  {
+    double D[WFX_MAXN * WFX_MAXN];
+    deriv_1d(P, D, true);
+    std::fill(table, table + (size_t)4 * nd * nd, 0.0);
+    auto at = [&](int a, size_t q, int dof) -> double& { return table[((size_t)a * nd + q) * nd + dof]; };
+    for (int qa = 0; qa < n; ++qa)
+      for (int qb = 0; qb < n; ++qb)
+        for (int qc = 0; qc < n; ++qc)
+        {
+          const size_t q = ((size_t)qa * n + qb) * n + qc;
+          at(0, q, perm[q]) = 1.0; // phi_i(x_q) = delta
+          for (int i = 0; i < n; ++i)
+          {
+            at(1, q, perm[(i * n + qb) * n + qc]) = D[qa * n + i];
+            at(2, q, perm[(qa * n + i) * n + qc]) = D[qb * n + i];
+            at(3, q, perm[(qa * n + qb) * n + i]) = D[qc * n + i];
+          }
+        }
+  }
   WFX_API_END
 }
 
