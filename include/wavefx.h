@@ -255,6 +255,14 @@ int wfx_wave_init(wfx_wave* wave);                                   /* :131-134
 int wfx_wave_set_state(wfx_wave* wave, const void* u_host, const void* v_host);
 int wfx_wave_get_state(wfx_wave* wave, void* u_host, void* v_host);
 int wfx_wave_state_ptrs(wfx_wave* wave, void** u_dev, void** v_dev);
+/* The right-hand sides on their own, device vectors of ndofs entries (dtype of the model):
+ *   f0(t, u, v, result): result = v                                  (:141-144)
+ *   f1(t, u, v, result): result = M^-1 (-c0^2 K u + boundary(g(t), v)) (:151-192), including the
+ *   ghost reduction on a distributed mesh.  result must not alias u or v. */
+int wfx_wave_f0(wfx_wave* wave, double t, const void* u_dev, const void* v_dev, void* result_dev,
+                void* stream);
+int wfx_wave_f1(wfx_wave* wave, double t, const void* u_dev, const void* v_dev, void* result_dev,
+                void* stream);
 /* rk4(startTime, finalTime, timeStep) (:198-287).  max_steps <= 0: run to tf.
  * Returns steps taken and the final time. */
 int wfx_wave_rk4(wfx_wave* wave, double t0, double tf, double dt, int64_t max_steps,

@@ -428,3 +428,33 @@ def test_stiffness_kernel_variants(wfx, orc, torch, monkeypatch, env):
     yo = np.zeros(mesh.ndofs)
     orc.stiffness_apply(mesh, P, Go, x, yo, dense=True)
     assert rel_l2(y.cpu().numpy(), yo) < TOL64
+
+
+@pytest.mark.gpu
+def test_right_hand_sides_f0_f1(wfx, orc, torch):
+    """LinearGLLOpt::f0 / f1 (LinearGLL.hpp:141-192) on their own: f1 = (K u + c0^2 g(t) m1 - c0 m2 v) / m
+    composed from the oracle's pieces."""
+    P, c0, f0, p0 = 4, 1500.0, 0.5e6, 6e4
+    mesh = _mesh(wfx, 4, P, 0.15)
+    Go, detJ = orc.precompute_geometric_data(mesh, P)
+    m = np.zeros(mesh.ndofs)
+    orc.mass_apply(mesh, P, detJ, np.ones(mesh.ndofs), m)
+    m1, m2 = orc.boundary_facet_mass(mesh, P)
+    rng = np.random.default_rng(3)
+    u, v = rng.standard_normal(mesh.ndofs), rng.standard_normal(mesh.ndofs)
+    eqn = wfx.LinearGLLOpt(mesh, None, P, c0, f0, p0)
+    ud, vd = dev(torch, u), dev(torch, v)
+    res = torch.full_like(ud, float("nan"))
+    for t in (0.3e-6, 2.0e-5):                       # inside and after the Hann ramp (4 periods = 8 us)
+        w0, T, alpha = 2.0 * np.pi * f0, 1.0 / f0, 4.0
+        window = 0.5 * (1.0 - np.cos(f0 * np.pi * t / alpha)) if t < T * alpha else 1.0
+        g = window * p0 * w0 / c0 * np.cos(w0 * t)
+        b = np.zeros(mesh.ndofs)
+        orc.stiffness_apply(mesh, P, Go, u, b, dense=True)
+        want = (b + c0 * c0 * g * m1 - c0 * m2 * v) / m
+        eqn.f1(t, ud, vd, res)
+        assert rel_l2(res.cpu().numpy(), want) < TOL64
+    eqn.f0(0.0, ud, vd, res)
+    assert torch.equal(res, vd)
+    with pytest.raises(RuntimeError):
+        eqn.f1(0.0, ud, vd, ud)

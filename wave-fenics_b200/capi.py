@@ -99,6 +99,8 @@ _SIG = {
     "wfx_wave_set_state": [_vp, _vp, _vp],
     "wfx_wave_get_state": [_vp, _vp, _vp],
     "wfx_wave_state_ptrs": [_vp, _vpp, _vpp],
+    "wfx_wave_f0": [_vp, C.c_double, _vp, _vp, _vp, _vp],
+    "wfx_wave_f1": [_vp, C.c_double, _vp, _vp, _vp, _vp],
     "wfx_wave_rk4": [_vp, C.c_double, C.c_double, C.c_double, C.c_int64, _c_i64p, _c_f64p, _vp],
     "wfx_wave_destroy": [_vp],
     # debug helper (not in wavefx.h): host-only plan construction + verification

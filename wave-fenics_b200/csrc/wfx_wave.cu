@@ -269,6 +269,44 @@ extern "C" int wfx_wave_state_ptrs(wfx_wave* w, void** u, void** v)
   WFX_API_END
 }
 
+namespace
+{
+// g(t) of LinearGLL.hpp:155-162: Hann ramp over the first alpha periods
+double source_amplitude(const wfx_wave* w, double tn)
+{
+  const double w0 = 2.0 * M_PI * w->f0, T = 1.0 / w->f0, alpha = 4.0; // :96-99
+  const double window = tn < T * alpha ? 0.5 * (1.0 - std::cos(w->f0 * M_PI * tn / alpha)) : 1.0;
+  return window * w->p0 * w0 / w->c0 * std::cos(w0 * tn);
+}
+} // namespace
+
+extern "C" int wfx_wave_f0(wfx_wave* w, double, const void* u, const void* v, void* result, void* stream)
+{
+  WFX_API_BEGIN
+  if (!w) fail("wave model is NULL");
+  if (!u || !v || !result) fail("f0: NULL vector");
+  ScopedDevice sd(w->ctx->device);
+  const size_t nb = (size_t)w->n * (w->dtype == WFX_F64 ? 8 : 4);
+  if (result != v) WFX_CUDA(cudaMemcpyAsync(result, v, nb, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  WFX_API_END
+}
+
+extern "C" int wfx_wave_f1(wfx_wave* w, double t, const void* u, const void* v, void* result, void* stream)
+{
+  WFX_API_BEGIN
+  if (!w) fail("wave model is NULL");
+  if (!u || !v || !result) fail("f1: NULL vector");
+  if (result == u || result == v) fail("f1: result must not alias u or v");
+  ScopedDevice sd(w->ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const double g = source_amplitude(w, t);
+  if (wfx_stiffness_apply(w->stiff, u, w->b.p, 0, st)) fail("%s", wfx_last_error());                     // :173-174
+  if (w->halo && wfx_halo_update_rev_fwd(w->halo, w->b.p, st)) fail("%s", wfx_last_error());             // :176
+  if (w->bnd && wfx_boundary_apply(w->bnd, w->c0, g, v, w->b.p, st)) fail("%s", wfx_last_error());       // :175
+  if (wfx_mass_apply_inverse(w->mass, w->b.p, result, st)) fail("%s", wfx_last_error());                 // :188-191
+  WFX_API_END
+}
+
 extern "C" int wfx_wave_rk4(wfx_wave* w, double t0, double tf, double dt, int64_t max_steps,
                             int64_t* steps_out, double* t_end, void* stream)
 {
@@ -276,7 +314,6 @@ extern "C" int wfx_wave_rk4(wfx_wave* w, double t0, double tf, double dt, int64_
   if (!w) fail("wave model is NULL");
   ScopedDevice sd(w->ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
-  const double w0 = 2.0 * M_PI * w->f0, T = 1.0 / w->f0, alpha = 4.0; // LinearGLL.hpp:96-99
   const double c_runge[4] = {0.0, 0.5, 0.5, 1.0};
   // Graph replay (one rank only: the distributed step spans two streams and NCCL).  A capture
   // cannot run on the legacy default stream: such callers are moved to an internal stream that
@@ -300,8 +337,7 @@ extern "C" int wfx_wave_rk4(wfx_wave* w, double t0, double tf, double dt, int64_
     for (int i = 0; i < 4; ++i)
     {
       const double tn = t + c_runge[i] * dt; // :257
-      const double window = tn < T * alpha ? 0.5 * (1.0 - std::cos(w->f0 * M_PI * tn / alpha)) : 1.0;
-      g[i] = window * w->p0 * w0 / w->c0 * std::cos(w0 * tn); // :162
+      g[i] = source_amplitude(w, tn); // :155-162
     }
     if (graph_ok && dt == dt_nominal)
     {

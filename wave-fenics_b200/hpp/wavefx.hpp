@@ -301,6 +301,15 @@ public:
   LinearGLLOpt& operator=(const LinearGLLOpt&) = delete;
 
   void init() { check(wfx_wave_init(_wave)); }                                                  // :131-134
+  // the right-hand sides on their own (:141-192), device arrays of ndofs entries
+  void f0(double t, const double* u_dev, const double* v_dev, double* result_dev, void* stream = nullptr)
+  {
+    check(wfx_wave_f0(_wave, t, u_dev, v_dev, result_dev, stream));
+  }
+  void f1(double t, const double* u_dev, const double* v_dev, double* result_dev, void* stream = nullptr)
+  {
+    check(wfx_wave_f1(_wave, t, u_dev, v_dev, result_dev, stream));
+  }
   // rk4(startTime, finalTime, timeStep) (:198-287); returns the number of steps taken
   std::int64_t rk4(double& startTime, double& finalTime, double& timeStep)
   {

@@ -336,6 +336,16 @@ class LinearGLLOpt:
         capi.call("wfx_wave_get_state", self.handle, C.c_void_p(u.ctypes.data), C.c_void_p(v.ctypes.data))
         return u, v
 
+    def f0(self, t, u, v, result):
+        """result = v (LinearGLL.hpp:141-144); device tensors."""
+        capi.call("wfx_wave_f0", self.handle, float(t), C.c_void_p(u.data_ptr()), C.c_void_p(v.data_ptr()),
+                  C.c_void_p(result.data_ptr()), _stream_ptr())
+
+    def f1(self, t, u, v, result):
+        """result = M^-1 (-c0^2 K u + boundary(g(t), v)) (LinearGLL.hpp:151-192); device tensors."""
+        capi.call("wfx_wave_f1", self.handle, float(t), C.c_void_p(u.data_ptr()), C.c_void_p(v.data_ptr()),
+                  C.c_void_p(result.data_ptr()), _stream_ptr())
+
     def rk4(self, startTime, finalTime, timeStep, max_steps=0, stream=None):
         steps, t_end = C.c_int64(), C.c_double()
         capi.call("wfx_wave_rk4", self.handle, float(startTime), float(finalTime), float(timeStep),
