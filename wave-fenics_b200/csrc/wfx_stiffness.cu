@@ -797,17 +797,18 @@ __global__ void permute_g_columns_kernel(T* __restrict__ G6, int64_t nrows)
 // per-degree launch configuration
 template <int N> struct Cfg;
 //                          SLOT  W  brick edge  cells/block (simple)  min CTAs/SM (brick)
-template <> struct Cfg<3> { static constexpr int SLOT = 16, W = 16, BE = 8, CPB = 16, MINB = 2; };
-template <> struct Cfg<4> { static constexpr int SLOT = 16, W = 8, BE = 4, CPB = 16, MINB = 4; };
+//                          preferred shared-memory carve-out in percent, fp64 / fp32 (0 = driver's choice)
+template <> struct Cfg<3> { static constexpr int SLOT = 16, W = 16, BE = 8, CPB = 16, MINB = 2, CARVEOUT = 0, CARVEOUT32 = 0; };
+template <> struct Cfg<4> { static constexpr int SLOT = 16, W = 8, BE = 4, CPB = 16, MINB = 4, CARVEOUT = 0, CARVEOUT32 = 0; };
 #ifndef WFX_P4_W
 #define WFX_P4_W 8
 #define WFX_P4_BE 4
 #define WFX_P4_MINB 2
 #endif
-template <> struct Cfg<5> { static constexpr int SLOT = 32, W = WFX_P4_W, BE = WFX_P4_BE, CPB = 8, MINB = WFX_P4_MINB; };
-template <> struct Cfg<6> { static constexpr int SLOT = 64, W = 1, BE = 2, CPB = 4, MINB = 8; };
-template <> struct Cfg<7> { static constexpr int SLOT = 64, W = 1, BE = 2, CPB = 4, MINB = 5; };
-template <> struct Cfg<8> { static constexpr int SLOT = 64, W = 1, BE = 2, CPB = 2, MINB = 3; };
+template <> struct Cfg<5> { static constexpr int SLOT = 32, W = WFX_P4_W, BE = WFX_P4_BE, CPB = 8, MINB = WFX_P4_MINB, CARVEOUT = 0, CARVEOUT32 = 0; };
+template <> struct Cfg<6> { static constexpr int SLOT = 64, W = 1, BE = 2, CPB = 4, MINB = 8, CARVEOUT = 58, CARVEOUT32 = 0; };
+template <> struct Cfg<7> { static constexpr int SLOT = 64, W = 1, BE = 2, CPB = 4, MINB = 5, CARVEOUT = 72, CARVEOUT32 = 58; };
+template <> struct Cfg<8> { static constexpr int SLOT = 64, W = 1, BE = 2, CPB = 2, MINB = 3, CARVEOUT = 0, CARVEOUT32 = 0; };
 
 struct LaunchCfg
 {
@@ -981,6 +982,17 @@ void configure_brick(wfx_stiffness* op)
   if constexpr (N == 5 && sizeof(T) == 8)
     WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutP4D>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  // Shared-memory carve-out (percent of the SM's 228 KB): L1 is what is left, and L1 is the landing
+  // buffer of the loads in flight.  Default: the driver's choice (max occupancy).
+  int carve = sizeof(T) == 8 ? C::CARVEOUT : C::CARVEOUT32; // measured per degree (profiles/r1_degree_sweep.md)
+  if (const char* e = std::getenv("WFX_CARVEOUT")) carve = std::atoi(e);
+  if (carve > 0)
+  {
+    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N>>,
+                                  cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>>,
+                                  cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+  }
 }
 template <typename T>
 void configure_any(wfx_stiffness* op)
