@@ -506,11 +506,15 @@ struct BrickArgs
   int uni_nloc, uni_nr;      // > 0: every batch has this many dof positions / rounds (no header loads)
 };
 
-// Shared memory of one CTA:  xl[nloc_pad] | yl[nloc_pad] | tiles[W][slot_elems] | sldm[rounds_max*W*NDP] (u16)
-//                            | scell[rounds_max*W] (i32) | mbarrier (u64)
+// Shared memory of one CTA
+//   generic:  xl[nloc_pad] | yl[nloc_pad] | tiles[W][L::SLOT_ELEMS] | sldm[rounds_max*W*NDP] (u16)
+//             | scell[rounds_max*W] (i32) | two mbarriers (TMA copy of sldm, round barrier)
+//   REG:      xl | yl | tiles | scell[rounds_max*W] (i32) | sbase[rounds_max*W] (u16) | mbarriers
 // REG: every batch of the launch is a regular brick (wfx_plan): the positions of a cell's points
 // in the shared arrays are base + ascpos(i)*Sx + ascpos(j)*Sy + ascpos(k), so no local dofmap is
 // staged and all three roles read their input lines straight from xl (no tile round trip for u).
+// At P4 fp64 the REG layout is 99.1 KB: two CTAs fit the 196 KB carve-out, which leaves 60 KB of
+// L1 -- do not grow it ("L1 is part of the budget").
 template <typename T, int N, int SLOT, int W, int MINB, bool REG, typename L>
 __global__ void __launch_bounds__(SLOT* W, MINB)
 stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
