@@ -156,3 +156,20 @@ def test_tabulate_basis_and_permutation_matches_oracle(wfx, orc, P):
     ident = np.zeros((nd, nd))
     ident[np.arange(nd), perm] = 1.0
     assert np.array_equal(table[0], ident)
+
+
+@pytest.mark.parametrize("P,shape,W,mesh_n", [(5, (4, 2, 2), 2, 4), (4, (4, 4, 2), 4, 8), (6, (2, 2, 4), 2, 4), (2, (8, 4, 4), 16, 8)])
+def test_brick_plan_non_cubic_bricks(wfx, P, shape, W, mesh_n):
+    # bricks need not be cubes: rounds of W conflict-free cells exist as soon as one axis has >= 2W/4 cells
+    mesh = wfx.create_box_hex(mesh_n, P, perturb=0.15)
+    code = shape[0] | (shape[1] << 8) | (shape[2] << 16)
+    s = wfx.capi.debug_plan_stats(P, mesh.dofmap, mesh.ndofs, _centroids(mesh), code, W)
+    nb = 1
+    for a in range(3):
+        nb *= -(-mesh_n // shape[a])
+    assert s["batches"] == nb
+    assert s["regular_batches"] == s["batches"]
+    dense = (P * shape[0] + 1) * (P * shape[1] + 1) * (P * shape[2] + 1)
+    assert dense <= s["nloc_max"] <= 1.05 * dense
+    # every round is full: cells per brick / 8 parity classes >= W in these cases
+    assert s["padded_slots"] == 0

@@ -30,26 +30,28 @@ struct Strides
   bool ok = false, tuned = false;
   int Sx = 0, Sy = 0;
 };
-Strides find_strides(int P, int be, int word_bytes, bool tuned)
+Strides find_strides(int P, const BrickShape& brick, int word_bytes, bool tuned)
 {
-  const int n = P + 1, E = P * be + 1;
+  const int n = P + 1;
+  const int Ex = P * brick.e[0] + 1, Ey = P * brick.e[1] + 1, Ez = P * brick.e[2] + 1; // lattice extents
   const int banks = word_bytes == 8 ? 16 : 32;
   Strides best;
-  // Degree 4, 64-bit words: the kernel has a layout in which ALL of a cell's shared-memory
-  // accesses (three roles, dof arrays and tiles) are conflict-free; it needs Sx = 5, Sy = 2
-  // (mod 16), see tools/bank_layout_search.py.  Costs 7 % padding of the dof arrays.
-  if (tuned && P == 4 && word_bytes == 8)
+  // Degree 4, 64-bit words, cubic bricks: the kernel has a layout in which ALL of a cell's
+  // shared-memory accesses (three roles, dof arrays and tiles) are conflict-free; it needs Sx = 5,
+  // Sy = 2 (mod 16), see tools/bank_layout_search.py.  Costs 7 % padding of the dof arrays.
+  if (tuned && P == 4 && word_bytes == 8 && brick.cubic())
   {
-    best.Sy = E;
+    best.Sy = Ez;
     while (best.Sy % 16 != 2) ++best.Sy;
-    best.Sx = (E - 1) * best.Sy + E;
+    best.Sx = (Ey - 1) * best.Sy + Ez;
     while (best.Sx % 16 != 5) ++best.Sx;
     best.ok = best.tuned = true;
     return best;
   }
+  const int dense = Ex * Ey * Ez;
   int best_conf = 1 << 30, best_cap = 1 << 30;
-  for (int Sy = E; Sy < E + 32; ++Sy)
-    for (int Sx = (E - 1) * Sy + E; Sx < (E - 1) * Sy + E + 32; ++Sx)
+  for (int Sy = Ez; Sy < Ez + 32; ++Sy)
+    for (int Sx = (Ey - 1) * Sy + Ez; Sx < (Ey - 1) * Sy + Ez + 32; ++Sx)
     {
       int conf = 0;
       for (int g0 = 0; g0 < n * n; g0 += banks)
@@ -61,8 +63,8 @@ Strides find_strides(int P, int be, int word_bytes, bool tuned)
           conf += cnt[bk]++;
         }
       }
-      const int cap = (E - 1) * (Sx + Sy) + E;
-      if (cap > E * E * E + (E * E * E) / 25) continue; // at most 4 % padding
+      const int cap = (Ex - 1) * Sx + (Ey - 1) * Sy + Ez;
+      if (cap > dense + dense / 25) continue; // at most 4 % padding
       if (conf < best_conf || (conf == best_conf && cap < best_cap))
       {
         best_conf = conf;
@@ -125,7 +127,7 @@ void verify_cell_colour_plan(const CellColourPlan& plan, int nd, int64_t ncells,
 }
 
 void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
-                      const float* centroid, int brick_edge, int W, int nloc_cap,
+                      const float* centroid, BrickShape brick, int W, int nloc_cap,
                       BrickPlan& plan, const uint8_t* dof_shared, int word_bytes, bool allow_tuned)
 {
   const int n = P + 1, nd = n * n * n;
@@ -133,7 +135,9 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
   if (nloc_cap > 65535) nloc_cap = 65535;
   if (nloc_cap < nd) fail("brick plan: shared-memory dof capacity %d below one cell", nloc_cap);
   if (W < 1) fail("brick plan: W < 1");
-  const int64_t max_cells = (int64_t)brick_edge * brick_edge * brick_edge;
+  for (int a = 0; a < 3; ++a)
+    if (brick.e[a] < 1 || brick.e[a] > 16) fail("brick plan: brick edge %d out of range [1,16]", brick.e[a]);
+  const int64_t max_cells = brick.cells();
   plan = BrickPlan();
   plan.P = P;
   plan.nd = nd;
@@ -172,8 +176,8 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
         int64_t ia = (int64_t)std::floor((centroid[3 * c + a] - lo[a]) / h + 0.5);
         if (ia < 0) ia = 0;
         if (ia > 0xFFFF) ia = 0xFFFF;
-        b[a] = (uint64_t)(ia / brick_edge);
-        loc[a] = (uint64_t)(ia % brick_edge);
+        b[a] = (uint64_t)(ia / brick.e[a]);
+        loc[a] = (uint64_t)(ia % brick.e[a]);
         cell_ijk[3 * c + a] = (int32_t)ia;
       }
       // brick coordinates in the high bits, in-brick position in the low bits
@@ -338,7 +342,7 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
   // far more than the conflict-free layout gains.  WFX_TUNED_STRIDES=1 enables it for experiments.
   bool want_tuned = false;
   if (const char* ev = std::getenv("WFX_TUNED_STRIDES")) want_tuned = allow_tuned && std::atoi(ev) != 0;
-  const Strides lay = have_coords ? find_strides(P, brick_edge, word_bytes, want_tuned) : Strides();
+  const Strides lay = have_coords ? find_strides(P, brick, word_bytes, want_tuned) : Strides();
   plan.Sx = lay.Sx;
   plan.Sy = lay.Sy;
   for (int i = 0; i < nb; ++i)
@@ -370,7 +374,6 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
     int nslots = nloc;
     if (have_coords && lay.ok)
     {
-      const int E = P * brick_edge + 1;
       int org[3] = {1 << 30, 1 << 30, 1 << 30};
       for (int64_t p = b.begin; p < b.end; ++p)
         for (int a = 0; a < 3; ++a) org[a] = std::min(org[a], cell_ijk[3 * (int64_t)order[p] + a]);
@@ -381,7 +384,7 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
         const int32_t* d = tdm + (int64_t)c * nd;
         int l3[3];
         for (int a = 0; a < 3; ++a) l3[a] = cell_ijk[3 * (int64_t)c + a] - org[a];
-        if (l3[0] >= brick_edge || l3[1] >= brick_edge || l3[2] >= brick_edge) { regular = false; break; }
+        if (l3[0] >= brick.e[0] || l3[1] >= brick.e[1] || l3[2] >= brick.e[2]) { regular = false; break; }
         for (int k = 0; k < n && regular; ++k)
           for (int ii = 0; ii < n && regular; ++ii)
             for (int jj = 0; jj < n; ++jj)
@@ -395,7 +398,7 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
       }
       if (regular)
       {
-        nslots = (E - 1) * (lay.Sx + lay.Sy) + E;
+        nslots = P * brick.e[0] * lay.Sx + P * brick.e[1] * lay.Sy + P * brick.e[2] + 1;
         if (nslots > nloc_cap || nslots > 65535) regular = false;
         // positions must be distinct
         if (regular)
@@ -486,7 +489,7 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
   if (lay.tuned && plan.n_regular != nb)
   {
     BrickPlan compact;
-    build_brick_plan(P, ncells, ndofs, tdm, centroid, brick_edge, W, nloc_cap, compact, dof_shared, word_bytes, false);
+    build_brick_plan(P, ncells, ndofs, tdm, centroid, brick, W, nloc_cap, compact, dof_shared, word_bytes, false);
     plan = std::move(compact);
   }
 }
@@ -599,7 +602,11 @@ extern "C" int wfx_debug_plan_stats(int P, int64_t ncells, int64_t ndofs,
   build_cell_colour_plan(nd, ncells, ndofs, tdm.data(), cp);
   verify_cell_colour_plan(cp, nd, ncells, ndofs, tdm.data());
   BrickPlan bp;
-  build_brick_plan(P, ncells, ndofs, tdm.data(), centroid_host, brick_edge, W, nloc_cap, bp);
+  // brick_edge > 255: a non-cubic brick packed as ex | ey << 8 | ez << 16
+  const BrickShape shape = brick_edge > 255
+                               ? BrickShape(brick_edge & 255, (brick_edge >> 8) & 255, (brick_edge >> 16) & 255)
+                               : BrickShape(brick_edge);
+  build_brick_plan(P, ncells, ndofs, tdm.data(), centroid_host, shape, W, nloc_cap, bp);
   verify_brick_plan(bp, tdm.data());
   if (stats)
   {

@@ -59,15 +59,25 @@ struct BrickPlan
   int Sx = 0, Sy = 0;              // strides of that placement
 };
 
+// Cells per brick along the three grid axes (x slowest).  A plain int means a cube.
+struct BrickShape
+{
+  int e[3];
+  BrickShape(int cube) : e{cube, cube, cube} {}
+  BrickShape(int ex, int ey, int ez) : e{ex, ey, ez} {}
+  int64_t cells() const { return (int64_t)e[0] * e[1] * e[2]; }
+  bool cubic() const { return e[0] == e[1] && e[1] == e[2]; }
+};
+
 // tdm: tensor-ordered dofmap in the kernels' k-major point order, [ncells][nd]
 void build_cell_colour_plan(int nd, int64_t ncells, int64_t ndofs, const int32_t* tdm,
                             CellColourPlan& plan);
 
 // centroid: [ncells][3] or nullptr (then cells are batched in the given order).
-// brick_edge: cells per brick edge; max_cells: batch capacity; nloc_cap: capacity of the
-// shared-memory dof arrays.
+// brick: cells per brick along each axis (batch capacity = their product); nloc_cap: capacity of
+// the shared-memory dof arrays.
 void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
-                      const float* centroid, int brick_edge, int W, int nloc_cap,
+                      const float* centroid, BrickShape brick, int W, int nloc_cap,
                       BrickPlan& plan, const uint8_t* dof_shared = nullptr, int word_bytes = 8,
                       bool allow_tuned = true);
 

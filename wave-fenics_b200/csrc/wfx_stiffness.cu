@@ -802,21 +802,27 @@ __global__ void permute_g_columns_kernel(T* __restrict__ G6, int64_t nrows)
 template <int N> struct Cfg;
 //                          SLOT  W  brick edge  cells/block (simple)  min CTAs/SM (brick)
 //                          preferred shared-memory carve-out in percent, fp64 / fp32 (0 = driver's choice)
-template <> struct Cfg<3> { static constexpr int SLOT = 16, W = 16, BE = 8, CPB = 16, MINB = 2, CARVEOUT = 0, CARVEOUT32 = 0; };
-template <> struct Cfg<4> { static constexpr int SLOT = 16, W = 8, BE = 4, CPB = 16, MINB = 4, CARVEOUT = 0, CARVEOUT32 = 0; };
+template <> struct Cfg<3> { static constexpr int SLOT = 16, W = 16, BX = 8, BY = 8, BZ = 8, CPB = 16, MINB = 2, CARVEOUT = 0, CARVEOUT32 = 0; };
+template <> struct Cfg<4> { static constexpr int SLOT = 16, W = 8, BX = 4, BY = 4, BZ = 4, CPB = 16, MINB = 4, CARVEOUT = 0, CARVEOUT32 = 0; };
 #ifndef WFX_P4_W
 #define WFX_P4_W 8
 #define WFX_P4_BE 4
 #define WFX_P4_MINB 2
 #endif
-template <> struct Cfg<5> { static constexpr int SLOT = 32, W = WFX_P4_W, BE = WFX_P4_BE, CPB = 8, MINB = WFX_P4_MINB, CARVEOUT = 0, CARVEOUT32 = 0; };
-template <> struct Cfg<6> { static constexpr int SLOT = 64, W = 1, BE = 2, CPB = 4, MINB = 8, CARVEOUT = 58, CARVEOUT32 = 0; };
-template <> struct Cfg<7> { static constexpr int SLOT = 64, W = 1, BE = 2, CPB = 4, MINB = 5, CARVEOUT = 72, CARVEOUT32 = 58; };
-template <> struct Cfg<8> { static constexpr int SLOT = 64, W = 1, BE = 2, CPB = 2, MINB = 3, CARVEOUT = 0, CARVEOUT32 = 0; };
+template <> struct Cfg<5> { static constexpr int SLOT = 32, W = WFX_P4_W, BX = WFX_P4_BE, BY = WFX_P4_BE, BZ = WFX_P4_BE, CPB = 8, MINB = WFX_P4_MINB, CARVEOUT = 0, CARVEOUT32 = 0; };
+#ifndef WFX_P5_W
+#define WFX_P5_W 1
+#define WFX_P5_BX 2
+#define WFX_P5_MINB 8
+#define WFX_P5_CARVE 58
+#endif
+template <> struct Cfg<6> { static constexpr int SLOT = 64, W = WFX_P5_W, BX = WFX_P5_BX, BY = 2, BZ = 2, CPB = 4, MINB = WFX_P5_MINB, CARVEOUT = WFX_P5_CARVE, CARVEOUT32 = 0; };
+template <> struct Cfg<7> { static constexpr int SLOT = 64, W = 1, BX = 2, BY = 2, BZ = 2, CPB = 4, MINB = 5, CARVEOUT = 72, CARVEOUT32 = 58; };
+template <> struct Cfg<8> { static constexpr int SLOT = 64, W = 1, BX = 2, BY = 2, BZ = 2, CPB = 2, MINB = 3, CARVEOUT = 0, CARVEOUT32 = 0; };
 
 struct LaunchCfg
 {
-  int SLOT, W, BE, CPB;
+  int SLOT, W, BX, BY, BZ, CPB;
 };
 int slot_elems_rt(int N)
 {
@@ -835,12 +841,12 @@ LaunchCfg launch_cfg(int N)
 {
   switch (N)
   {
-  case 3: return {Cfg<3>::SLOT, Cfg<3>::W, Cfg<3>::BE, Cfg<3>::CPB};
-  case 4: return {Cfg<4>::SLOT, Cfg<4>::W, Cfg<4>::BE, Cfg<4>::CPB};
-  case 5: return {Cfg<5>::SLOT, Cfg<5>::W, Cfg<5>::BE, Cfg<5>::CPB};
-  case 6: return {Cfg<6>::SLOT, Cfg<6>::W, Cfg<6>::BE, Cfg<6>::CPB};
-  case 7: return {Cfg<7>::SLOT, Cfg<7>::W, Cfg<7>::BE, Cfg<7>::CPB};
-  case 8: return {Cfg<8>::SLOT, Cfg<8>::W, Cfg<8>::BE, Cfg<8>::CPB};
+  case 3: return {Cfg<3>::SLOT, Cfg<3>::W, Cfg<3>::BX, Cfg<3>::BY, Cfg<3>::BZ, Cfg<3>::CPB};
+  case 4: return {Cfg<4>::SLOT, Cfg<4>::W, Cfg<4>::BX, Cfg<4>::BY, Cfg<4>::BZ, Cfg<4>::CPB};
+  case 5: return {Cfg<5>::SLOT, Cfg<5>::W, Cfg<5>::BX, Cfg<5>::BY, Cfg<5>::BZ, Cfg<5>::CPB};
+  case 6: return {Cfg<6>::SLOT, Cfg<6>::W, Cfg<6>::BX, Cfg<6>::BY, Cfg<6>::BZ, Cfg<6>::CPB};
+  case 7: return {Cfg<7>::SLOT, Cfg<7>::W, Cfg<7>::BX, Cfg<7>::BY, Cfg<7>::BZ, Cfg<7>::CPB};
+  case 8: return {Cfg<8>::SLOT, Cfg<8>::W, Cfg<8>::BX, Cfg<8>::BY, Cfg<8>::BZ, Cfg<8>::CPB};
   }
   fail("stiffness: degree %d not supported (2..7)", N - 1);
 }
@@ -1162,14 +1168,14 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
       // (brick_edge^3 cells, 8 colours) first and verify after planning
       const int ndp = (op->nd + 7) & ~7;
       auto meta_bytes = [&](int rounds) { return (size_t)rounds * lc.W * (ndp * 2 + 4); };
-      const int rounds_guess = std::max(8, (lc.BE * lc.BE * lc.BE + lc.W - 1) / lc.W);
+      const int rounds_guess = std::max(8, (lc.BX * lc.BY * lc.BZ + lc.W - 1) / lc.W);
       const size_t tiles_bytes = (size_t)lc.W * slot_elems_rt(op->N) * esz;
       const size_t work = tiles_bytes + meta_bytes(rounds_guess) + 32;
       const size_t avail = ctx->smem_optin > work + 1024 ? ctx->smem_optin - work - 1024 : 0;
       int nloc_cap = (int)std::min<size_t>(avail / (2 * esz), 65535);
       if (const char* e = std::getenv("WFX_NLOC_CAP")) nloc_cap = std::min(nloc_cap, std::atoi(e));
-      int be = lc.BE;
-      if (const char* e = std::getenv("WFX_BRICK_EDGE")) be = std::max(1, std::atoi(e));
+      BrickShape be(lc.BX, lc.BY, lc.BZ);
+      if (const char* e = std::getenv("WFX_BRICK_EDGE")) be = BrickShape(std::max(1, std::atoi(e)));
       BrickPlan bp;
       build_brick_plan(op->P, op->ncells, ndofs, tdm.data(),
                        geom->centroid.empty() ? nullptr : geom->centroid.data(), be, lc.W, nloc_cap, bp,
