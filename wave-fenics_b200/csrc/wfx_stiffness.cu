@@ -809,7 +809,13 @@ template <> struct Cfg<4> { static constexpr int SLOT = 16, W = 8, BX = 4, BY = 
 #define WFX_P4_BE 4
 #define WFX_P4_MINB 2
 #endif
-template <> struct Cfg<5> { static constexpr int SLOT = 32, W = WFX_P4_W, BX = WFX_P4_BE, BY = WFX_P4_BE, BZ = WFX_P4_BE, CPB = 8, MINB = WFX_P4_MINB, CARVEOUT = 0, CARVEOUT32 = 0; };
+#ifndef WFX_P4_BZ
+#define WFX_P4_BZ WFX_P4_BE
+#endif
+#ifndef WFX_P4_CARVE
+#define WFX_P4_CARVE 0
+#endif
+template <> struct Cfg<5> { static constexpr int SLOT = 32, W = WFX_P4_W, BX = WFX_P4_BE, BY = WFX_P4_BE, BZ = WFX_P4_BZ, CPB = 8, MINB = WFX_P4_MINB, CARVEOUT = WFX_P4_CARVE, CARVEOUT32 = 0; };
 #ifndef WFX_P5_W
 #define WFX_P5_W 1
 #define WFX_P5_BX 2
