@@ -173,3 +173,27 @@ def test_brick_plan_non_cubic_bricks(wfx, P, shape, W, mesh_n):
     assert dense <= s["nloc_max"] <= 1.05 * dense
     # every round is full: cells per brick / 8 parity classes >= W in these cases
     assert s["padded_slots"] == 0
+
+
+def test_brick_plan_invariants_on_random_connectivity(wfx):
+    """Property test (hypothesis): for ARBITRARY cell -> dof connectivity -- nothing like a mesh --
+    the planner must still produce plans that satisfy every invariant the kernels rely on
+    (wfx_debug_plan_stats runs verify_brick_plan / verify_cell_colour_plan and fails otherwise)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 2 ** 31 - 1), st.sampled_from([1, 2]), st.integers(1, 14), st.sampled_from([1, 2, 4, 8]),
+           st.sampled_from([1, 2, 3, 4]), st.booleans(), st.integers(0, 3))
+    def run(seed, P, ncells, W, be, with_centroids, extra):
+        rng = np.random.default_rng(seed)
+        nd = (P + 1) ** 3
+        ndofs = int(rng.integers(nd, nd * ncells + 1)) + extra
+        dofmap = np.stack([rng.choice(ndofs - extra, size=nd, replace=False) for _ in range(ncells)]).astype(np.int32)
+        cen = rng.uniform(0, 1, size=(ncells, 3)).astype(np.float32) if with_centroids else None
+        cap = int(rng.integers(nd, 4 * nd + 1))
+        s = wfx.capi.debug_plan_stats(P, dofmap, ndofs, cen, be, W, nloc_cap=cap)
+        assert s["nloc_max"] <= max(cap, nd)
+        assert s["batches"] >= 1 and s["rounds"] >= s["batches"]
+        assert s["untouched"] == ndofs - len(np.unique(dofmap))
+
+    run()
