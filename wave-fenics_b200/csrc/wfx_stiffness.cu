@@ -356,7 +356,8 @@ template <typename T, int N, typename L, typename Sync>
 __device__ __forceinline__ void cell_part1(const T (&u)[N], typename Vec2<T>::type (&g)[N][3],
                                            T* __restrict__ tiles, const RoleOff& ro,
                                            const DMat<T, N>& Dm, T coeff, bool active, Sync sync,
-                                           T (&f2)[N], PhaseTimer& tm)
+                                           T (&f2)[N], PhaseTimer& tm,
+                                           const typename Vec2<T>::type* gnext = nullptr)
 {
   T* A = tiles;
   T* AT = tiles + L::AT_OFF;
@@ -378,7 +379,7 @@ __device__ __forceinline__ void cell_part1(const T (&u)[N], typename Vec2<T>::ty
   }
   sync();
   tm.mark(2);
-  if (active) g_multiply<T, N, L>(u, g, A, AT, ro, Dm, coeff, f2);
+  if (active) g_multiply<T, N, L>(u, g, A, AT, ro, Dm, coeff, f2, gnext);
   tm.mark(3);
 }
 
@@ -645,10 +646,11 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
     bool g_requested = false; // next cell's G already requested inside part 1
     int li[N];
     T u[N], yv[N], f2[N];
+    // this thread's column of the next cell's G: requested plane by plane inside the G multiply
+    const V2* gnext = cn >= 0 ? reinterpret_cast<const V2*>(a.G6 + (int64_t)cn * (6 * ND)) + gcol : nullptr;
+    g_requested = active;
     if constexpr (REG)
     {
-      const V2* gnext = cn >= 0 ? reinterpret_cast<const V2*>(a.G6 + (int64_t)cn * (6 * ND)) + gcol : nullptr;
-      g_requested = active;
       const int base = active ? (int)sbase[r * W + slot] : 0;
       T lj[N], lI[N];
 #pragma unroll
@@ -675,8 +677,8 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
         u[k] = active ? xl[li[k]] : T(0);
         yv[k] = 0;
       }
-      if constexpr (SLOT <= 32) cell_part1<T, N, L>(u, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2, tm);
-      else cell_part1<T, N, L>(u, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2, tm);
+      if constexpr (SLOT <= 32) cell_part1<T, N, L>(u, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2, tm, gnext);
+      else cell_part1<T, N, L>(u, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2, tm, gnext);
     }
     // G of this cell is consumed: request the next cell's G into the same registers so
     // that the loads fly during part 2 and the next gather
