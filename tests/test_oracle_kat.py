@@ -213,3 +213,71 @@ def test_rk4_plane_wave_sanity(wfx, orc):
     for k in np.unique(key)[::7]:
         vals = u[key == k]
         assert np.ptp(vals) <= 1e-9 * np.abs(u).max()
+
+
+@pytest.mark.parametrize("P", [2, 3, 4])
+def test_stiffness_against_first_principles_numpy(wfx, orc, P):
+    """Independent derivation, sharing no code with the oracle or the library tables: GLL nodes from the
+    roots of P_n' (numpy Legendre), weights 2/(n(n+1) P_n(x)^2), Lagrange derivatives by barycentric
+    formulas, the trilinear Jacobian differentiated by hand, and
+        v^T K u = -c0^2 sum_cells sum_q grad_X u(q) . G_q grad_X v(q),  G_q = clamp(J_q^-1 (w_q |det J_q|) J_q^-T)
+    on a perturbed (non-affine) mesh with random fields.  Only the dof layout (perm, dofmap) is taken
+    from the code under test -- it is pinned separately by the literal P2 permutation."""
+    from numpy.polynomial import legendre as Lg
+    n = P + 1
+    # GLL on [-1,1]: endpoints and roots of P_P'; map to [0,1]
+    cP = np.zeros(P + 1)
+    cP[P] = 1.0
+    xi = np.concatenate([[-1.0], np.sort(Lg.legroots(Lg.legder(cP))), [1.0]])
+    w = 2.0 / (P * (P + 1) * Lg.legval(xi, cP) ** 2)
+    x01, w01 = (xi + 1) / 2, w / 2
+    # barycentric derivative matrix on ascending nodes: Dasc[q,i] = l_i'(x_q)
+    bw = np.array([1.0 / np.prod([x01[i] - x01[j] for j in range(n) if j != i]) for i in range(n)])
+    Dasc = np.zeros((n, n))
+    for q in range(n):
+        for i in range(n):
+            if i != q:
+                Dasc[q, i] = bw[i] / bw[q] / (x01[q] - x01[i])
+        Dasc[q, q] = -Dasc[q].sum()
+    # code ordering of 1-D nodes: [0, 1, interior...]  (ascending position of code index a)
+    pos = np.array([0, P] + list(range(1, P)))
+    pts = x01[pos]
+    wts = w01[pos]
+    D = Dasc[np.ix_(pos, pos)]
+    mesh = _mesh(wfx, 2, P, perturb=0.2)
+    perm = orc.perm(P)
+    rng = np.random.default_rng(11)
+    u, v = rng.standard_normal(mesh.ndofs), rng.standard_normal(mesh.ndofs)
+    total = 0.0
+    A, B, Cc = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    for c in range(mesh.ncells):
+        dofs = mesh.dofmap[c][perm]                      # tensor order t = (a*n + b)*n + c
+        U, V = u[dofs].reshape(n, n, n), v[dofs].reshape(n, n, n)
+        gU = np.stack([np.einsum("qa,abc->qbc", D, U), np.einsum("qb,abc->aqc", D, U), np.einsum("qc,abc->abq", D, U)], -1)
+        gV = np.stack([np.einsum("qa,abc->qbc", D, V), np.einsum("qb,abc->aqc", D, V), np.einsum("qc,abc->abq", D, V)], -1)
+        xv = mesh.x[mesh.xdofs[c]]                       # vertex v = ix + 2 iy + 4 iz
+        X = np.stack([pts[A], pts[B], pts[Cc]], -1)      # reference point of every node
+        J = np.zeros((n, n, n, 3, 3))
+        for vtx in range(8):
+            bits = [(vtx >> a) & 1 for a in range(3)]
+            f = [X[..., a] if bits[a] else 1.0 - X[..., a] for a in range(3)]
+            df = [1.0 if bits[a] else -1.0 for a in range(3)]
+            for a in range(3):                           # d phi_v / d X_a
+                g = df[a] * f[(a + 1) % 3] * f[(a + 2) % 3]
+                J[..., :, a] += xv[vtx][:, None, None, None].transpose(1, 2, 3, 0) * g[..., None]
+        detJ = np.abs(np.linalg.det(J))
+        Jinv = np.linalg.inv(J)
+        wq = wts[A] * wts[B] * wts[Cc]
+        Gq = np.einsum("...ia,...ja->...ij", Jinv, Jinv) * (wq * detJ)[..., None, None]   # J^-1 (detJ w) J^-T
+        # the reference's clamp of G (common/precomputation.hpp:105-107, xt::isclose defaults): with an
+        # ABSOLUTE tolerance of 1e-8 it zeroes real entries on a mesh this small -- a 1e-7 relative effect
+        # on v^T K u that belongs to the reference's definition of the operator
+        for target in (-1.0, 0.0, 1.0):
+            Gq = np.where(np.abs(Gq - target) <= 1e-8 + 1e-5 * abs(target), target, Gq)
+        total += float(np.einsum("...i,...ij,...j->...", gU, Gq, gV).sum())
+    want = -C0 * C0 * total
+    G, _ = orc.precompute_geometric_data(mesh, P)
+    ku = np.zeros(mesh.ndofs)
+    orc.stiffness_apply(mesh, P, G, u, ku, dense=True)
+    got = float(v @ ku)
+    assert abs(got - want) <= 1e-11 * abs(want), (got, want)
