@@ -281,3 +281,100 @@ def test_stiffness_against_first_principles_numpy(wfx, orc, P):
     orc.stiffness_apply(mesh, P, G, u, ku, dense=True)
     got = float(v @ ku)
     assert abs(got - want) <= 1e-11 * abs(want), (got, want)
+
+
+def test_rk4_against_textbook_runge_kutta(wfx, orc):
+    """The oracle's restatement of LinearGLLOpt::rk4 (stage bookkeeping of LinearGLL.hpp:244-270) equals
+    the textbook classical RK4 applied to y' = F(t, y), y = (u, v),
+        F = (v,  M^-1 (-c0^2 K u + c0^2 g(t) m1 - c0 m2 v)),
+    written here directly in numpy (it shares the operator pieces with the oracle, not the time stepper)."""
+    P, c0, f0, p0 = 3, C0, 0.5e6, 6e4
+    mesh = wfx.create_box_hex((3, 2, 2), P, (L * 3 / 8, L * 2 / 8, L * 2 / 8), perturb=0.1)
+    G, detJ = orc.precompute_geometric_data(mesh, P)
+    m = np.zeros(mesh.ndofs)
+    orc.mass_apply(mesh, P, detJ, np.ones(mesh.ndofs), m)
+    m1, m2 = orc.boundary_facet_mass(mesh, P)
+    dt = wfx.cfl_timestep(mesh.h_min, c0, P, f0)
+    w0, T, alpha = 2.0 * np.pi * f0, 1.0 / f0, 4.0
+
+    def F(t, u, v):
+        window = 0.5 * (1.0 - np.cos(f0 * np.pi * t / alpha)) if t < T * alpha else 1.0
+        g = window * p0 * w0 / c0 * np.cos(w0 * t)
+        b = np.zeros(mesh.ndofs)
+        orc.stiffness_apply(mesh, P, G, u, b, dense=True)
+        return v.copy(), (b + c0 * c0 * g * m1 - c0 * m2 * v) / m
+
+    steps = 7
+    u, v, t = np.zeros(mesh.ndofs), np.zeros(mesh.ndofs), 0.0
+    for _ in range(steps):
+        k1u, k1v = F(t, u, v)
+        k2u, k2v = F(t + dt / 2, u + dt / 2 * k1u, v + dt / 2 * k1v)
+        k3u, k3v = F(t + dt / 2, u + dt / 2 * k2u, v + dt / 2 * k2v)
+        k4u, k4v = F(t + dt, u + dt * k3u, v + dt * k3v)
+        u = u + dt / 6 * (k1u + 2 * k2u + 2 * k3u + k4u)
+        v = v + dt / 6 * (k1v + 2 * k2v + 2 * k3v + k4v)
+        t += dt
+    uo, vo = np.zeros(mesh.ndofs), np.zeros(mesh.ndofs)
+    s, t_end = orc.rk4(mesh, P, G, m, m1, m2, c0, f0, p0, 0.0, 1.0, dt, uo, vo, max_steps=steps)
+    assert s == steps and abs(t_end - t) < 1e-18
+    assert np.abs(u).max() > 0
+    assert np.linalg.norm(uo - u) <= 1e-12 * np.linalg.norm(u)
+    assert np.linalg.norm(vo - v) <= 1e-12 * np.linalg.norm(v)
+
+
+@pytest.mark.parametrize("P", [2, 4])
+def test_lumped_and_facet_masses_against_first_principles(wfx, orc, P):
+    """m_i = sum over cells of w_q |det J_q| at node i (collocated GLL), and the facet masses
+    m_Gamma,i = sum over tagged facets of w_f |J_f| with |J_f| the area element of the face map, both
+    evaluated here with an independent GLL rule and hand-differentiated trilinear map."""
+    from numpy.polynomial import legendre as Lg
+    n = P + 1
+    cP = np.zeros(P + 1)
+    cP[P] = 1.0
+    xi = np.concatenate([[-1.0], np.sort(Lg.legroots(Lg.legder(cP))), [1.0]])
+    w = 2.0 / (P * (P + 1) * Lg.legval(xi, cP) ** 2)
+    pos = np.array([0, P] + list(range(1, P)))
+    pts, wts = ((xi + 1) / 2)[pos], (w / 2)[pos]
+    mesh = _mesh(wfx, 2, P, perturb=0.2)
+    perm = orc.perm(P)
+    A, B, Cc = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    X = np.stack([pts[A], pts[B], pts[Cc]], -1)
+
+    def jacobian(xv):
+        J = np.zeros((n, n, n, 3, 3))
+        for vtx in range(8):
+            bits = [(vtx >> a) & 1 for a in range(3)]
+            f = [X[..., a] if bits[a] else 1.0 - X[..., a] for a in range(3)]
+            for a in range(3):
+                g = (1.0 if bits[a] else -1.0) * f[(a + 1) % 3] * f[(a + 2) % 3]
+                J[..., :, a] += xv[vtx][None, None, None, :] * g[..., None]
+        return J
+
+    m = np.zeros(mesh.ndofs)
+    m1, m2 = np.zeros(mesh.ndofs), np.zeros(mesh.ndofs)
+    wq = wts[A] * wts[B] * wts[Cc]
+    facets = {(int(c), int(f)): int(t) for c, f, t in zip(mesh.facet_cells, mesh.facet_local, mesh.facet_tags)}
+    # hexahedron facets: 0 z-, 1 y-, 2 x-, 3 x+, 4 y+, 5 z+  -> (normal axis, fixed tensor index)
+    face_of = {0: (2, 0), 1: (1, 0), 2: (0, 0), 3: (0, 1), 4: (1, 1), 5: (2, 1)}
+    for c in range(mesh.ncells):
+        dofs = mesh.dofmap[c][perm].reshape(n, n, n)
+        J = jacobian(mesh.x[mesh.xdofs[c]])
+        np.add.at(m, dofs, wq * np.abs(np.linalg.det(J)))
+        for lf, (axis, side) in face_of.items():
+            tag = facets.get((c, lf))
+            if tag is None:
+                continue
+            t1, t2 = [a for a in range(3) if a != axis]
+            area = np.linalg.norm(np.cross(J[..., :, t1], J[..., :, t2]), axis=-1)   # |dx/dX_t1 x dx/dX_t2|
+            wf = (wts[[A, B, Cc][t1]] * wts[[A, B, Cc][t2]]) * area
+            sel = [slice(None)] * 3
+            sel[axis] = side                                                         # code index 0 / 1 = the two ends
+            np.add.at(m1 if tag == 1 else m2, dofs[tuple(sel)], wf[tuple(sel)])
+    _, detJ = orc.precompute_geometric_data(mesh, P)
+    mo = np.zeros(mesh.ndofs)
+    orc.mass_apply(mesh, P, detJ, np.ones(mesh.ndofs), mo)
+    m1o, m2o = orc.boundary_facet_mass(mesh, P)
+    np.testing.assert_allclose(mo, m, rtol=1e-12)
+    assert m1.sum() > 0 and m2.sum() > 0
+    np.testing.assert_allclose(m1o, m1, rtol=1e-12, atol=1e-18)
+    np.testing.assert_allclose(m2o, m2, rtol=1e-12, atol=1e-18)
