@@ -51,7 +51,7 @@ def _worker(rank, world, port, gshape, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,gshape", [(2, (4, 3, 2)), (4, (4, 4, 3))])
+@pytest.mark.parametrize("world,gshape", [(2, (4, 3, 2)), (4, (4, 4, 3)), (6, (6, 4, 2))])
 def test_partitioned_operator_equals_global(world, gshape, wfx, orc):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -86,3 +86,5 @@ def test_partitioned_operator_equals_global(world, gshape, wfx, orc):
 def test_rank_grid_matches_reference_decompose3d(wfx):
     from wave_fenics_b200 import partition
     assert [partition.rank_grid(w) for w in (1, 2, 4, 8, 16)] == [(1, 1, 1), (2, 1, 1), (2, 2, 1), (2, 2, 2), (4, 2, 2)]
+    # not a power of two (the reference has no rule): most cubic factorisation
+    assert [partition.rank_grid(w) for w in (3, 6, 12, 27)] == [(3, 1, 1), (3, 2, 1), (3, 2, 2), (3, 3, 3)]

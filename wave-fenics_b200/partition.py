@@ -14,9 +14,22 @@ from .mesh import HexMesh, _vertex_coords, cell_h, lattice_pos
 
 
 def rank_grid(world):
-    """2^x ranks -> (2^x0, 2^x1, 2^x2) with x = x0+x1+x2, as decompose3d; other sizes: 1-D."""
+    """2^x ranks -> (2^x0, 2^x1, 2^x2) with x = x0+x1+x2, as decompose3d (demo/gpu_cg/mesh.hpp:37-48,
+    which only handles powers of two); other sizes: the factorisation a >= b >= c with the smallest
+    a + b + c, i.e. the least interface area per rank."""
+    if world < 1:
+        raise ValueError("world size must be positive")
     if world & (world - 1):
-        return (world, 1, 1)
+        best = (world, 1, 1)
+        for c in range(1, int(round(world ** (1 / 3))) + 2):
+            if world % c:
+                continue
+            for b in range(c, int((world // c) ** 0.5) + 2):
+                if (world // c) % b == 0 and (world // c) // b >= b:
+                    cand = ((world // c) // b, b, c)
+                    if sum(cand) < sum(best):
+                        best = cand
+        return best
     x = world.bit_length() - 1
     q, r = divmod(x, 3)
     return tuple(2 ** (q + (1 if i < r else 0)) for i in range(3))
