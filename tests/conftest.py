@@ -14,6 +14,15 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def wfx():
+    # a fresh checkout has no libwavefx.so (built artefacts are not tracked): compile it first --
+    # nvcc cross-compiles sm_100a without a GPU, same as __graft_entry__.build()
+    lib = os.environ.get("WFX_LIB") or os.path.join(ROOT, "wave-fenics_b200", "libwavefx.so")
+    if not os.path.exists(lib):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("wfx_build", os.path.join(ROOT, "wave-fenics_b200", "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
     import wave_fenics_b200
     return wave_fenics_b200
 
