@@ -105,9 +105,15 @@ def run_reference(args):
     cells = args.ref_cells
     for _ in range(args.warmup):
         cpu_operator_sample(min(cells, 8), args.P, threads)
-    t = []
-    ndofs = 0
-    for _ in range(args.steps):
+    # bounded: if K steps of the requested sample would not end within ~2.5 minutes, shrink the sample
+    # mesh (the cost is proportional to the number of cells; the rate in DoF/s is what is reported)
+    ndofs, dt = cpu_operator_sample(cells, args.P, threads)
+    budget = 150.0
+    if dt * args.steps > budget and cells > 8:
+        cells = max(8, int(cells * (budget / (dt * args.steps)) ** (1.0 / 3.0)))
+        ndofs, dt = cpu_operator_sample(cells, args.P, threads)
+    t = [dt]
+    for _ in range(args.steps - 1):
         ndofs, dt = cpu_operator_sample(cells, args.P, threads)
         t.append(dt)
     ms = 1e3 * float(np.mean(t))
@@ -333,7 +339,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="default: 1000 (b200 arm), 5 (reference arm)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells", type=int, default=64, help="cells per axis per GPU")
@@ -343,6 +349,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rk4", action="store_true")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 1000 if args.impl == "b200" else 5
+    args.steps = max(1, args.steps)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
