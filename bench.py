@@ -1,17 +1,25 @@
 #!/usr/bin/env python
-"""Benchmark of the waveFEniCS hot path on B200 (see the contract in DESIGN.md section 6).
+"""Benchmark of the waveFEniCS hot path on B200 (see the contract in DESIGN.md section 5).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--scaling weak|strong]
 
 N = 1 workload: BASELINE.json configs[1] -- single-B200 stiffness + mass operator apply,
 64^3 hex cells, P4 (16 974 593 dofs), fp64.  One "step" = one fused apply
 kv = M^-1 (-c0^2 K u).  `value` = GDoF/s with all inputs resident in HBM; `e2e` = the same
 apply through the C-ABI host entry point (pinned host x -> device -> apply -> host y).
-N > 1: the same per-GPU block on every rank of a cartesian partition (weak scaling), the
-interface dofs of K u reduced with the NCCL halo exchange before the mass inverse.
+N > 1 (weak, the default): the same per-GPU block on every rank of a cartesian partition, the
+interface dofs of K u reduced with the halo exchange before the mass inverse.
+--scaling strong: BASELINE configs[3], a fixed 128^3-cell global mesh split over the N ranks.
+
+Timing: R windows of K applies each, every window bracketed by barrier + synchronize on both
+sides and timed with CUDA events on the launching stream, max over ranks per window; `value`
+comes from the MEDIAN window (all windows are reported).  A second, >= 0.6 s window gives the
+sustained (power-capped) figure with its own clock record.  The nvidia-smi sampler starts
+before the first barrier, so no rank does host work inside another rank's window.
 
 --impl reference times the CPU restatement of the reference operator (oracle/, built with the
-reference's own compiler flags) on the box's host cores, on a bounded sample of the workload.
+reference's own compiler flags) on the box's host cores, on a bounded sample of the workload;
+it never imports the product package.
 """
 import argparse
 import json
@@ -38,47 +46,67 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-class ClockSampler:
-    """nvidia-smi SM clock / throttle-reason sampler running during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+def host_threads():
+    """Host cores this process may use.  Not OMP_NUM_THREADS: torch.distributed.run sets it to 1."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        n = os.cpu_count() or 1
+    return max(1, min(n, 32))  # thread-private y copies: bound the memory
 
-    def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+
+class ClockSampler:
+    """nvidia-smi SM clock / throttle-reason sampler; rows are time-stamped so that one sampler
+    serves several timed regions (summary(t0, t1) = the rows that fall inside a region)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index=0, period_ms=50):
+        self.rows, self.proc, self.index, self.period = [], None, index, period_ms
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", str(self.period)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t_end = time.time() + 3.0
+            while not self.rows and time.time() < t_end:  # wait until it is really sampling
+                time.sleep(0.02)
         except OSError:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
+        if self.proc:
+            time.sleep(1.5 * self.period / 1e3)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self, t0=None, t1=None):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        self.thread.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].startswith("Active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        rows = [r for (t, r) in self.rows if len(r) >= 7 and (t0 is None or t >= t0) and (t1 is None or t <= t1)]
+        num = lambda s: float(s) if s.replace(".", "", 1).isdigit() else None
+        sm = [num(r[0]) for r in rows if num(r[0]) is not None]
+        mx = [num(r[1]) for (_, r) in self.rows if len(r) >= 7 and num(r[1]) is not None]
+        pw = [num(r[2]) for r in rows if num(r[2]) is not None]
+        reasons = sorted({self.NAMES[i] for r in rows for i in range(4) if r[3 + i].startswith("Active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None,
                 "reasons": reasons, "samples": len(sm)}
 
 
+# ---- CPU reference arm (oracle only; no product import) ------------------------------------------
 def cpu_operator_sample(cells, P, threads, repeats=1):
     """Times the reference CPU operator (dense skernel + b/m) on a cells^3 sample mesh."""
-    import wave_fenics_b200 as wfx
-    from oracle import oracle
-    mesh = wfx.create_box_hex(cells, P, (L, L, L), perturb=0.0)
+    from oracle import oracle, refmesh
+    mesh = refmesh.box(cells, P, (L, L, L))
     G, detJ = oracle.precompute_geometric_data(mesh, P)
     m = np.zeros(mesh.ndofs)
     oracle.mass_apply(mesh, P, detJ, np.ones(mesh.ndofs), m)
@@ -100,8 +128,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle
-    threads = min(oracle.max_threads(), 32)  # thread-private y copies: bound the memory
+    threads = host_threads()
     cells = args.ref_cells
     for _ in range(args.warmup):
         cpu_operator_sample(min(cells, 8), args.P, threads)
@@ -121,7 +148,7 @@ def run_reference(args):
     sample = f"{cells}^3 cells P{args.P} ({ndofs} dofs) dense skernel + b/m, {threads} OpenMP threads, -Ofast -march=native"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"stiffness+mass apply, P{args.P} hex, fp64 (CPU restatement of the reference operator; bounded sample)",
                        "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
@@ -130,7 +157,10 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ---- product arm ------------------------------------------------------------------------------------
 def run_b200(args):
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
     import wave_fenics_b200 as wfx
@@ -145,19 +175,26 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = wfx.Context.get(local_rank)
     P, N = args.P, args.cells
+    from wave_fenics_b200 import partition
+    grid = partition.rank_grid(world)
 
     halo = None
-    if world == 1:
-        mesh = wfx.create_box_hex(N, P, (L, L, L), perturb=args.perturb)
+    if args.scaling == "strong":
+        gshape = (args.global_cells,) * 3
+        glen = (L, L, L)
     else:
-        from wave_fenics_b200 import partition
-        grid = partition.rank_grid(world)
         gshape = tuple(N * g for g in grid)
-        mesh = partition.create_box_hex_partition(gshape, P, tuple(L * g for g in grid), grid, rank, perturb=args.perturb)
+        glen = tuple(L * g for g in grid)
+    if world == 1:
+        mesh = wfx.create_box_hex(gshape, P, glen, perturb=args.perturb)
+    else:
+        mesh = partition.create_box_hex_partition(gshape, P, glen, grid, rank, perturb=args.perturb)
         halo = partition.make_halo(mesh, ctx, np.float64)
+    t_setup = time.perf_counter()
     geo = wfx.Geometry(mesh, P, ctx=ctx)
     stiff = wfx.StiffnessOperator(mesh, P, ctx=ctx, geometry=geo)
     mass = wfx.MassOperator(mesh, P, ctx=ctx, geometry=geo)
+    t_setup = time.perf_counter() - t_setup
     info = stiff.info()
     if halo is not None:
         mass.assemble(halo)
@@ -166,11 +203,11 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     g = torch.Generator(device=dev).manual_seed(42 + rank)
     x = torch.randn(mesh.ndofs, dtype=torch.float64, device=dev, generator=g)
+    if halo is not None:
+        halo.update_fwd(x)  # ghost copies of the input agree with their owners (scatter_fwd, LinearGLL.hpp:164)
     y = torch.empty_like(x)
 
-    import ctypes as C
-
-    # high priority: the small pack / NCCL / unpack kernels must not queue behind the interior batches
+    # high priority: the small pack / exchange / unpack kernels must not queue behind the interior batches
     comm_stream = torch.cuda.Stream(device=dev, priority=-1) if halo is not None else None
 
     def step():
@@ -192,53 +229,139 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def max_over_ranks(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def window(k):
+        """k steps, barrier + synchronize on both sides, device time of this rank in ms"""
+        sync_all()
+        ev0.record()
+        for _ in range(k):
+            step()
+        ev1.record()
+        sync_all()
+        return ev0.elapsed_time(ev1)
+
     for _ in range(args.warmup):
         step()
-    sync_all()
+    # the sampler (a forked nvidia-smi) starts BEFORE the first barrier of the timed windows
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
     sync_all()
-    clocks = sampler.stop() if rank == 0 else None
-    ms_total = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    tw0 = time.time()
+    win_local = [window(args.steps) for _ in range(args.windows)]
+    tw1 = time.time()
+    win_ms = max_over_ranks(win_local)
+    ms_total = float(np.median(win_ms))
     ms = ms_total / args.steps
     ndofs_global = mesh.ndofs_global
     value = ndofs_global / (ms * 1e-3) / 1e9
 
+    # sustained: one window of >= args.sustain_s seconds of back-to-back applies (power cap territory)
+    sustained = None
+    if args.sustain_s > 0:
+        k_sus = max(args.steps, int(np.ceil(args.sustain_s * 1e3 / ms)))
+        ts0 = time.time()
+        ms_sus = max_over_ranks([window(k_sus)])[0] / k_sus
+        ts1 = time.time()
+        sustained = {"ms_per_step": ms_sus, "steps": k_sus, "value": ndofs_global / (ms_sus * 1e-3) / 1e9}
+    if rank == 0:
+        sampler.stop()
+    clocks = sampler.summary(tw0, tw1) if rank == 0 else None
+    if rank == 0 and sustained:
+        sustained["clocks"] = sampler.summary(ts0 + 0.1, ts1)
+
+    # correctness of what was just timed, inside the run: the product path against an independent
+    # second GPU implementation (per-cell kernel, coloured cells, global read-modify-write; plain
+    # ghost reduction, then b/m), and bitwise agreement of all copies of a rank-shared dof.
+    parity = None
+    if not args.no_parity:
+        simple = wfx.StiffnessOperator(mesh, P, ctx=ctx, geometry=geo, mode=wfx.capi.STIFF_CELL_COLOUR)
+        step()
+        y2 = torch.empty_like(x)
+        simple.apply(x, y2, beta=0)
+        if halo is not None:
+            halo.update_rev_fwd(y2)
+        minv = torch.from_numpy(mass.inverse_diagonal()).to(dev)
+        y2 *= minv
+        sl = mesh.size_local
+        num = torch.stack([((y[:sl] - y2[:sl]) ** 2).sum(), (y2[:sl] ** 2).sum()])
+        ghosts_equal = 1
+        if halo is not None:
+            dist.all_reduce(num)
+            z = y.clone()
+            halo.update_fwd(z)
+            ge = torch.tensor([int(torch.equal(z, y))], device=dev)
+            dist.all_reduce(ge, op=dist.ReduceOp.MIN)
+            ghosts_equal = int(ge.item())
+        rel = float(torch.sqrt(num[0] / num[1]).item())
+        parity = {"rel_l2_vs_cell_kernel": rel, "tol": 1e-12, "ghost_copies_bitwise_equal": bool(ghosts_equal),
+                  "ok": bool(rel < 1e-12 and ghosts_equal)}
+        del simple, y2, minv
+        assert parity["ok"], f"in-run parity check failed: {parity}"
+
+    # structured fast path (SURVEY 8f-2): the same mesh without the vertex perturbation -- every cell a
+    # parallelepiped, G = w_q * A_cell, 6 scalars per cell, per-point G never read.  Separate roofline
+    # with its own algorithmic bytes.
+    affine = None
+    if world == 1 and not args.no_affine and args.perturb > 0:
+        mesh_a = wfx.create_box_hex(gshape, P, glen, perturb=0.0)
+        geo_a = wfx.Geometry(mesh_a, P, ctx=ctx)
+        stiff_a = wfx.StiffnessOperator(mesh_a, P, ctx=ctx, geometry=geo_a)
+        mass_a = wfx.MassOperator(mesh_a, P, ctx=ctx, geometry=geo_a)
+        minv_a = mass_a.inverse_diagonal_ptr()
+        ki_a, info_a = stiff_a.kernel_info(), stiff_a.info()
+        for _ in range(args.warmup):
+            stiff_a.apply_scaled(x, minv_a, y)
+        wa = []
+        for _ in range(args.windows):
+            sync_all()
+            ev0.record()
+            for _ in range(args.steps):
+                stiff_a.apply_scaled(x, minv_a, y)
+            ev1.record()
+            sync_all()
+            wa.append(ev0.elapsed_time(ev1) / args.steps)
+        ms_a = float(np.median(wa))
+        # parity of the fast path inside the run: against the per-cell kernel on the per-point G
+        simple_a = wfx.StiffnessOperator(mesh_a, P, ctx=ctx, geometry=geo_a, mode=wfx.capi.STIFF_CELL_COLOUR)
+        ya = torch.empty_like(x)
+        simple_a.apply(x, ya, beta=0)
+        ya *= torch.from_numpy(mass_a.inverse_diagonal()).to(dev)
+        rel_a = float(((y - ya).norm() / ya.norm()).item())
+        assert rel_a < 1e-12, f"affine fast path differs from the general kernel: {rel_a}"
+        affine = {"ms_per_step": ms_a, "value": mesh_a.ndofs / (ms_a * 1e-3) / 1e9, "unit": UNIT,
+                  "kernel": ki_a, "bytes_per_step": info_a["bytes"], "windows_ms_per_step": wa,
+                  "rel_l2_vs_cell_kernel_general_G": rel_a}
+        del simple_a, ya, stiff_a, mass_a, geo_a, mesh_a
+
     # end-to-end through the C-ABI host entry point, pinned host buffers, copies in the timed region
-    e2e = None
+    xh = torch.empty(mesh.ndofs, dtype=torch.float64).pin_memory()
+    yh = torch.empty(mesh.ndofs, dtype=torch.float64).pin_memory()
+    xh.copy_(x)
+    n_e2e = max(3, min(args.steps, 10))
     if world == 1:
-        xh = torch.empty(mesh.ndofs, dtype=torch.float64).pin_memory()
-        yh = torch.empty(mesh.ndofs, dtype=torch.float64).pin_memory()
-        xh.copy_(x)
         call = lambda: wfx.capi.call("wfx_stiffness_mass_apply_host", stiff.handle, mass.handle,
                                      C.c_void_p(xh.data_ptr()), C.c_void_p(yh.data_ptr()))
         for _ in range(3):
             call()
-        n_e2e = max(3, min(args.steps, 10))
         t0 = time.perf_counter()
         for _ in range(n_e2e):
             call()
         dt = (time.perf_counter() - t0) / n_e2e
-        assert torch.allclose(yh, y.cpu(), rtol=0, atol=0), "host-path result differs from device path"
+        step()
+        assert torch.equal(yh, y.cpu()), "host-path result differs from device path"
         e2e = {"value": mesh.ndofs / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": mesh.ndofs * 8,
                "d2h_bytes_per_step": mesh.ndofs * 8, "ms_per_step": dt * 1e3}
     else:
         # every rank: its part of x from pinned host memory, the distributed apply (halo included),
         # its part of the result back to pinned host memory
-        xh = torch.empty(mesh.ndofs, dtype=torch.float64).pin_memory()
-        yh = torch.empty(mesh.ndofs, dtype=torch.float64).pin_memory()
-        xh.copy_(x)
-
         def host_step():
             x.copy_(xh, non_blocking=True)
             step()
@@ -247,15 +370,12 @@ def run_b200(args):
 
         for _ in range(3):
             host_step()
-        n_e2e = max(3, min(args.steps, 10))
         sync_all()
         t0 = time.perf_counter()
         for _ in range(n_e2e):
             host_step()
         sync_all()
-        t = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+        dt = max_over_ranks([(time.perf_counter() - t0) / n_e2e])[0]
         nb = torch.tensor([mesh.ndofs * 8], dtype=torch.int64, device=dev)
         dist.all_reduce(nb)
         e2e = {"value": ndofs_global / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(nb.item()),
@@ -271,17 +391,17 @@ def run_b200(args):
         eqn.init()
         dt_w = wfx.cfl_timestep(mesh.h_min, 1500.0, P, 0.5e6)
         eqn.rk4(0.0, 1.0, dt_w, max_steps=2)
-        sync_all()
         k_rk = max(3, min(args.steps, 10))
-        ev0.record()
-        eqn.rk4(2 * dt_w, 1.0, dt_w, max_steps=k_rk)
-        ev1.record()
-        sync_all()
-        ms_rk = ev0.elapsed_time(ev1) / k_rk
-        if world > 1:
-            t = torch.tensor([ms_rk], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_rk = float(t.item())
+        rk_local = []
+        for w in range(3):
+            sync_all()
+            ev0.record()
+            eqn.rk4((2 + w * k_rk) * dt_w, 1.0, dt_w, max_steps=k_rk)
+            ev1.record()
+            sync_all()
+            rk_local.append(ev0.elapsed_time(ev1) / k_rk)
+        rk_ms = max_over_ranks(rk_local)
+        ms_rk = float(np.median(rk_ms))
         u_chk, _ = eqn.get_state()
         # (the wave starts at x = 0: ranks away from the source face are still at rest)
         assert np.isfinite(u_chk).all() and (rank != 0 or np.abs(u_chk).max() > 0)
@@ -289,7 +409,7 @@ def run_b200(args):
         # write b) + the fused stage updates (10 + 11 + 11 + 7 vector passes)
         s8 = 8
         b_step = 4 * (info["num_cells"] * info["num_dofs"] * (6 * s8 + 4) + mesh.ndofs * 2 * s8) + 39 * mesh.ndofs * s8
-        rk4 = {"ms_per_step": ms_rk, "steps": k_rk, "dofs_global": int(ndofs_global),
+        rk4 = {"ms_per_step": ms_rk, "windows_ms_per_step": rk_ms, "steps": k_rk, "dofs_global": int(ndofs_global),
                "gdof_steps_per_s": ndofs_global / (ms_rk * 1e-3) / 1e9,
                "bytes_per_step_per_gpu": b_step, "achieved_gbs_per_gpu": b_step / (ms_rk * 1e-3) / 1e9}
 
@@ -303,34 +423,56 @@ def run_b200(args):
     # dominant kernel = stiff_brick_kernel: the step is its `nlaunches` colour launches, so the
     # kernel's average launch duration is ms / nlaunches and its algorithmic bytes per launch are
     # bytes / nlaunches; achieved = bytes per step / step time.
+    nc_nd = info["num_cells"] * info["num_dofs"]
+    bytes_no_dofmap = info["bytes"] - 4.0 * nc_nd
     achieved = info["bytes"] / (ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and args.cells == 64 and P == 4 and args.scaling == "weak":
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "stiff_brick_kernel",
+                "bytes_per_step": info["bytes"], "launches_per_step": info["nlaunches"],
+                # the regular-brick kernel never reads a per-point dofmap (positions are arithmetic; it reads
+                # one int32 per brick DOF instead): the same time against the bytes without the +4 B/point term
+                "frac_no_dofmap": bytes_no_dofmap / (ms * 1e-3) / 1e9 / peak,
+                "limiter": "HBM is the bounding roofline; ncu shows the kernel co-limited by the L1TEX/LSU "
+                           "data pipe and load latency at this occupancy (DESIGN.md section 6)"}
+    if sustained:
+        roofline["sustained"] = {"ms_per_step": sustained["ms_per_step"], "steps": sustained["steps"],
+                                 "achieved": info["bytes"] / (sustained["ms_per_step"] * 1e-3) / 1e9,
+                                 "frac": info["bytes"] / (sustained["ms_per_step"] * 1e-3) / 1e9 / peak,
+                                 "peak": peak, "clocks": sustained.get("clocks")}
+    if affine:
+        ach_a = affine["bytes_per_step"] / (affine["ms_per_step"] * 1e-3) / 1e9
+        affine["roofline"] = {"bound": "hbm", "achieved": ach_a, "peak": peak, "unit": "GB/s", "frac": ach_a / peak,
+                              "note": "algorithmic bytes of the fast path: 6 scalars of G per cell + x, 1/m, y once"}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle
-        threads = min(oracle.max_threads(), 32)
+        threads = host_threads()
         nd_cpu, t_cpu = cpu_operator_sample(args.ref_cells, P, threads)
         cpu = {"value": nd_cpu / t_cpu / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{args.ref_cells}^3 cells P{P} ({nd_cpu} dofs), dense skernel + b/m, {threads} OpenMP threads, -Ofast -march=native"}
+    s = 8
+    g_bytes, vec_bytes = 6 * s * nc_nd, 3 * s * mesh.ndofs
+    shape = "x".join(map(str, mesh.shape))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"stiffness+mass apply kv=M^-1(-c0^2 K u), {N}^3 hex cells per GPU, P{P}, fp64, "
+            "config": {"workload": f"stiffness+mass apply kv=M^-1(-c0^2 K u), {shape} hex cells per GPU, P{P}, fp64, "
                                    f"{'perturbed (non-affine)' if args.perturb else 'affine'} geometry, general 6-entry G per point",
-                       "cells_per_gpu": N ** 3, "dofs_global": int(ndofs_global), "degree": P,
-                       "l2_policy": "inputs larger than L2 (G 1.57 GB + vectors 0.4 GB per apply vs 126 MB L2)",
-                       "partition": "1" if world == 1 else "x".join(map(str, partition.rank_grid(world)))},
-            "clocks": clocks,
-            "e2e": e2e if e2e else {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                                    "note": "multi-GPU e2e = device-resident path"},
-            "gpu_launches": args.steps * (info["nlaunches"] + (0 if halo is None else 5)),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "stiff_brick_kernel",
-                         "bytes_per_step": info["bytes"], "launches_per_step": info["nlaunches"]},
-            "cpu_baseline": cpu, "rk4": rk4}
+                       "cells_per_gpu": int(info["num_cells"]), "dofs_global": int(ndofs_global), "degree": P,
+                       "l2_policy": f"inputs larger than L2 (G {g_bytes / 1e9:.2f} GB + vectors {vec_bytes / 1e9:.2f} GB per apply "
+                                    f"vs 126 MB L2); no flush needed",
+                       "dofmap": "brick-implicit (one int32 per brick dof, no per-point dofmap is read): see roofline.frac_no_dofmap",
+                       "timing": f"median of {args.windows} windows of {args.steps} applies, max over ranks per window",
+                       "partition": "x".join(map(str, grid)), "setup_s": round(t_setup, 2),
+                       "kernel": stiff.kernel_info(), "halo_transport": halo.transport if halo is not None else None},
+            "windows_ms": win_ms, "window_ms_min": min(win_ms), "window_ms_max": max(win_ms),
+            "clocks": clocks, "sustained": sustained, "parity": parity, "affine_fast_path": affine,
+            "e2e": e2e,
+            "gpu_launches": (args.windows * args.steps) * (info["nlaunches"] + (0 if halo is None else 5)),
+            "roofline": roofline, "cpu_baseline": cpu, "rk4": rk4}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -339,22 +481,26 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=None, help="default: 20 (b200 arm), 5 (reference arm)")
+    ap.add_argument("--steps", type=int, default=None, help="applies per timed window; default 20 (b200 arm), 5 (reference arm)")
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--windows", type=int, default=7, help="timed windows; the median is reported")
+    ap.add_argument("--sustain-s", type=float, default=0.6, help="length of the sustained window in seconds (0 = skip)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cells", type=int, default=64, help="cells per axis per GPU")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--cells", type=int, default=64, help="weak scaling: cells per axis per GPU")
+    ap.add_argument("--global-cells", type=int, default=128, help="strong scaling: cells per axis of the global mesh")
     ap.add_argument("--P", type=int, default=4)
     ap.add_argument("--perturb", type=float, default=0.15)
     ap.add_argument("--ref-cells", type=int, default=48, help="CPU sample mesh (cells per axis)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rk4", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-affine", action="store_true")
     args = ap.parse_args()
     if args.steps is None:
-        # 20 applies = 9 ms: boost clocks.  Sustained load (1000 applies, 0.5 s) runs into the board's
-        # software power cap: SM clock 1.70 instead of 1.97 GHz, 0.50 instead of 0.46 ms per apply
-        # (profiles/r1_scaling.md) -- the kernel is latency-bound, so it follows the SM clock.
         args.steps = 20 if args.impl == "b200" else 5
     args.steps = max(1, args.steps)
+    args.windows = max(5, args.windows)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)

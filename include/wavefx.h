@@ -107,6 +107,16 @@ int wfx_geometry_create(wfx_ctx* ctx, int P, int dtype, int64_t ncells, int64_t 
 /* Copy back in the reference layout: G [ncells][nq][3][3], detJ [ncells][nq] (fp64;
  * either pointer may be NULL). */
 int wfx_geometry_get(wfx_geom* geom, double* G_host, double* detJ_host);
+/* n_affine: cells whose G is w_q times one constant matrix to rounding (parallelepipeds, detected from
+ * the computed clamped G).  When every cell is affine the stiffness operator takes the structured
+ * fast path: 6 scalars per CELL instead of 6 per point, the per-point array is never read. */
+int wfx_geometry_info(wfx_geom* geom, int64_t* ncells, int64_t* n_affine);
+/* Heterogeneous medium: multiplies the stored G of cell c by coeff_host[c] > 0, e.g.
+ * (c0[c] / c0_ref)^2 so that a stiffness operator created with c0_ref applies -c0(x)^2 K with a
+ * piecewise-constant speed of sound at no cost per apply.  The reference leaves this open
+ * (`// TODO: Compute coefficients`, common/LinearGLL.hpp:170; `params` ignored at
+ * common/operators.hpp:113-115).  The mass (detJ) is not touched.  Call before applying. */
+int wfx_geometry_scale_cells(wfx_geom* geom, const double* coeff_host);
 int wfx_geometry_destroy(wfx_geom* geom);
 
 /* general-point building blocks of common/precompute.hpp (no fabs, no clamp, weights
@@ -139,7 +149,8 @@ int wfx_stiffness_apply(wfx_stiffness* op, const void* x_dev, void* y_dev, int b
  * non-shared dofs only; shared dofs are scaled by wfx_halo_update_rev_fwd_scaled after
  * their sum is complete.  part = -1 runs both parts.  Part 1 continues the apply that the
  * preceding part-0 call on the same stream started: same x_dev / y_dev, x unchanged in between
- * (its first kernel may start while part 0 is still draining). */
+ * (its first kernel may start while part 0 is still draining).  The operator keeps no per-apply
+ * state: different streams may apply it concurrently (to different y). */
 int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, int64_t ndofs,
                                      const int32_t* dofmap_host, double c0, int flags,
                                      int64_t nshared, const int32_t* shared_dofs_host,
@@ -163,6 +174,13 @@ int wfx_stiffness_mass_apply_host(wfx_stiffness* op, wfx_mass* mass, const void*
 int wfx_stiffness_info(wfx_stiffness* op, int64_t* num_cells, int* num_dofs_per_cell,
                        int64_t* ndofs, double* flops, double* bytes, int* ncolours,
                        int* nlaunches);
+/* Which kernel the plan selected: variant -1 simple per-cell kernel, 0 generic brick kernel (staged
+ * local dofmap), 1 regular-brick kernel (arithmetic positions), 2 the same with the conflict-free P4
+ * layout; affine = 1: structured fast path (6 scalars of G per cell, the per-point array is never
+ * read); mixed = 1: regular batches and irregular batches run their own kernel (two launches per
+ * colour). */
+int wfx_stiffness_kernel_info(wfx_stiffness* op, int* variant, int* affine, int* mixed,
+                              int* regular_batches, int* batches, int64_t* smem_bytes);
 int wfx_stiffness_destroy(wfx_stiffness* op);
 
 /* ---- mass: MassOperatorCPU (common/operators.hpp:43-109) / SpectralMassOperator
@@ -229,13 +247,21 @@ int wfx_comm_destroy(wfx_comm* comm);
  *   fwd_send_*: per destination rank, the owned local indices whose values ghosts elsewhere
  *               mirror (scatter_fwd_indices + offsets);
  *   fwd_recv_*: per source rank, the local ghost positions (>= size_local) filled from it.
+ * size_local / num_ghosts: the index map's sizes; offsets, ranks and every index are validated
+ * against them on the host (send indices in [0, size_local), receive indices in the ghost part,
+ * every ghost slot filled by one owner).  Collective over the communicator.
  * update_fwd: owner -> ghost copy (:132-143).  update_rev: ghost -> owner add (:189-199),
  * contributions added in neighbour order (atomic-free).  update_rev_fwd: the two fused,
  * one NCCL group each, leaving every copy of a shared dof bitwise identical. */
-int wfx_halo_create(wfx_ctx* ctx, wfx_comm* comm, int dtype, int n_send_nbr,
-                    const int32_t* send_ranks, const int32_t* send_offsets,
+int wfx_halo_create(wfx_ctx* ctx, wfx_comm* comm, int dtype, int64_t size_local, int64_t num_ghosts,
+                    int n_send_nbr, const int32_t* send_ranks, const int32_t* send_offsets,
                     const int32_t* send_indices, int n_recv_nbr, const int32_t* recv_ranks,
                     const int32_t* recv_offsets, const int32_t* recv_indices, wfx_halo** halo);
+/* 1: the fused ghost reduction runs over NVLink peer memory (one kernel that writes the neighbours'
+ * receive buffers directly), 0: over NCCL send/recv groups.  Peer memory is chosen when every rank
+ * of the communicator is a process on this host with a peer-accessible GPU; the environment
+ * variable WFX_HALO_TRANSPORT = auto | nccl | p2p overrides (p2p: fail instead of falling back). */
+int wfx_halo_transport(wfx_halo* halo, int* transport);
 int wfx_halo_update_fwd(wfx_halo* halo, void* x_dev, void* stream);
 int wfx_halo_update_rev(wfx_halo* halo, void* x_dev, void* stream);
 int wfx_halo_update_rev_fwd(wfx_halo* halo, void* x_dev, void* stream);
@@ -247,18 +273,26 @@ int wfx_halo_destroy(wfx_halo* halo);
 /* ---- wave model + RK4: LinearGLLOpt (common/LinearGLL.hpp:37-287) ----------
  * Borrows the operators (they must outlive the model).  halo may be NULL (one rank).
  * size_local: number of owned dofs (axpy touches owned entries only, :30).
- * State vectors u_n, v_n live on the device in the operators' dtype. */
+ * State vectors u_n, v_n live on the device in the operators' dtype.
+ * Distributed meshes: halo must have the model's dtype.  The lumped mass and the facet masses are
+ * summed over the ranks here when the model is fp64; an fp32 model must have them assembled
+ * beforehand (wfx_mass_assemble / wfx_boundary_assemble with a separate fp64 halo) or create fails. */
 int wfx_wave_create(wfx_ctx* ctx, wfx_stiffness* stiff, wfx_mass* mass, wfx_boundary* bnd,
                     wfx_halo* halo, int64_t size_local, double c0, double f0, double p0,
                     wfx_wave** wave);
 int wfx_wave_init(wfx_wave* wave);                                   /* :131-134 */
+/* Copies the state to the device; on a distributed mesh the ghost entries are then overwritten by
+ * their owners' values (u->scatter_fwd(), v->scatter_fwd(), :164,167). */
 int wfx_wave_set_state(wfx_wave* wave, const void* u_host, const void* v_host);
 int wfx_wave_get_state(wfx_wave* wave, void* u_host, void* v_host);
 int wfx_wave_state_ptrs(wfx_wave* wave, void** u_dev, void** v_dev);
 /* The right-hand sides on their own, device vectors of ndofs entries (dtype of the model):
  *   f0(t, u, v, result): result = v                                  (:141-144)
  *   f1(t, u, v, result): result = M^-1 (-c0^2 K u + boundary(g(t), v)) (:151-192), including the
- *   ghost reduction on a distributed mesh.  result must not alias u or v. */
+ *   ghost reduction on a distributed mesh.  result must not alias u or v.
+ *   Precondition on a distributed mesh: the ghost entries of u and v equal their owners' values
+ *   (the reference calls scatter_fwd on its own u, v first, :164,167; here u and v are the caller's
+ *   const vectors -- wfx_halo_update_fwd them if in doubt). */
 int wfx_wave_f0(wfx_wave* wave, double t, const void* u_dev, const void* v_dev, void* result_dev,
                 void* stream);
 int wfx_wave_f1(wfx_wave* wave, double t, const void* u_dev, const void* v_dev, void* result_dev,

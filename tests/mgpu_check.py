@@ -64,6 +64,57 @@ def main():
     err2 = np.linalg.norm(y2.cpu().numpy() - want) / np.linalg.norm(want)
     assert err2 < 1e-12, f"rank {rank}: split/scaled apply differs, rel L2 {err2:.3e}"
 
+    # transports: the fused ghost reduction over NVLink peer memory (one kernel writing the neighbours'
+    # buffers) must equal the NCCL send/recv path bitwise (same neighbour-order summation), also when
+    # repeated back to back (the flag epochs) and with the owner-side scaling
+    os.environ["WFX_HALO_TRANSPORT"] = "nccl"
+    halo_nccl = partition.Halo(mesh, ctx, comm=halo.comm)
+    del os.environ["WFX_HALO_TRANSPORT"]
+    assert halo_nccl.transport == "nccl"
+    transport = halo.transport
+    want_t = os.environ.get("WFX_EXPECT_TRANSPORT")
+    assert want_t is None or transport == want_t, f"halo transport is {transport}, expected {want_t}"
+    gen = torch.Generator(device=dev).manual_seed(7 + rank)
+    for it in range(6):
+        w = torch.randn(mesh.ndofs, dtype=torch.float64, device=dev, generator=gen)
+        wa, wb = w.clone(), w.clone()
+        if it % 2:
+            halo.update_rev_fwd_scaled(wa, minv)
+            halo_nccl.update_rev_fwd_scaled(wb, minv)
+        else:
+            halo.update_rev_fwd(wa)
+            halo_nccl.update_rev_fwd(wb)
+        torch.cuda.synchronize()
+        assert torch.equal(wa, wb), f"rank {rank}: {transport} and nccl ghost reductions differ (iteration {it})"
+    # fp32 halo + fp32 model: masses assembled through a separate fp64 set-up halo
+    halo32 = partition.Halo(mesh, ctx, np.float32, comm=halo.comm)
+    w32 = torch.randn(mesh.ndofs, dtype=torch.float32, device=dev, generator=gen)
+    os.environ["WFX_HALO_TRANSPORT"] = "nccl"
+    halo32n = partition.Halo(mesh, ctx, np.float32, comm=halo.comm)
+    del os.environ["WFX_HALO_TRANSPORT"]
+    wa, wb = w32.clone(), w32.clone()
+    halo32.update_rev_fwd(wa)
+    halo32n.update_rev_fwd(wb)
+    torch.cuda.synchronize()
+    assert torch.equal(wa, wb)
+    try:
+        mass.__class__(mesh, P, ctx=ctx, geometry=geo).assemble(halo32)
+        raise AssertionError("assembling the fp64 diagonal through an fp32 halo must fail")
+    except wfx.WfxError:
+        pass
+    dt32 = wfx.cfl_timestep(gmesh.h_min, c0, P, f0)
+    geqn32 = wfx.LinearGLLOpt(gmesh, None, P, c0, f0, p0, dtype=np.float32, ctx=ctx)
+    geqn32.init()
+    geqn32.rk4(0.0, 1.0, dt32, max_steps=10)
+    ug32, _ = geqn32.get_state()
+    eqn32 = wfx.LinearGLLOpt(mesh, None, P, c0, f0, p0, dtype=np.float32, ctx=ctx, halo=halo32)
+    eqn32.init()
+    eqn32.rk4(0.0, 1.0, dt32, max_steps=10)
+    u32, _ = eqn32.get_state()
+    e32 = np.linalg.norm(u32.astype(np.float64) - ug32[mesh.global_dofs]) / max(np.linalg.norm(ug32), 1e-300)
+    assert e32 < 2e-5, f"rank {rank}: fp32 distributed RK4 mismatch {e32:.3e}"
+    del eqn32, geqn32
+
     # forward update alone: ghosts take the owner's value
     z = torch.from_numpy(xg[mesh.global_dofs].copy()).to(dev)
     z[mesh.size_local:] = -1.0
@@ -95,7 +146,7 @@ def main():
     assert torch.equal(lo, hi), "copies of a shared dof differ between ranks"
     dist.barrier()
     if rank == 0:
-        print(f"mgpu_check ok: world {world} grid {grid} apply {err:.2e} rk4 u {eu:.2e} v {ev:.2e}")
+        print(f"mgpu_check ok: world {world} grid {grid} transport {transport} apply {err:.2e} rk4 u {eu:.2e} v {ev:.2e} fp32 {e32:.1e}")
     dist.destroy_process_group()
 
 

@@ -36,3 +36,29 @@ def test_default_arm_fails_loudly_without_gpu():
                        timeout=600, cwd=ROOT)
     assert r.returncode != 0
     assert not any(l.startswith("{") and '"value"' in l for l in r.stdout.splitlines())
+
+
+def test_reference_arm_is_independent_of_the_product_library():
+    """The CPU arm must not import the product package: it runs with the library path pointing
+    nowhere (capi raises on import when libwavefx.so is missing), under torch.distributed.run's
+    OMP_NUM_THREADS=1, and still uses the host cores it may run on."""
+    env = dict(os.environ, WFX_LIB="/nonexistent/libwavefx.so", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--ref-cells", "4"], capture_output=True, text=True, timeout=600, cwd=ROOT,
+                       env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d["cpu_baseline"]["cores"] == max(1, min(len(os.sched_getaffinity(0)), 32))
+
+
+def test_oracle_mesh_generator_matches_the_product_generator(wfx):
+    """oracle/refmesh.py (numpy + the oracle's permutation) and wave-fenics_b200/mesh.py (libwavefx's
+    permutation) are independent and produce the same DOLFINx-layout arrays."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from oracle import refmesh
+    for n, P, pert in (((3, 4, 5), 3, 0.1), (4, 4, 0.15), (2, 7, 0.0)):
+        a = wfx.create_box_hex(n, P, (0.1, 0.2, 0.3), perturb=pert)
+        b = refmesh.box(n, P, (0.1, 0.2, 0.3), perturb=pert)
+        assert np.array_equal(a.x, b.x) and np.array_equal(a.xdofs, b.xdofs) and np.array_equal(a.dofmap, b.dofmap)
+        assert a.ndofs == b.ndofs

@@ -219,6 +219,178 @@ def test_config2_full_size_properties(wfx, torch):
     assert abs(float(xl @ y2) - want) < 1e-11 * abs(want)
 
 
+def _host_threads():
+    import os
+    return max(1, min(len(os.sched_getaffinity(0)), 32))
+
+
+def test_config2_as_benchmarked_vs_oracle(wfx, orc, torch):
+    """BASELINE config 2 exactly as bench.py times it -- 64^3 cells, P4, fp64, perturb = 0.15 (non-affine,
+    full 3x3 G), the regular-brick kernel with the fused mass inverse -- against the reference's dense
+    skernel applied to EVERY cell (OpenMP over cells) and against the sum-factorised oracle."""
+    P, N = 4, 64
+    mesh = wfx.create_box_hex(N, P, (L, L, L), perturb=0.15)
+    assert mesh.ndofs == 16974593
+    nt = _host_threads()
+    Go, detJ = orc.precompute_geometric_data(mesh, P)
+    m = np.zeros(mesh.ndofs)
+    orc.mass_apply(mesh, P, detJ, np.ones(mesh.ndofs), m)
+    x = np.random.default_rng(42).standard_normal(mesh.ndofs)
+    kd = np.zeros(mesh.ndofs)
+    orc.stiffness_apply(mesh, P, Go, x, kd, dense=True, nthreads=nt)      # common/operators.hpp:113-133,183-200
+    ks = np.zeros(mesh.ndofs)
+    orc.stiffness_apply(mesh, P, Go, x, ks, dense=False, nthreads=nt)
+    assert rel_l2(ks, kd) < 1e-13
+    geo = wfx.Geometry(mesh, P)
+    op = wfx.StiffnessOperator(mesh, P, geometry=geo)
+    mass = wfx.MassOperator(mesh, P, geometry=geo)
+    assert np.array_equal(mass.diagonal(), m)
+    xd = dev(torch, x)
+    y = torch.full((mesh.ndofs,), float("nan"), dtype=torch.float64, device="cuda")
+    op.apply_scaled(xd, mass.inverse_diagonal_ptr(), y)                    # the timed call of bench.py
+    assert rel_l2(y.cpu().numpy(), kd / m) < TOL64                         # LinearGLL.hpp:188-191
+    y0 = np.random.default_rng(43).standard_normal(mesh.ndofs)
+    yd = dev(torch, y0)
+    op(xd, yd)                                                             # y += A x
+    assert rel_l2(yd.cpu().numpy() - y0, kd) < TOL64
+    # the end-to-end host entry point of bench.py's e2e leg gives the same bits as the device path
+    import ctypes as C
+    yh = np.empty(mesh.ndofs)
+    wfx.capi.call("wfx_stiffness_mass_apply_host", op.handle, mass.handle, C.c_void_p(x.ctypes.data),
+                  C.c_void_p(yh.ctypes.data))
+    assert np.array_equal(yh, y.cpu().numpy())
+    # a random 512-cell subset of the same mesh as a mesh of its own (irregular batches: the generic
+    # staged-dofmap kernel) against the dense skernel on those cells
+    import copy
+    sel = np.sort(np.random.default_rng(1).choice(mesh.ncells, 512, replace=False))
+    sub = copy.copy(mesh)
+    sub.xdofs = np.ascontiguousarray(mesh.xdofs[sel])
+    sub.dofmap = np.ascontiguousarray(mesh.dofmap[sel])
+    sop = wfx.StiffnessOperator(sub, P)
+    ys = torch.full((mesh.ndofs,), float("nan"), dtype=torch.float64, device="cuda")
+    sop.apply(xd, ys, beta=0)
+    kss = np.zeros(mesh.ndofs)
+    orc.stiffness_apply(sub, P, np.ascontiguousarray(Go[sel]), x, kss, dense=True)
+    assert rel_l2(ys.cpu().numpy(), kss) < TOL64
+
+
+@pytest.mark.parametrize("N", [9, 13])
+def test_ragged_mesh_mixed_plan_vs_oracle(wfx, orc, torch, N):
+    """Cells per axis not a multiple of the 4-cell brick (config 5's 133 = 33*4 + 1): full bricks run
+    the regular-brick kernel, the ragged rim the generic one, in the same apply."""
+    P = 4
+    mesh = _mesh(wfx, N, P, 0.15)
+    op = wfx.StiffnessOperator(mesh, P)
+    Go, _ = orc.precompute_geometric_data(mesh, P)
+    x = np.random.default_rng(42).standard_normal(mesh.ndofs)
+    yo = np.zeros(mesh.ndofs)
+    orc.stiffness_apply(mesh, P, Go, x, yo, dense=True, nthreads=_host_threads())
+    y = torch.full((mesh.ndofs,), float("nan"), dtype=torch.float64, device="cuda")
+    op.apply(dev(torch, x), y, beta=0)
+    assert rel_l2(y.cpu().numpy(), yo) < TOL64
+    y2 = torch.full_like(y, float("nan"))
+    op.apply(dev(torch, x), y2, beta=0)
+    assert torch.equal(y, y2)
+
+
+# ---- f2: affine / structured fast path -------------------------------------------------------------
+@pytest.mark.parametrize("P,N,dtype", [(4, 8, np.float64), (2, 16, np.float64), (3, 8, np.float64), (5, 4, np.float64),
+                                       (4, 8, np.float32)])
+def test_affine_fast_path_matches_reference(wfx, orc, torch, monkeypatch, P, N, dtype):
+    """Parallelepiped cells (sheared box: full symmetric A, not just a diagonal): every cell is
+    detected as affine, the operator takes the kernels that read 6 scalars of G per CELL, and the
+    result still matches the reference's per-point G through the dense skernel."""
+    mesh = wfx.create_box_hex(N, P, (L, 0.8 * L, 1.3 * L))
+    shear = np.array([[1.0, 0.2, 0.1], [0.0, 1.0, 0.3], [0.0, 0.0, 1.0]])
+    mesh.x = mesh.x @ shear.T                                   # affine map of the whole mesh
+    geo = wfx.Geometry(mesh, P, dtype=dtype)
+    assert geo.info()["n_affine"] == mesh.ncells
+    op = wfx.StiffnessOperator(mesh, P, dtype=dtype, geometry=geo)
+    assert op.kernel_info()["affine"] and op.kernel_info()["variant"] == "brick-regular"
+    assert op.info()["bytes"] == mesh.ncells * 6 * np.dtype(dtype).itemsize + 3 * mesh.ndofs * np.dtype(dtype).itemsize
+    Go, _ = orc.precompute_geometric_data(mesh, P)
+    x = np.random.default_rng(42).standard_normal(mesh.ndofs).astype(dtype)
+    yo = np.zeros(mesh.ndofs)
+    orc.stiffness_apply(mesh, P, Go, x.astype(np.float64), yo, dense=True, nthreads=_host_threads())
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    y = torch.full((mesh.ndofs,), float("nan"), dtype=tdt, device="cuda")
+    op.apply(dev(torch, x), y, beta=0)
+    assert rel_l2(y.cpu().numpy(), yo) < (TOL64 if dtype == np.float64 else TOL32)
+    # the general kernel on the same geometry (per-point G) agrees to rounding
+    monkeypatch.setenv("WFX_AFFINE", "0")
+    op2 = wfx.StiffnessOperator(mesh, P, dtype=dtype, geometry=geo)
+    assert not op2.kernel_info()["affine"]
+    y2 = torch.full_like(y, float("nan"))
+    op2.apply(dev(torch, x), y2, beta=0)
+    assert rel_l2(y2.cpu().numpy(), y.cpu().numpy().astype(np.float64)) < (1e-14 if dtype == np.float64 else 1e-6)
+
+
+def test_affine_detection_is_per_cell(wfx, torch):
+    """One moved vertex makes exactly the cells around it non-affine; the operator then stays on
+    the general path."""
+    P, N = 4, 6
+    mesh = wfx.create_box_hex(N, P, (L, L, L))
+    v = (3 * (N + 1) + 3) * (N + 1) + 3                       # an interior vertex
+    mesh.x[v] += 0.1 * L / N
+    geo = wfx.Geometry(mesh, P)
+    assert geo.info()["n_affine"] == mesh.ncells - 8
+    assert not wfx.StiffnessOperator(mesh, P, geometry=geo).kernel_info()["affine"]
+
+
+# ---- f4: heterogeneous speed of sound folded into G ---------------------------------------------------
+@pytest.mark.parametrize("perturb", [0.0, 0.15])
+def test_piecewise_constant_speed_of_sound(wfx, orc, torch, perturb):
+    """c0(x) constant per cell (the reference's `// TODO: Compute coefficients`, LinearGLL.hpp:170):
+    scaling the stored G of cell c by (c0[c]/c0_ref)^2 makes the unchanged kernels apply -c0(x)^2 K."""
+    P, N = 4, 6
+    mesh = _mesh(wfx, N, P, perturb)
+    c0 = 1500.0 * (1.0 + 0.3 * np.random.default_rng(5).uniform(-1, 1, mesh.ncells))
+    geo = wfx.Geometry(mesh, P)
+    geo.scale_cells((c0 / 1500.0) ** 2)
+    op = wfx.StiffnessOperator(mesh, P, geometry=geo)
+    Go, _ = orc.precompute_geometric_data(mesh, P)
+    Go = Go * ((c0 / 1500.0) ** 2)[:, None, None, None]
+    x = np.random.default_rng(42).standard_normal(mesh.ndofs)
+    yo = np.zeros(mesh.ndofs)
+    orc.stiffness_apply(mesh, P, np.ascontiguousarray(Go), x, yo, dense=True, nthreads=_host_threads())
+    y = torch.full((mesh.ndofs,), float("nan"), dtype=torch.float64, device="cuda")
+    op.apply(dev(torch, x), y, beta=0)
+    assert rel_l2(y.cpu().numpy(), yo) < TOL64
+    with pytest.raises(wfx.WfxError):
+        geo.scale_cells(np.zeros(mesh.ncells))
+
+
+# ---- mixed plans: lattice bricks and irregular batches in one apply ------------------------------------
+def test_mixed_plan_regular_and_irregular_batches(wfx, orc, torch):
+    """A structured mesh with some cells duplicated in place (overlapping cells with fresh dofs): the
+    bricks holding a duplicate are no lattice bricks any more.  Those batches run the generic
+    (staged-dofmap) kernel, all others the regular-brick kernel, two launches per colour."""
+    import copy
+    P, N = 4, 8
+    base = _mesh(wfx, N, P, 0.15)
+    dup = np.array([3, 77, 200, 201, 450], dtype=np.int64)
+    mesh = copy.copy(base)
+    nd = (P + 1) ** 3
+    extra = base.ndofs + np.arange(len(dup) * nd, dtype=np.int32).reshape(len(dup), nd)
+    mesh.xdofs = np.concatenate([base.xdofs, base.xdofs[dup]])
+    mesh.dofmap = np.concatenate([base.dofmap, extra])
+    mesh.ndofs = base.ndofs + len(dup) * nd
+    op = wfx.StiffnessOperator(mesh, P)
+    ki = op.kernel_info()
+    assert ki["mixed"] and 0 < ki["regular_batches"] < ki["batches"]
+    Go, _ = orc.precompute_geometric_data(mesh, P)
+    x = np.random.default_rng(42).standard_normal(mesh.ndofs)
+    yo = np.zeros(mesh.ndofs)
+    orc.stiffness_apply(mesh, P, Go, x, yo, dense=True, nthreads=_host_threads())
+    y = torch.full((mesh.ndofs,), float("nan"), dtype=torch.float64, device="cuda")
+    op.apply(dev(torch, x), y, beta=0)
+    assert rel_l2(y.cpu().numpy(), yo) < TOL64
+    y0 = np.random.default_rng(1).standard_normal(mesh.ndofs)
+    yd = dev(torch, y0)
+    op(dev(torch, x), yd)
+    assert rel_l2(yd.cpu().numpy() - y0, yo) < TOL64
+
+
 # ---- a5: boundary form -------------------------------------------------------------------------
 def test_boundary_operator(wfx, orc, torch):
     P = 4

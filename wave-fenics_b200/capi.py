@@ -52,6 +52,8 @@ _SIG = {
     "wfx_memcpy_d2h": [_vp, _vp, _vp, C.c_int64],
     "wfx_geometry_create": [_vp, C.c_int, C.c_int, C.c_int64, C.c_int64, _c_f64p, _c_i32p, _vpp],
     "wfx_geometry_get": [_vp, _c_f64p, _c_f64p],
+    "wfx_geometry_info": [_vp, _c_i64p, _c_i64p],
+    "wfx_geometry_scale_cells": [_vp, _c_f64p],
     "wfx_geometry_destroy": [_vp],
     "wfx_compute_jacobian_data": [_vp, C.c_int64, C.c_int64, _c_f64p, _c_i32p, C.c_int, _c_f64p,
                                   _c_f64p, _c_f64p, _c_f64p, _c_f64p, _c_f64p],
@@ -67,6 +69,8 @@ _SIG = {
     "wfx_stiffness_mass_apply_host": [_vp, _vp, _vp, _vp],
     "wfx_stiffness_info": [_vp, _c_i64p, C.POINTER(C.c_int), _c_i64p, _c_f64p, _c_f64p,
                            C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "wfx_stiffness_kernel_info": [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                  C.POINTER(C.c_int), C.POINTER(C.c_int), _c_i64p],
     "wfx_stiffness_destroy": [_vp],
     "wfx_mass_create": [_vp, _vp, C.c_int64, _c_i32p, _vpp],
     "wfx_mass_apply": [_vp, _vp, _vp, C.c_int, _vp],
@@ -88,8 +92,9 @@ _SIG = {
     "wfx_comm_unique_id": [C.c_char_p],
     "wfx_comm_create": [_vp, C.c_char_p, C.c_int, C.c_int, _vpp],
     "wfx_comm_destroy": [_vp],
-    "wfx_halo_create": [_vp, _vp, C.c_int, C.c_int, _c_i32p, _c_i32p, _c_i32p, C.c_int, _c_i32p,
-                        _c_i32p, _c_i32p, _vpp],
+    "wfx_halo_create": [_vp, _vp, C.c_int, C.c_int64, C.c_int64, C.c_int, _c_i32p, _c_i32p, _c_i32p, C.c_int,
+                        _c_i32p, _c_i32p, _c_i32p, _vpp],
+    "wfx_halo_transport": [_vp, C.POINTER(C.c_int)],
     "wfx_halo_update_fwd": [_vp, _vp, _vp],
     "wfx_halo_update_rev": [_vp, _vp, _vp],
     "wfx_halo_update_rev_fwd": [_vp, _vp, _vp],
@@ -206,5 +211,5 @@ def debug_plan_stats(P, dofmap, ndofs, centroid=None, brick_edge=4, W=8, nloc_ca
     call("wfx_debug_plan_stats", P, ncells, ndofs, i32p(dofmap.reshape(-1)), cptr, brick_edge, W,
          nloc_cap, stats.ctypes.data_as(_c_i64p))
     keys = ["cell_colours", "batches", "batch_colours", "nloc_max", "rounds", "padded_slots",
-            "private_dofs", "batch_dofs", "untouched", "regular_batches", "Sx", "Sy"]
+            "private_dofs", "batch_dofs", "untouched", "regular_batches", "Sx", "Sy", "ms_cell_plan", "ms_brick_plan"]
     return dict(zip(keys, stats.tolist()))

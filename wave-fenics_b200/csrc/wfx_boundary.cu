@@ -189,8 +189,8 @@ extern "C" int wfx_boundary_assemble(wfx_boundary* op, wfx_halo* halo)
 {
   WFX_API_BEGIN
   if (!op || !halo) fail("NULL argument");
+  if (halo_dtype(halo) != WFX_F64) fail("boundary assemble: needs an fp64 halo (facet masses are summed in fp64)");
   if (op->assembled) return 0; // idempotent
-  op->assembled = true;
   ScopedDevice sd(op->ctx->device);
   // dense fp64 vectors through the ghost reduction, then compact again: a dof may carry a
   // boundary term here only because a neighbouring rank owns the tagged facet
@@ -228,8 +228,15 @@ extern "C" int wfx_boundary_assemble(wfx_boundary* op, wfx_halo* halo)
     op->d_m1.upload(op->h_m1);
     op->d_m2.upload(op->h_m2);
   }
+  op->assembled = true; // only after the reduction succeeded
   WFX_API_END
 }
+
+namespace wfx
+{
+bool boundary_assembled(const wfx_boundary* op) { return op->assembled; }
+int boundary_dtype(const wfx_boundary* op) { return op->dtype; }
+} // namespace wfx
 
 extern "C" int wfx_boundary_destroy(wfx_boundary* op)
 {

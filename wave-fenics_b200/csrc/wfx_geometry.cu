@@ -16,6 +16,8 @@ wfx_geom::~wfx_geom()
 {
   if (G6) cudaFree(G6);
   if (dJw) cudaFree(dJw);
+  if (Gc) cudaFree(Gc);
+  if (affine) cudaFree(affine);
 }
 
 namespace
@@ -146,6 +148,58 @@ geom_gll_kernel(int n, int64_t ncells, const double* __restrict__ x,
   }
 }
 
+// Affine-cell detection, one warp per cell: A = G(q0) / w_q0 at the first point, then every point
+// must satisfy |G(q) - w_q A| <= tol * w_q * max|A| entry by entry (the reference's G is
+// J^-1 (|det J| w_q) J^-T, precomputation.hpp:95-100: on a parallelepiped J is constant, so G is
+// w_q times a constant matrix up to rounding -- unless the absolute-tolerance clamp of :105-107 bit
+// at some points only, in which case the cell stays on the general path).
+template <typename T>
+__global__ void __launch_bounds__(256)
+affine_detect_kernel(int n, int64_t ncells, const T* __restrict__ G6, Tables1D tab, double tol,
+                     T* __restrict__ Gc, uint8_t* __restrict__ flag)
+{
+  const int n2 = n * n, nq = n2 * n;
+  const int64_t c = blockIdx.x * (int64_t)(blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (c >= ncells) return;
+  const T* g = G6 + c * (int64_t)nq * 6;
+  auto entry = [&](int k, int col, int m) { return (double)g[((int64_t)(k * 3 + m / 2) * n2 + col) * 2 + (m & 1)]; };
+  double A[6], amax = 0;
+  const double w0 = tab.wts[0] * tab.wts[0] * tab.wts[0];
+#pragma unroll
+  for (int m = 0; m < 6; ++m)
+  {
+    A[m] = entry(0, 0, m) / w0;
+    amax = fmax(amax, fabs(A[m]));
+  }
+  bool ok = amax > 0;
+  for (int r = lane; r < nq; r += 32)
+  {
+    const int k = r / n2, col = r - k * n2, i = col / n, j = col - i * n;
+    const double w = tab.wts[i] * tab.wts[j] * tab.wts[k];
+#pragma unroll
+    for (int m = 0; m < 6; ++m) ok = ok && fabs(entry(k, col, m) - w * A[m]) <= tol * w * amax;
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  if (lane == 0)
+  {
+    flag[c] = ok ? 1 : 0;
+#pragma unroll
+    for (int m = 0; m < 6; ++m) Gc[c * 6 + m] = (T)A[m];
+  }
+}
+
+// G[c] *= coeff[c] for every point of cell c (and the per-cell form)
+template <typename T>
+__global__ void __launch_bounds__(256)
+scale_cells_kernel(int64_t ncells, int per_cell, const double* __restrict__ coeff, T* __restrict__ G6,
+                   T* __restrict__ Gc)
+{
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (gid < ncells * per_cell) G6[gid] = (T)((double)G6[gid] * coeff[gid / per_cell]);
+  if (gid < ncells * 6) Gc[gid] = (T)((double)Gc[gid] * coeff[gid / 6]);
+}
+
 // common/precompute.hpp building blocks at arbitrary reference points.
 __global__ void __launch_bounds__(256)
 jacobian_data_kernel(int nq, int64_t ncells, const double* __restrict__ x,
@@ -230,9 +284,52 @@ extern "C" int wfx_geometry_create(wfx_ctx* ctx, int P, int dtype, int64_t ncell
     else
       geom_gll_kernel<float><<<grid, 256>>>(n, ncells, dx.p, dxd.p, tab, (float*)g->G6, g->dJw);
     WFX_CUDA(cudaGetLastError());
+    // affine cells
+    WFX_CUDA(cudaMalloc(&g->Gc, (size_t)ncells * 6 * esz));
+    WFX_CUDA(cudaMalloc((void**)&g->affine, (size_t)ncells));
+    const unsigned agrid = (unsigned)((ncells + 7) / 8);
+    if (dtype == WFX_F64)
+      affine_detect_kernel<double><<<agrid, 256>>>(n, ncells, (const double*)g->G6, tab, 1e-13, (double*)g->Gc, g->affine);
+    else
+      affine_detect_kernel<float><<<agrid, 256>>>(n, ncells, (const float*)g->G6, tab, 2e-6, (float*)g->Gc, g->affine);
+    WFX_CUDA(cudaGetLastError());
     WFX_CUDA(cudaDeviceSynchronize());
+    std::vector<uint8_t> fl((size_t)ncells);
+    WFX_CUDA(cudaMemcpy(fl.data(), g->affine, (size_t)ncells, cudaMemcpyDeviceToHost));
+    for (uint8_t f : fl) g->n_affine += f;
   }
   *out = guard.release();
+  WFX_API_END
+}
+
+extern "C" int wfx_geometry_info(wfx_geom* g, int64_t* ncells, int64_t* n_affine)
+{
+  WFX_API_BEGIN
+  if (!g) fail("geom is NULL");
+  if (ncells) *ncells = g->ncells;
+  if (n_affine) *n_affine = g->n_affine;
+  WFX_API_END
+}
+
+extern "C" int wfx_geometry_scale_cells(wfx_geom* g, const double* coeff_host)
+{
+  WFX_API_BEGIN
+  if (!g || !coeff_host) fail("NULL argument");
+  if (g->ncells == 0) return 0;
+  ScopedDevice sd(g->ctx->device);
+  for (int64_t c = 0; c < g->ncells; ++c)
+    if (!(coeff_host[c] > 0) || !std::isfinite(coeff_host[c])) fail("cell coefficient %lld is not positive and finite", (long long)c);
+  DevBuf<double> d((size_t)g->ncells);
+  d.upload(coeff_host, (size_t)g->ncells);
+  const int per_cell = g->nq * 6;
+  const int64_t total = g->ncells * per_cell;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (g->dtype == WFX_F64)
+    scale_cells_kernel<double><<<grid, 256>>>(g->ncells, per_cell, d.p, (double*)g->G6, (double*)g->Gc);
+  else
+    scale_cells_kernel<float><<<grid, 256>>>(g->ncells, per_cell, d.p, (float*)g->G6, (float*)g->Gc);
+  WFX_CUDA(cudaGetLastError());
+  WFX_CUDA(cudaDeviceSynchronize());
   WFX_API_END
 }
 

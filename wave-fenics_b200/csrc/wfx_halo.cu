@@ -1,8 +1,20 @@
-// Ghost-dof halo exchange over NCCL (NVLink 5 / NVSwitch inside one box).
-// Replaces VectorUpdater (demo/gpu_scatter_mpi/VectorUpdater.hpp:21-230): CUDA-aware
-// MPI_Irecv/MPI_Send per neighbour become one ncclGroup of ncclSend/ncclRecv on the
-// caller's stream; the atomicAdd unpack of update_rev (:197-198, common/cuda/scatter.cu:38-45)
-// becomes a segmented reduction that adds the neighbours' contributions in neighbour order.
+// Ghost-dof halo exchange inside one NVLink 5 / NVSwitch box.
+// Replaces VectorUpdater (demo/gpu_scatter_mpi/VectorUpdater.hpp:21-230).
+//
+// Two transports:
+//  * peer memory (default when every rank of the communicator is a process on this host whose
+//    GPU is peer-accessible): the fused ghost reduction  update_rev_fwd[_scaled]  -- the one
+//    exchange a time-step stage needs -- is ONE kernel.  Every rank writes its ghost partial sums
+//    straight into the owner's receive buffer over NVLink (buffers exported with cudaIpc at
+//    create time), releases a per-CTA flag there, the owner adds the contributions in neighbour
+//    order (atomic-free segmented reduction, optional 1/m scaling), writes the finished value
+//    straight into every ghost holder's receive buffer, releases a flag, and the holders unpack.
+//    No pack kernels, no NCCL groups, no host involvement: two NVLink one-way trips.
+//  * NCCL (fallback, and the checker of the first in the multi-GPU tests): CUDA-aware
+//    MPI_Irecv/MPI_Send per neighbour (:114-129,171-186) become one ncclGroup of
+//    ncclSend/ncclRecv per direction on the caller's stream; the atomicAdd unpack of update_rev
+//    (:197-198, common/cuda/scatter.cu:38-45) becomes the same segmented reduction.
+// update_fwd / update_rev on their own (set-up, tests) always take the NCCL path.
 #include "wfx_internal.h"
 
 #include <nccl.h>
@@ -10,6 +22,7 @@
 #include <algorithm>
 #include <cstring>
 #include <dlfcn.h>
+#include <unistd.h>
 
 using namespace wfx;
 
@@ -25,34 +38,37 @@ struct NcclApi
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
+NcclApi load_nccl()
+{
+  NcclApi api;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) fail("cannot load libnccl.so.2: %s", dlerror());
+  auto sym = [&](const char* name) {
+    void* p = dlsym(h, name);
+    if (!p) fail("libnccl.so.2 lacks %s", name);
+    return p;
+  };
+  api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+  api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+  api.Send = (decltype(api.Send))sym("ncclSend");
+  api.Recv = (decltype(api.Recv))sym("ncclRecv");
+  api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+  api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+  api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+  api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+  return api;
+}
+
 const NcclApi& nccl()
 {
-  static NcclApi api;
-  static bool ready = false;
-  if (!ready)
-  {
-    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!h) fail("cannot load libnccl.so.2: %s", dlerror());
-    auto sym = [&](const char* name) {
-      void* p = dlsym(h, name);
-      if (!p) fail("libnccl.so.2 lacks %s", name);
-      return p;
-    };
-    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
-    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
-    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
-    api.Send = (decltype(api.Send))sym("ncclSend");
-    api.Recv = (decltype(api.Recv))sym("ncclRecv");
-    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
-    api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
-    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
-    ready = true;
-  }
+  static const NcclApi api = load_nccl(); // function-local static: initialised once, thread-safe
   return api;
 }
 } // namespace
@@ -72,6 +88,38 @@ struct wfx_comm
   int nranks = 0, rank = 0;
 };
 
+namespace
+{
+constexpr int P2P_CTAS = 32;     // CTAs of the fused exchange kernel = flags per neighbour and direction
+constexpr int P2P_THREADS = 256;
+constexpr int P2P_MAXR = 64;     // largest communicator the peer-memory transport handles
+
+// what a rank publishes to the others at create time (all-gathered as bytes)
+struct P2PPub
+{
+  cudaIpcMemHandle_t handle;      // of the rank's pool
+  uint64_t host_hash;
+  int32_t ok, device, pid, pad;
+  int64_t rbuf_off[P2P_MAXR];     // byte offset in the pool where rank r's ghost contributions land (-1: none)
+  int64_t fbuf_off[P2P_MAXR];     // ... where owner r's finished values land
+  int64_t rflag_off[P2P_MAXR];    // byte offset of the flag row rank r releases after its reverse push
+  int64_t fflag_off[P2P_MAXR];    // ... after its forward push
+  int32_t rcount[P2P_MAXR];       // entries expected from rank r in the reverse / forward direction
+  int32_t fcount[P2P_MAXR];
+};
+
+uint64_t host_hash()
+{
+  char name[256] = {0};
+  gethostname(name, sizeof(name) - 1);
+  uint64_t h = 1469598103934665603ull;
+  for (const char* p = name; *p; ++p) h = (h ^ (unsigned char)*p) * 1099511628211ull;
+  // processes in different containers of one machine may share a host name but not /dev/shm:
+  // the boot id is the same, the IPC namespace is not -- good enough here, the open is checked anyway
+  return h;
+}
+} // namespace
+
 struct wfx_halo
 {
   wfx_ctx* ctx = nullptr;
@@ -85,6 +133,22 @@ struct wfx_halo
   int64_t nuniq = 0;
   DevBuf<int32_t> d_uniq, d_useg_src;
   DevBuf<int64_t> d_useg_off;
+  // peer-memory transport
+  bool p2p = false;
+  uint32_t epoch = 0;
+  unsigned char* pool = nullptr;      // rbuf | fbuf | rflags | fflags, exported with cudaIpc
+  size_t rbuf_o = 0, fbuf_o = 0, rflag_o = 0, fflag_o = 0, pool_bytes = 0;
+  std::vector<void*> peer_base;       // opened pools, indexed by rank (nullptr: not a neighbour)
+  DevBuf<void*> d_rbuf_dst, d_fbuf_dst;          // per recv / send neighbour: where my values go
+  DevBuf<uint32_t*> d_rflag_dst, d_fflag_dst;    // per recv / send neighbour: the flag row I release
+  DevBuf<int32_t> d_send_off, d_recv_off;
+  DevBuf<uint8_t> d_slot_nbr;                    // send slot -> send neighbour
+  ~wfx_halo()
+  {
+    for (void* p : peer_base)
+      if (p) cudaIpcCloseMemHandle(p);
+    if (pool) cudaFree(pool);
+  }
 };
 
 namespace
@@ -117,7 +181,127 @@ __global__ void unpack_add_kernel(int64_t nuniq, const int32_t* __restrict__ uni
   x[uniq[j]] = s;
 }
 
+// ---- peer-memory transport ------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
+{
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// data another GPU wrote into this GPU's memory: read at L2, never from a stale L1 line
+template <typename T> __device__ __forceinline__ T ld_peer_written(const T* p) { return __ldcg(p); }
+
+template <typename T>
+struct P2PArgs
+{
+  T* x;
+  const T* scale; // nullable
+  int n_recv_nbr, n_send_nbr;
+  const int32_t* recv_off;
+  const int32_t* recv_idx;
+  T* const* rbuf_dst;
+  uint32_t* const* rflag_dst;
+  int64_t nuniq;
+  const int32_t* uniq;
+  const int64_t* useg_off;
+  const int32_t* useg_src;
+  const T* rbuf;
+  const uint32_t* rflags;
+  const uint8_t* slot_nbr;
+  const int32_t* send_off;
+  T* const* fbuf_dst;
+  uint32_t* const* fflag_dst;
+  int64_t nrecv;
+  const T* fbuf;
+  const uint32_t* fflags;
+  uint32_t epoch;
+};
+
+// The fused ghost reduction.  No CTA waits for another CTA of its own grid, only for flags that
+// remote grids release, and no remote CTA needs more than this rank's flags of the same phase:
+// the CTAs need not be co-resident, so the kernel may share the GPU with the interior batches.
+template <typename T>
+__global__ void __launch_bounds__(P2P_THREADS)
+halo_p2p_kernel(const P2PArgs<T> a)
+{
+  const int cta = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
+  // 1. ghost partial sums -> their owners' receive buffers
+  for (int n = 0; n < a.n_recv_nbr; ++n)
+  {
+    const int beg = a.recv_off[n], end = a.recv_off[n + 1];
+    T* dst = a.rbuf_dst[n];
+    for (int i = beg + cta * P2P_THREADS + tid; i < end; i += G * P2P_THREADS) dst[i - beg] = a.x[a.recv_idx[i]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < a.n_recv_nbr) st_release_sys(a.rflag_dst[tid] + cta, a.epoch);
+  // 2. all contributions to my owned dofs have arrived
+  for (int f = tid; f < a.n_send_nbr * G; f += P2P_THREADS)
+    while ((int32_t)(ld_acquire_sys(a.rflags + f) - a.epoch) < 0) __nanosleep(32);
+  __syncthreads();
+  // 3. owner: add in neighbour order, scale, keep, and hand the finished value to every holder
+  for (int64_t j = cta * P2P_THREADS + tid; j < a.nuniq; j += (int64_t)G * P2P_THREADS)
+  {
+    const int32_t d = a.uniq[j];
+    T s = a.x[d];
+    const int64_t p0 = a.useg_off[j], p1 = a.useg_off[j + 1];
+    for (int64_t p = p0; p < p1; ++p) s += ld_peer_written(a.rbuf + a.useg_src[p]);
+    if (a.scale) s *= a.scale[d];
+    a.x[d] = s;
+    for (int64_t p = p0; p < p1; ++p)
+    {
+      const int32_t q = a.useg_src[p];
+      const int n = a.slot_nbr[q];
+      a.fbuf_dst[n][q - a.send_off[n]] = s;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < a.n_send_nbr) st_release_sys(a.fflag_dst[tid] + cta, a.epoch);
+  // 4. the owners' values of my ghosts have arrived
+  for (int f = tid; f < a.n_recv_nbr * G; f += P2P_THREADS)
+    while ((int32_t)(ld_acquire_sys(a.fflags + f) - a.epoch) < 0) __nanosleep(32);
+  __syncthreads();
+  // 5. unpack
+  for (int64_t i = cta * P2P_THREADS + tid; i < a.nrecv; i += (int64_t)G * P2P_THREADS)
+    a.x[a.recv_idx[i]] = ld_peer_written(a.fbuf + i);
+}
+
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + 255) / 256); }
+
+template <typename T>
+void exchange_p2p(wfx_halo* h, T* x, cudaStream_t st, const T* scale)
+{
+  P2PArgs<T> a;
+  a.x = x;
+  a.scale = scale;
+  a.n_recv_nbr = (int)h->recv_ranks.size();
+  a.n_send_nbr = (int)h->send_ranks.size();
+  a.recv_off = h->d_recv_off.p;
+  a.recv_idx = h->d_recv_idx.p;
+  a.rbuf_dst = (T* const*)h->d_rbuf_dst.p;
+  a.rflag_dst = h->d_rflag_dst.p;
+  a.nuniq = h->nuniq;
+  a.uniq = h->d_uniq.p;
+  a.useg_off = h->d_useg_off.p;
+  a.useg_src = h->d_useg_src.p;
+  a.rbuf = (const T*)(h->pool + h->rbuf_o);
+  a.rflags = (const uint32_t*)(h->pool + h->rflag_o);
+  a.slot_nbr = h->d_slot_nbr.p;
+  a.send_off = h->d_send_off.p;
+  a.fbuf_dst = (T* const*)h->d_fbuf_dst.p;
+  a.fflag_dst = h->d_fflag_dst.p;
+  a.nrecv = h->nrecv;
+  a.fbuf = (const T*)(h->pool + h->fbuf_o);
+  a.fflags = (const uint32_t*)(h->pool + h->fflag_o);
+  a.epoch = ++h->epoch;
+  halo_p2p_kernel<T><<<P2P_CTAS, P2P_THREADS, 0, st>>>(a);
+  WFX_CUDA(cudaGetLastError());
+}
 
 template <typename T>
 void exchange(wfx_halo* h, bool forward, T* x, cudaStream_t st, const T* scale = nullptr)
@@ -157,6 +341,12 @@ void run(wfx_halo* h, int what, void* x, void* stream, const void* scale = nullp
   if (!x) fail("halo: NULL vector");
   ScopedDevice sd(h->ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (what == 3 && h->p2p)
+  {
+    if (h->dtype == WFX_F64) exchange_p2p<double>(h, (double*)x, st, (const double*)scale);
+    else exchange_p2p<float>(h, (float*)x, st, (const float*)scale);
+    return;
+  }
   if (h->dtype == WFX_F64)
   {
     if (what & 1) exchange<double>(h, false, (double*)x, st, (const double*)scale);
@@ -167,6 +357,145 @@ void run(wfx_halo* h, int what, void* x, void* stream, const void* scale = nullp
     if (what & 1) exchange<float>(h, false, (float*)x, st, (const float*)scale);
     if (what & 2) exchange<float>(h, true, (float*)x, st);
   }
+}
+
+// all-gather of one fixed-size record per rank through NCCL (create time only)
+template <typename R>
+void allgather_records(wfx_comm* c, const R& mine, std::vector<R>& all)
+{
+  DevBuf<unsigned char> d_in(sizeof(R)), d_out(sizeof(R) * (size_t)c->nranks);
+  WFX_CUDA(cudaMemcpy(d_in.p, &mine, sizeof(R), cudaMemcpyHostToDevice));
+  WFX_NCCL(nccl().AllGather(d_in.p, d_out.p, sizeof(R), ncclChar, c->comm, nullptr));
+  WFX_CUDA(cudaStreamSynchronize(nullptr));
+  all.resize((size_t)c->nranks);
+  WFX_CUDA(cudaMemcpy(all.data(), d_out.p, sizeof(R) * (size_t)c->nranks, cudaMemcpyDeviceToHost));
+}
+
+// Sets up the peer-memory transport; returns false (after every rank has agreed) when it is not
+// available.  Collective over the communicator.
+bool setup_p2p(wfx_halo* h, size_t esz)
+{
+  wfx_comm* c = h->comm;
+  const int nr = c->nranks, me = c->rank;
+  auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  P2PPub pub;
+  memset(&pub, 0, sizeof(pub));
+  pub.ok = nr <= P2P_MAXR && h->send_ranks.size() < 256 && h->recv_ranks.size() < 256 ? 1 : 0;
+  pub.host_hash = host_hash();
+  pub.device = h->ctx->device;
+  pub.pid = (int32_t)getpid();
+  for (int r = 0; r < P2P_MAXR; ++r) pub.rbuf_off[r] = pub.fbuf_off[r] = pub.rflag_off[r] = pub.fflag_off[r] = -1;
+  // pool: rbuf (contributions to my owned dofs, send-list layout) | fbuf (owners' values of my
+  // ghosts, recv-list layout) | one flag row of P2P_CTAS words per neighbour and direction
+  h->rbuf_o = 0;
+  h->fbuf_o = align(h->rbuf_o + (size_t)h->nsend * esz);
+  h->rflag_o = align(h->fbuf_o + (size_t)h->nrecv * esz);
+  h->fflag_o = align(h->rflag_o + h->send_ranks.size() * P2P_CTAS * 4);
+  h->pool_bytes = align(h->fflag_o + h->recv_ranks.size() * P2P_CTAS * 4) + 256;
+  if (pub.ok)
+  {
+    if (cudaMalloc((void**)&h->pool, h->pool_bytes) != cudaSuccess || cudaMemset(h->pool, 0, h->pool_bytes) != cudaSuccess
+        || cudaDeviceSynchronize() != cudaSuccess || cudaIpcGetMemHandle(&pub.handle, h->pool) != cudaSuccess)
+    {
+      cudaGetLastError();
+      pub.ok = 0;
+    }
+  }
+  if (pub.ok)
+  {
+    for (size_t i = 0; i < h->send_ranks.size(); ++i)
+    {
+      const int r = h->send_ranks[i];
+      pub.rbuf_off[r] = (int64_t)(h->rbuf_o + (size_t)h->send_off[i] * esz);
+      pub.rflag_off[r] = (int64_t)(h->rflag_o + i * P2P_CTAS * 4);
+      pub.rcount[r] = h->send_off[i + 1] - h->send_off[i];
+    }
+    for (size_t j = 0; j < h->recv_ranks.size(); ++j)
+    {
+      const int r = h->recv_ranks[j];
+      pub.fbuf_off[r] = (int64_t)(h->fbuf_o + (size_t)h->recv_off[j] * esz);
+      pub.fflag_off[r] = (int64_t)(h->fflag_o + j * P2P_CTAS * 4);
+      pub.fcount[r] = h->recv_off[j + 1] - h->recv_off[j];
+    }
+  }
+  std::vector<P2PPub> all;
+  allgather_records(c, pub, all);
+  bool ok = true;
+  for (int r = 0; r < nr; ++r) ok = ok && all[r].ok && all[r].host_hash == pub.host_hash;
+  // the two ends of every edge must agree on the message sizes (guards against inconsistent input)
+  if (ok)
+  {
+    for (size_t j = 0; j < h->recv_ranks.size() && ok; ++j)
+    {
+      const int o = h->recv_ranks[j];
+      ok = all[o].rbuf_off[me] >= 0 && all[o].rcount[me] == h->recv_off[j + 1] - h->recv_off[j];
+    }
+    for (size_t i = 0; i < h->send_ranks.size() && ok; ++i)
+    {
+      const int g = h->send_ranks[i];
+      ok = all[g].fbuf_off[me] >= 0 && all[g].fcount[me] == h->send_off[i + 1] - h->send_off[i];
+    }
+  }
+  // open the neighbours' pools
+  h->peer_base.assign((size_t)nr, nullptr);
+  if (ok)
+  {
+    std::vector<int> nbrs(h->send_ranks.begin(), h->send_ranks.end());
+    nbrs.insert(nbrs.end(), h->recv_ranks.begin(), h->recv_ranks.end());
+    std::sort(nbrs.begin(), nbrs.end());
+    nbrs.erase(std::unique(nbrs.begin(), nbrs.end()), nbrs.end());
+    for (int r : nbrs)
+    {
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+      {
+        cudaGetLastError();
+        ok = false;
+        break;
+      }
+      h->peer_base[r] = p;
+    }
+  }
+  // agree: one rank that cannot open a pool sends everybody to the NCCL path
+  struct Vote { int32_t ok; };
+  std::vector<Vote> votes;
+  allgather_records(c, Vote{ok ? 1 : 0}, votes);
+  for (const Vote& v : votes) ok = ok && v.ok;
+  if (!ok)
+  {
+    for (void*& p : h->peer_base)
+    {
+      if (p) cudaIpcCloseMemHandle(p);
+      p = nullptr;
+    }
+    if (h->pool) cudaFree(h->pool);
+    h->pool = nullptr;
+    return false;
+  }
+  std::vector<void*> rdst, fdst;
+  std::vector<uint32_t*> rfl, ffl;
+  for (size_t j = 0; j < h->recv_ranks.size(); ++j)
+  {
+    const int o = h->recv_ranks[j];
+    rdst.push_back((unsigned char*)h->peer_base[o] + all[o].rbuf_off[me]);
+    rfl.push_back((uint32_t*)((unsigned char*)h->peer_base[o] + all[o].rflag_off[me]));
+  }
+  std::vector<uint8_t> slot_nbr((size_t)h->nsend);
+  for (size_t i = 0; i < h->send_ranks.size(); ++i)
+  {
+    const int g = h->send_ranks[i];
+    fdst.push_back((unsigned char*)h->peer_base[g] + all[g].fbuf_off[me]);
+    ffl.push_back((uint32_t*)((unsigned char*)h->peer_base[g] + all[g].fflag_off[me]));
+    for (int q = h->send_off[i]; q < h->send_off[i + 1]; ++q) slot_nbr[q] = (uint8_t)i;
+  }
+  h->d_rbuf_dst.upload(rdst);
+  h->d_rflag_dst.upload(rfl);
+  h->d_fbuf_dst.upload(fdst);
+  h->d_fflag_dst.upload(ffl);
+  h->d_slot_nbr.upload(slot_nbr);
+  h->d_send_off.upload(h->send_off);
+  h->d_recv_off.upload(h->recv_off);
+  return true;
 }
 } // namespace
 
@@ -214,16 +543,48 @@ extern "C" int wfx_comm_destroy(wfx_comm* c)
   WFX_API_END
 }
 
-extern "C" int wfx_halo_create(wfx_ctx* ctx, wfx_comm* comm, int dtype, int n_send_nbr,
-                               const int32_t* send_ranks, const int32_t* send_offsets,
-                               const int32_t* send_indices, int n_recv_nbr,
-                               const int32_t* recv_ranks, const int32_t* recv_offsets,
-                               const int32_t* recv_indices, wfx_halo** out)
+namespace
+{
+// offsets start at 0 and never decrease, neighbour ranks are valid and distinct, indices lie in the
+// stated part of the vector: bad input must fail here, not as out-of-bounds device writes
+void validate_lists(const char* what, int nnbr, const int32_t* ranks, const int32_t* offsets,
+                    const int32_t* indices, int nranks, int me, int64_t lo, int64_t hi)
+{
+  if (nnbr == 0) return;
+  if (!ranks || !offsets) fail("halo: %s ranks / offsets are NULL", what);
+  if (offsets[0] != 0) fail("halo: %s offsets do not start at 0", what);
+  std::vector<uint8_t> seen((size_t)nranks, 0);
+  for (int i = 0; i < nnbr; ++i)
+  {
+    if (offsets[i + 1] < offsets[i]) fail("halo: %s offsets decrease at neighbour %d", what, i);
+    const int r = ranks[i];
+    if (r < 0 || r >= nranks || r == me) fail("halo: bad %s rank %d", what, r);
+    if (seen[r]) fail("halo: %s rank %d listed twice", what, r);
+    seen[r] = 1;
+  }
+  const int64_t n = offsets[nnbr];
+  if (n > 0 && !indices) fail("halo: %s indices are NULL", what);
+  for (int64_t p = 0; p < n; ++p)
+    if (indices[p] < lo || indices[p] >= hi)
+      fail("halo: %s index %d outside [%lld, %lld)", what, indices[p], (long long)lo, (long long)hi);
+}
+} // namespace
+
+extern "C" int wfx_halo_create(wfx_ctx* ctx, wfx_comm* comm, int dtype, int64_t size_local,
+                               int64_t num_ghosts, int n_send_nbr, const int32_t* send_ranks,
+                               const int32_t* send_offsets, const int32_t* send_indices,
+                               int n_recv_nbr, const int32_t* recv_ranks,
+                               const int32_t* recv_offsets, const int32_t* recv_indices,
+                               wfx_halo** out)
 {
   WFX_API_BEGIN
   if (!ctx || !comm || !out) fail("NULL argument");
   if (dtype != WFX_F64 && dtype != WFX_F32) fail("unknown dtype %d", dtype);
   if (n_send_nbr < 0 || n_recv_nbr < 0) fail("negative neighbour count");
+  if (size_local < 0 || num_ghosts < 0) fail("halo: negative vector size");
+  validate_lists("send", n_send_nbr, send_ranks, send_offsets, send_indices, comm->nranks, comm->rank, 0, size_local);
+  validate_lists("receive", n_recv_nbr, recv_ranks, recv_offsets, recv_indices, comm->nranks, comm->rank, size_local,
+                 size_local + num_ghosts);
   ScopedDevice sd(ctx->device);
   auto h = std::make_unique<wfx_halo>();
   h->ctx = ctx;
@@ -235,12 +596,18 @@ extern "C" int wfx_halo_create(wfx_ctx* ctx, wfx_comm* comm, int dtype, int n_se
   else h->send_off.assign(1, 0);
   if (n_recv_nbr) h->recv_off.assign(recv_offsets, recv_offsets + n_recv_nbr + 1);
   else h->recv_off.assign(1, 0);
-  for (int r : h->send_ranks)
-    if (r < 0 || r >= comm->nranks || r == comm->rank) fail("halo: bad destination rank %d", r);
-  for (int r : h->recv_ranks)
-    if (r < 0 || r >= comm->nranks || r == comm->rank) fail("halo: bad source rank %d", r);
   h->nsend = h->send_off.back();
   h->nrecv = h->recv_off.back();
+  {
+    // a ghost slot is filled by exactly one owner
+    std::vector<uint8_t> seen((size_t)num_ghosts, 0);
+    for (int64_t p = 0; p < h->nrecv; ++p)
+    {
+      uint8_t& s = seen[recv_indices[p] - size_local];
+      if (s) fail("halo: ghost slot %d listed twice", recv_indices[p]);
+      s = 1;
+    }
+  }
   const size_t esz = dtype == WFX_F64 ? 8 : 4;
   if (h->nsend)
   {
@@ -272,7 +639,28 @@ extern "C" int wfx_halo_create(wfx_ctx* ctx, wfx_comm* comm, int dtype, int n_se
     h->d_recv_idx.upload(recv_indices, (size_t)h->nrecv);
     h->d_recv_buf.alloc((size_t)h->nrecv * esz);
   }
+  // transport: peer memory unless told otherwise or unavailable (collective decision)
+  int want = -1; // -1 auto, 0 NCCL, 1 peer memory required
+  if (const char* e = std::getenv("WFX_HALO_TRANSPORT"))
+  {
+    if (!strcmp(e, "nccl")) want = 0;
+    else if (!strcmp(e, "p2p")) want = 1;
+    else if (strcmp(e, "auto")) fail("WFX_HALO_TRANSPORT must be auto, nccl or p2p");
+  }
+  if (want != 0 && comm->nranks > 1)
+  {
+    h->p2p = setup_p2p(h.get(), esz);
+    if (want == 1 && !h->p2p) fail("halo: peer-memory transport requested but not available");
+  }
   *out = h.release();
+  WFX_API_END
+}
+
+extern "C" int wfx_halo_transport(wfx_halo* h, int* transport)
+{
+  WFX_API_BEGIN
+  if (!h || !transport) fail("NULL argument");
+  *transport = h->p2p ? 1 : 0;
   WFX_API_END
 }
 

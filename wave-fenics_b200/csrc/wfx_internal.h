@@ -103,6 +103,10 @@ double clamp_m101(double v);                              // xt::isclose clamp t
 int stiffness_dtype(const struct ::wfx_stiffness* op);    // wfx_stiffness.cu
 bool stiffness_has_split(const struct ::wfx_stiffness* op); // interface/interior parts present
 int halo_dtype(const struct ::wfx_halo* h);                // wfx_halo.cu
+bool mass_assembled(const struct ::wfx_mass* op);          // wfx_mass.cu: diagonal summed over the ranks
+int mass_dtype(const struct ::wfx_mass* op);
+bool boundary_assembled(const struct ::wfx_boundary* op);  // wfx_boundary.cu: facet masses summed over the ranks
+int boundary_dtype(const struct ::wfx_boundary* op);
 // wfx_boundary_apply with the source amplitude g read from device memory at run time (CUDA-graph
 // replays of a time step change g without touching the graph), wfx_boundary.cu
 void boundary_apply_dev(struct ::wfx_boundary* op, double c0, const double* g_dev, const void* vn, void* b,
@@ -143,6 +147,14 @@ struct wfx_geom
   void* G6 = nullptr;     // T
   std::vector<uint8_t> g_colpos; // empty: identity; else column of point (i,j) = g_colpos[i*n+j]
   double* dJw = nullptr;  // fp64
+  // Affine cells (parallelepipeds): G[c,q] = w_q * A_c with one symmetric 3x3 A_c per cell.  Detected
+  // from the computed (clamped) per-point G, so a cell counts as affine only if the per-cell form
+  // reproduces the reference's values to rounding.  Gc [ncells][6] (00,01,02,11,12,22), dtype T,
+  // meaningful where affine[c] != 0; n_affine == ncells selects the stiffness kernels that never
+  // read G6 (structured fast path).
+  void* Gc = nullptr;
+  uint8_t* affine = nullptr;  // device [ncells]
+  int64_t n_affine = 0;
   // cell centroids (host) for the locality-preserving batch plan
   std::vector<float> centroid; // [ncells][3]
   ~wfx_geom();

@@ -275,8 +275,15 @@ extern "C" int wfx_mass_assemble(wfx_mass* op, wfx_halo* halo)
 {
   WFX_API_BEGIN
   if (!op || !halo) fail("NULL argument");
-  if (op->ndofs == 0 || op->assembled) return 0; // idempotent
-  op->assembled = true;
+  // the diagonal is reduced in fp64 whatever the operator's dtype: an fp32 halo would
+  // reinterpret the doubles (the model's own halo is not usable here for fp32 models)
+  if (halo_dtype(halo) != WFX_F64) fail("mass assemble: needs an fp64 halo (the diagonal is summed in fp64)");
+  if (op->assembled) return 0; // idempotent
+  if (op->ndofs == 0)
+  {
+    op->assembled = true;
+    return 0;
+  }
   ScopedDevice sd(op->ctx->device);
   if (wfx_halo_update_rev_fwd(halo, op->d_m64.p, nullptr)) fail("%s", wfx_last_error());
   const unsigned grid = (unsigned)((op->ndofs + 255) / 256);
@@ -286,8 +293,15 @@ extern "C" int wfx_mass_assemble(wfx_mass* op, wfx_halo* halo)
     mass_finish_kernel<float><<<grid, 256>>>(op->ndofs, op->d_m64.p, (float*)op->d_m, (float*)op->d_minv);
   WFX_CUDA(cudaGetLastError());
   WFX_CUDA(cudaDeviceSynchronize());
+  op->assembled = true; // only after the reduction succeeded: a failed call can be repeated
   WFX_API_END
 }
+
+namespace wfx
+{
+bool mass_assembled(const wfx_mass* op) { return op->assembled; }
+int mass_dtype(const wfx_mass* op) { return op->dtype; }
+} // namespace wfx
 
 extern "C" int wfx_mass_diagonal(wfx_mass* op, const void** m)
 {

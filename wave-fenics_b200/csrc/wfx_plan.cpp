@@ -4,6 +4,7 @@
 #include "wfx_internal.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -598,15 +599,20 @@ extern "C" int wfx_debug_plan_stats(int P, int64_t ncells, int64_t ndofs,
           if (d < 0 || d >= ndofs) fail("dofmap entry out of range");
           tdm[c * nd + k * n2 + i * n + j] = d;
         }
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t0 = now();
   CellColourPlan cp;
   build_cell_colour_plan(nd, ncells, ndofs, tdm.data(), cp);
+  const double t_cc = now() - t0;
   verify_cell_colour_plan(cp, nd, ncells, ndofs, tdm.data());
   BrickPlan bp;
   // brick_edge > 255: a non-cubic brick packed as ex | ey << 8 | ez << 16
   const BrickShape shape = brick_edge > 255
                                ? BrickShape(brick_edge & 255, (brick_edge >> 8) & 255, (brick_edge >> 16) & 255)
                                : BrickShape(brick_edge);
+  t0 = now();
   build_brick_plan(P, ncells, ndofs, tdm.data(), centroid_host, shape, W, nloc_cap, bp);
+  const double t_bp = now() - t0;
   verify_brick_plan(bp, tdm.data());
   if (stats)
   {
@@ -622,6 +628,8 @@ extern "C" int wfx_debug_plan_stats(int P, int64_t ncells, int64_t ndofs,
     stats[9] = bp.n_regular;
     stats[10] = bp.Sx;
     stats[11] = bp.Sy;
+    stats[12] = (int64_t)(t_cc * 1e3); // ms: cell colour plan
+    stats[13] = (int64_t)(t_bp * 1e3); // ms: brick plan
   }
   WFX_API_END
 }

@@ -126,10 +126,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+template <int N> struct Cfg; // per-degree launch configuration (below)
+
 template <typename T, int N>
 struct DMat
 {
   T d[N * N]; // D[q*N+i] = l_i'(x_q), [0,1,interior] ordering, clamped
+  T w[N];     // 1-D GLL weights (affine fast path: G(q) = w_i w_j w_k * A_cell)
 };
 
 // Optional phase timer (build with -DWFX_TIMING): lane 0 of every warp accumulates the
@@ -274,15 +277,16 @@ __device__ __forceinline__ int g_column(const RoleOff& ro, int lane, int g_order
   return ro.colK;
 }
 
-// G of one cell for this thread's column: [k][pair] 2-vectors, streamed once from HBM.
-template <typename T, int N>
+// G of one cell for this thread's column: [k][pair] 2-vectors, streamed once from HBM.  The
+// registers hold a window of GW planes (GW = N: the whole cell); this loads the first GW.
+template <typename T, int N, int GW>
 __device__ __forceinline__ void load_G(const T* __restrict__ Gc, int col,
-                                       typename Vec2<T>::type (&g)[N][3])
+                                       typename Vec2<T>::type (&g)[GW][3])
 {
   using V2 = typename Vec2<T>::type;
   const V2* gp = reinterpret_cast<const V2*>(Gc) + col;
 #pragma unroll
-  for (int k = 0; k < N; ++k)
+  for (int k = 0; k < GW; ++k)
 #pragma unroll
     for (int p = 0; p < 3; ++p) g[k][p] = ld_stream(gp + (k * 3 + p) * (N * N));
 }
@@ -322,14 +326,65 @@ __device__ __forceinline__ void line_transform(T* __restrict__ row, const DMat<T
 }
 
 // second half of part 1: w2 from the register line, w0 / w1 from the tiles, f = coeff * G w
-// gnext (nullable): this thread's column of the NEXT cell's G; plane k of it is requested into
-// g[k] as soon as plane k of the current cell is consumed, so the 3*N loads of a cell are spread
-// over the phase instead of hitting the load pipe (and L1, their landing buffer) in one burst.
-template <typename T, int N, typename L>
-__device__ __forceinline__ void g_multiply(const T (&u)[N], typename Vec2<T>::type (&g)[N][3],
+// The G registers are a rotating window of GW planes over the stream "cell, next cell, ...":
+// as soon as plane k is consumed its slot is refilled with the plane GW positions further on
+// (gcur: this cell, gnext: the next one, nullable), so the loads of a cell are spread over the
+// phase instead of hitting the load pipe (and L1, their landing buffer) in one burst.  GW = N keeps
+// a whole cell in flight (P <= 4); the higher degrees hold fewer planes to stay inside the register
+// budget and lean on the L2 prefetch for latency.  N is padded to a multiple of GW with planes that
+// are never loaded, which keeps every slot index a compile-time constant.
+template <typename T, int N, typename L, int GW>
+__device__ __forceinline__ void g_multiply(const T (&u)[N], typename Vec2<T>::type (&g)[GW][3],
                                            T* __restrict__ A, T* __restrict__ AT, const RoleOff& ro,
                                            const DMat<T, N>& Dm, T coeff, T (&f2)[N],
-                                           const typename Vec2<T>::type* gnext = nullptr)
+                                           const typename Vec2<T>::type* gcur,
+                                           const typename Vec2<T>::type* gnext)
+{
+  constexpr int NP = ((N + GW - 1) / GW) * GW;
+#pragma unroll
+  for (int k = 0; k < NP; ++k)
+  {
+    constexpr int dummy = 0;
+    (void)dummy;
+    if (k < N)
+    {
+      T w2 = 0;
+#pragma unroll
+      for (int m = 0; m < N; ++m) w2 += Dm.d[k * N + m] * u[m];
+      const T w0 = AT[k * L::PS_T + ro.kT];
+      const T w1 = A[k * L::PS_A + ro.kA];
+      const T g00 = g[k % GW][0].x, g01 = g[k % GW][0].y, g02 = g[k % GW][1].x;
+      const T g11 = g[k % GW][1].y, g12 = g[k % GW][2].x, g22 = g[k % GW][2].y;
+      AT[k * L::PS_T + ro.kT] = coeff * (g00 * w0 + g01 * w1 + g02 * w2); // f0
+      A[k * L::PS_A + ro.kA] = coeff * (g01 * w0 + g11 * w1 + g12 * w2);  // f1
+      f2[k] = coeff * (g02 * w0 + g12 * w1 + g22 * w2);
+    }
+    const int t = k + GW;
+    if (t < N)
+    {
+      if (gcur)
+      {
+#pragma unroll
+        for (int p = 0; p < 3; ++p) g[k % GW][p] = ld_stream(gcur + (t * 3 + p) * (N * N));
+      }
+    }
+    else if (t >= NP && t - NP < N)
+    {
+      if (gnext)
+      {
+#pragma unroll
+        for (int p = 0; p < 3; ++p) g[k % GW][p] = ld_stream(gnext + ((t - NP) * 3 + p) * (N * N));
+      }
+    }
+  }
+}
+
+// Affine cells: G(q) = w_q A with one symmetric A per cell (ga: 00,01,02,11,12,22) and
+// csk[k] = coeff * w_i w_j w_k for this thread's column -- no per-point G is read.
+template <typename T, int N, typename L>
+__device__ __forceinline__ void g_multiply_affine(const T (&u)[N], const T (&ga)[6], const T (&csk)[N],
+                                                  T* __restrict__ A, T* __restrict__ AT, const RoleOff& ro,
+                                                  const DMat<T, N>& Dm, T (&f2)[N])
 {
 #pragma unroll
   for (int k = 0; k < N; ++k)
@@ -339,24 +394,18 @@ __device__ __forceinline__ void g_multiply(const T (&u)[N], typename Vec2<T>::ty
     for (int m = 0; m < N; ++m) w2 += Dm.d[k * N + m] * u[m];
     const T w0 = AT[k * L::PS_T + ro.kT];
     const T w1 = A[k * L::PS_A + ro.kA];
-    const T g00 = g[k][0].x, g01 = g[k][0].y, g02 = g[k][1].x;
-    const T g11 = g[k][1].y, g12 = g[k][2].x, g22 = g[k][2].y;
-    AT[k * L::PS_T + ro.kT] = coeff * (g00 * w0 + g01 * w1 + g02 * w2); // f0
-    A[k * L::PS_A + ro.kA] = coeff * (g01 * w0 + g11 * w1 + g12 * w2);  // f1
-    f2[k] = coeff * (g02 * w0 + g12 * w1 + g22 * w2);
-    if (gnext)
-    {
-#pragma unroll
-      for (int p = 0; p < 3; ++p) g[k][p] = ld_stream(gnext + (k * 3 + p) * (N * N));
-    }
+    AT[k * L::PS_T + ro.kT] = csk[k] * (ga[0] * w0 + ga[1] * w1 + ga[2] * w2); // f0
+    A[k * L::PS_A + ro.kA] = csk[k] * (ga[1] * w0 + ga[3] * w1 + ga[4] * w2);  // f1
+    f2[k] = csk[k] * (ga[2] * w0 + ga[4] * w1 + ga[5] * w2);
   }
 }
 
-template <typename T, int N, typename L, typename Sync>
-__device__ __forceinline__ void cell_part1(const T (&u)[N], typename Vec2<T>::type (&g)[N][3],
+template <typename T, int N, typename L, int GW, typename Sync>
+__device__ __forceinline__ void cell_part1(const T (&u)[N], typename Vec2<T>::type (&g)[GW][3],
                                            T* __restrict__ tiles, const RoleOff& ro,
                                            const DMat<T, N>& Dm, T coeff, bool active, Sync sync,
                                            T (&f2)[N], PhaseTimer& tm,
+                                           const typename Vec2<T>::type* gcur = nullptr,
                                            const typename Vec2<T>::type* gnext = nullptr)
 {
   T* A = tiles;
@@ -379,18 +428,19 @@ __device__ __forceinline__ void cell_part1(const T (&u)[N], typename Vec2<T>::ty
   }
   sync();
   tm.mark(2);
-  if (active) g_multiply<T, N, L>(u, g, A, AT, ro, Dm, coeff, f2, gnext);
+  if (active) g_multiply<T, N, L, GW>(u, g, A, AT, ro, Dm, coeff, f2, gcur, gnext);
   tm.mark(3);
 }
 
 // Part 1 when all three roles already hold their input line (regular bricks: the lines are
 // read straight from the batch's staged dofs): no tile round trip for u and one barrier less.
-template <typename T, int N, typename L, typename Sync>
+template <typename T, int N, typename L, int GW, typename Sync>
 __device__ __forceinline__ void cell_part1_reg(const T (&u)[N], const T (&lj)[N], const T (&lI)[N],
-                                               typename Vec2<T>::type (&g)[N][3],
+                                               typename Vec2<T>::type (&g)[GW][3],
                                                T* __restrict__ tiles, const RoleOff& ro,
                                                const DMat<T, N>& Dm, T coeff, bool active, Sync sync,
                                                T (&f2)[N], PhaseTimer& tm,
+                                               const typename Vec2<T>::type* gcur = nullptr,
                                                const typename Vec2<T>::type* gnext = nullptr)
 {
   T* A = tiles;
@@ -414,7 +464,39 @@ __device__ __forceinline__ void cell_part1_reg(const T (&u)[N], const T (&lj)[N]
   }
   sync();
   tm.mark(2);
-  if (active) g_multiply<T, N, L>(u, g, A, AT, ro, Dm, coeff, f2, gnext);
+  if (active) g_multiply<T, N, L, GW>(u, g, A, AT, ro, Dm, coeff, f2, gcur, gnext);
+  tm.mark(3);
+}
+
+template <typename T, int N, typename L, typename Sync>
+__device__ __forceinline__ void cell_part1_reg_affine(const T (&u)[N], const T (&lj)[N], const T (&lI)[N],
+                                                      const T (&ga)[6], const T (&csk)[N],
+                                                      T* __restrict__ tiles, const RoleOff& ro,
+                                                      const DMat<T, N>& Dm, bool active, Sync sync,
+                                                      T (&f2)[N], PhaseTimer& tm)
+{
+  T* A = tiles;
+  T* AT = tiles + L::AT_OFF;
+  tm.mark(1);
+  if (active)
+  {
+#pragma unroll
+    for (int n = 0; n < N; ++n)
+    {
+      T s1 = 0, s0 = 0;
+#pragma unroll
+      for (int m = 0; m < N; ++m)
+      {
+        s1 += Dm.d[n * N + m] * lj[m];
+        s0 += Dm.d[n * N + m] * lI[m];
+      }
+      A[ro.rA + L::eA(n)] = s1;  // w1(i, n, k)
+      AT[ro.rT + L::eT(n)] = s0; // w0(n, j, k)
+    }
+  }
+  sync();
+  tm.mark(2);
+  if (active) g_multiply_affine<T, N, L>(u, ga, csk, A, AT, ro, Dm, f2);
   tm.mark(3);
 }
 
@@ -471,10 +553,10 @@ stiff_cell_kernel(const int32_t* __restrict__ cells, int ncl, const int32_t* __r
     u[k] = active ? x[dof[k]] : T(0);
     yv[k] = 0;
   }
-  if (active) load_G<T, N>(G6 + cell * (int64_t)(6 * ND), g_column<LayoutStd<N>, N>(ro, col, g_order), g);
+  if (active) load_G<T, N, N>(G6 + cell * (int64_t)(6 * ND), g_column<LayoutStd<N>, N>(ro, col, g_order), g);
   PhaseTimer tm;
   tm.start(false);
-  cell_part1<T, N, LayoutStd<N>>(u, g, s_w[slot], ro, Dm, coeff, active, BlockSync(), f2, tm);
+  cell_part1<T, N, LayoutStd<N>, N>(u, g, s_w[slot], ro, Dm, coeff, active, BlockSync(), f2, tm);
   cell_part2<T, N, LayoutStd<N>>(f2, s_w[slot], ro, Dm, active, BlockSync(), yv, tm);
   if (active)
   {
@@ -493,6 +575,7 @@ struct BrickArgs
   const int32_t* slot_cell;
   const uint16_t* ldm;
   const T* G6;
+  const T* Gc;    // AFF kernels: one symmetric 3x3 (6 entries) per cell
   const T* x;
   T* y;
   const T* scale; // nullable: applied on the LAST touch of a dof
@@ -505,6 +588,7 @@ struct BrickArgs
   int Sx, Sy;                // REG kernels: strides of the brick lattice in the shared arrays
   int g_order;               // column order of G6 (see g_column)
   int uni_nloc, uni_nr;      // > 0: every batch has this many dof positions / rounds (no header loads)
+  const int32_t* batch_ids;  // mixed plans: batch of CTA i is batch_ids[batch0 + i] (nullptr: batch0 + i)
 };
 
 // Shared memory of one CTA
@@ -516,14 +600,18 @@ struct BrickArgs
 // staged and all three roles read their input lines straight from xl (no tile round trip for u).
 // At P4 fp64 the REG layout is 99.1 KB: two CTAs fit the 196 KB carve-out, which leaves 60 KB of
 // L1 -- do not grow it ("L1 is part of the budget").
-template <typename T, int N, int SLOT, int W, int MINB, bool REG, typename L>
+// AFF (with REG): every cell is affine -- G(q) = w_q A_cell, 6 scalars per cell from a.Gc; the
+// per-point array G6 is never read (structured fast path).
+template <typename T, int N, int SLOT, int W, int MINB, bool REG, typename L, bool AFF = false>
 __global__ void __launch_bounds__(SLOT* W, MINB)
 stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
 {
+  static_assert(!AFF || REG, "the affine path is built for regular bricks only");
   // U: batch dofs handled per thread in one pass of the staging / write-back loops; all their
   // loads are issued before the first is consumed (two dependent memory round trips per pass)
   constexpr int N2 = N * N, ND = N2 * N, NT = SLOT * W, NDP = ndp_of<N>();
   constexpr int U = 21;
+  constexpr int GW = Cfg<N>::GW; // planes of G held in registers (rotating window, see g_multiply)
   using V2 = typename Vec2<T>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* xl = reinterpret_cast<T*>(smem_raw);
@@ -552,7 +640,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   pdl_launch_dependents(); // the next colour may start staging; it waits before touching y
   PhaseTimer tm;
   tm.start(threadIdx.x % 32 == 0);
-  const int b = batch0 + blockIdx.x;
+  const int b = a.batch_ids ? __ldg(a.batch_ids + batch0 + blockIdx.x) : batch0 + (int)blockIdx.x;
   // batch header: arithmetic when the plan is uniform (saves a memory round trip), else loaded
   const int64_t d0 = a.uni_nloc ? (int64_t)b * a.uni_nloc : __ldg(a.dof_off + b);
   const int nloc = a.uni_nloc ? a.uni_nloc : (int)(__ldg(a.dof_off + b + 1) - d0);
@@ -578,7 +666,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   // trip before anything else can be issued: ALL loads that depend only on the batch header (the
   // dof indices of the first pass, the slot tables, the first cells) are issued back to back
   // into registers first and consumed afterwards -- two round trips instead of six.
-  V2 g[N][3];
+  V2 g[GW][3];
   uint32_t e[U];
 #pragma unroll
   for (int q = 0; q < U; ++q) e[q] = tid + q * NT < nloc ? ld_once(a.bdofs + d0 + tid + q * NT) : BD_HOLE;
@@ -592,7 +680,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   for (int q = 1; q <= PF_DIST; ++q) cpf[q - 1] = q < nr ? __ldg(a.slot_cell + (int64_t)(r0 + q) * W + slot) : -1;
   // The G of the first 1 + PF_DIST rounds goes to L2 by bulk prefetch (one request per cell): the
   // register loads issued later are then L2 hits and leave the SM's load queue quickly.
-  if constexpr ((6 * ND * sizeof(T)) % 16 == 0)
+  if constexpr ((6 * ND * sizeof(T)) % 16 == 0 && !AFF)
     if (col == 0)
     {
       if (c0 >= 0) l2_prefetch_bulk(a.G6 + (int64_t)c0 * (6 * ND), (uint32_t)(6 * ND * sizeof(T)));
@@ -629,7 +717,23 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
     }
   }
   tm.mark(10);
-  if (lane_ok && c0 >= 0) load_G<T, N>(a.G6 + (int64_t)c0 * (6 * ND), gcol, g);
+  T ga[6], csk[N]; // AFF: the cell's matrix and coeff * w_i w_j w_k of this thread's column
+  if constexpr (AFF)
+  {
+    T wi = 0, wj = 0; // (static indices into the parameter bank: no local copy of Dm)
+#pragma unroll
+    for (int q = 0; q < N; ++q)
+    {
+      if (q == ro.iK) wi = Dm.w[q];
+      if (q == ro.jK) wj = Dm.w[q];
+    }
+    const T wij = a.coeff * wi * wj;
+#pragma unroll
+    for (int k = 0; k < N; ++k) csk[k] = wij * Dm.w[k];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) ga[q] = c0 >= 0 ? __ldg(a.Gc + (int64_t)c0 * 6 + q) : T(0);
+  }
+  else if (lane_ok && c0 >= 0) load_G<T, N, GW>(a.G6 + (int64_t)c0 * (6 * ND), gcol, g);
   cp_async_wait_all();
   tm.mark(11);
   if constexpr (!REG)
@@ -647,8 +751,15 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
     int li[N];
     T u[N], yv[N], f2[N];
     // this thread's column of the next cell's G: requested plane by plane inside the G multiply
-    const V2* gnext = cn >= 0 ? reinterpret_cast<const V2*>(a.G6 + (int64_t)cn * (6 * ND)) + gcol : nullptr;
+    const V2* gnext = (!AFF && cn >= 0) ? reinterpret_cast<const V2*>(a.G6 + (int64_t)cn * (6 * ND)) + gcol : nullptr;
+    const V2* gcur = (!AFF && cell >= 0) ? reinterpret_cast<const V2*>(a.G6 + (int64_t)cell * (6 * ND)) + gcol : nullptr;
     g_requested = active;
+    T gan[6]; // AFF: the next cell's matrix, requested a round ahead
+    if constexpr (AFF)
+    {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) gan[q] = cn >= 0 ? __ldg(a.Gc + (int64_t)cn * 6 + q) : T(0);
+    }
     if constexpr (REG)
     {
       const int base = active ? (int)sbase[r * W + slot] : 0;
@@ -664,8 +775,15 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
         lI[m] = active ? xl[base + offI + am * a.Sx] : T(0);
         yv[m] = 0;
       }
-      if constexpr (SLOT <= 32) cell_part1_reg<T, N, L>(u, lj, lI, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2, tm, gnext);
-      else cell_part1_reg<T, N, L>(u, lj, lI, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2, tm, gnext);
+      if constexpr (AFF)
+      {
+        if constexpr (SLOT <= 32) cell_part1_reg_affine<T, N, L>(u, lj, lI, ga, csk, tiles, ro, Dm, active, WarpSync(), f2, tm);
+        else cell_part1_reg_affine<T, N, L>(u, lj, lI, ga, csk, tiles, ro, Dm, active, BlockSync(), f2, tm);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) ga[q] = gan[q];
+      }
+      else if constexpr (SLOT <= 32) cell_part1_reg<T, N, L, GW>(u, lj, lI, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2, tm, gcur, gnext);
+      else cell_part1_reg<T, N, L, GW>(u, lj, lI, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2, tm, gcur, gnext);
     }
     else
     {
@@ -677,15 +795,16 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
         u[k] = active ? xl[li[k]] : T(0);
         yv[k] = 0;
       }
-      if constexpr (SLOT <= 32) cell_part1<T, N, L>(u, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2, tm, gnext);
-      else cell_part1<T, N, L>(u, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2, tm, gnext);
+      if constexpr (SLOT <= 32) cell_part1<T, N, L, GW>(u, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2, tm, gcur, gnext);
+      else cell_part1<T, N, L, GW>(u, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2, tm, gcur, gnext);
     }
     // G of this cell is consumed: request the next cell's G into the same registers so
     // that the loads fly during part 2 and the next gather
     {
-      if (lane_ok && cn >= 0 && !g_requested) load_G<T, N>(a.G6 + (int64_t)cn * (6 * ND), gcol, g);
+      if constexpr (!AFF)
+        if (lane_ok && cn >= 0 && !g_requested) load_G<T, N, GW>(a.G6 + (int64_t)cn * (6 * ND), gcol, g);
       // keep the L2 prefetch PF_DIST rounds ahead of the register loads
-      if constexpr ((6 * ND * sizeof(T)) % 16 == 0)
+      if constexpr ((6 * ND * sizeof(T)) % 16 == 0 && !AFF)
         if (col == 0 && r + 1 + PF_DIST < nr)
         {
           const int c2 = scell[(r + 1 + PF_DIST) * W + slot];
@@ -702,9 +821,9 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
       // cells' G, the batch's dof list and its local dofmap -- what that CTA waits for first.
       if (r == nr - 1 && col == 0 && (int)blockIdx.x + a.pf_stride < (int)gridDim.x)
       {
-        const int bn = b + a.pf_stride;
+        const int bn = a.batch_ids ? __ldg(a.batch_ids + batch0 + blockIdx.x + a.pf_stride) : b + a.pf_stride;
         const int r0n = a.uni_nr ? bn * a.uni_nr : __ldg(a.round_off + bn);
-        if constexpr ((6 * ND * sizeof(T)) % 16 == 0)
+        if constexpr ((6 * ND * sizeof(T)) % 16 == 0 && !AFF)
         {
           const int cq = __ldg(a.slot_cell + (int64_t)r0n * W + slot);
           if (cq >= 0) l2_prefetch_bulk(a.G6 + (int64_t)cq * (6 * ND), (uint32_t)(6 * ND * sizeof(T)));
@@ -773,7 +892,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   }
   if (nloc <= tid) pdl_wait(); // threads without a batch dof still honour the dependency
   tm.mark(9);
-  tm.flush((batch0 + blockIdx.x) * W + slot);
+  tm.flush(b * W + slot);
 }
 
 template <typename T>
@@ -801,11 +920,11 @@ __global__ void permute_g_columns_kernel(T* __restrict__ G6, int64_t nrows)
 }
 
 // per-degree launch configuration
-template <int N> struct Cfg;
 //                          SLOT  W  brick edge  cells/block (simple)  min CTAs/SM (brick)
 //                          preferred shared-memory carve-out in percent, fp64 / fp32 (0 = driver's choice)
-template <> struct Cfg<3> { static constexpr int SLOT = 16, W = 16, BX = 8, BY = 8, BZ = 8, CPB = 16, MINB = 2, CARVEOUT = 0, CARVEOUT32 = 0; };
-template <> struct Cfg<4> { static constexpr int SLOT = 16, W = 8, BX = 4, BY = 4, BZ = 4, CPB = 16, MINB = 4, CARVEOUT = 0, CARVEOUT32 = 0; };
+//                          GW: planes of G held in registers (must not exceed N; N = whole cell one round ahead)
+template <> struct Cfg<3> { static constexpr int SLOT = 16, W = 16, BX = 8, BY = 8, BZ = 8, CPB = 16, MINB = 2, CARVEOUT = 0, CARVEOUT32 = 0, GW = 3; };
+template <> struct Cfg<4> { static constexpr int SLOT = 16, W = 8, BX = 4, BY = 4, BZ = 4, CPB = 16, MINB = 4, CARVEOUT = 0, CARVEOUT32 = 0, GW = 4; };
 #ifndef WFX_P4_W
 #define WFX_P4_W 8
 #define WFX_P4_BE 4
@@ -817,16 +936,40 @@ template <> struct Cfg<4> { static constexpr int SLOT = 16, W = 8, BX = 4, BY = 
 #ifndef WFX_P4_CARVE
 #define WFX_P4_CARVE 0
 #endif
-template <> struct Cfg<5> { static constexpr int SLOT = 32, W = WFX_P4_W, BX = WFX_P4_BE, BY = WFX_P4_BE, BZ = WFX_P4_BZ, CPB = 8, MINB = WFX_P4_MINB, CARVEOUT = WFX_P4_CARVE, CARVEOUT32 = 0; };
+#ifndef WFX_P4_GW
+#define WFX_P4_GW 5
+#endif
+#ifndef WFX_P5_GW
+#define WFX_P5_GW 3
+#endif
+#ifndef WFX_P6_GW
+#define WFX_P6_GW 4
+#endif
+#ifndef WFX_P7_GW
+#define WFX_P7_GW 4
+#endif
+#ifndef WFX_P6_MINB
+#define WFX_P6_MINB 5
+#endif
+#ifndef WFX_P7_MINB
+#define WFX_P7_MINB 3
+#endif
+template <> struct Cfg<5> { static constexpr int SLOT = 32, W = WFX_P4_W, BX = WFX_P4_BE, BY = WFX_P4_BE, BZ = WFX_P4_BZ, CPB = 8, MINB = WFX_P4_MINB, CARVEOUT = WFX_P4_CARVE, CARVEOUT32 = 0, GW = WFX_P4_GW; };
 #ifndef WFX_P5_W
 #define WFX_P5_W 1
+#endif
+#ifndef WFX_P5_BX
 #define WFX_P5_BX 2
+#endif
+#ifndef WFX_P5_MINB
 #define WFX_P5_MINB 8
+#endif
+#ifndef WFX_P5_CARVE
 #define WFX_P5_CARVE 58
 #endif
-template <> struct Cfg<6> { static constexpr int SLOT = 64, W = WFX_P5_W, BX = WFX_P5_BX, BY = 2, BZ = 2, CPB = 4, MINB = WFX_P5_MINB, CARVEOUT = WFX_P5_CARVE, CARVEOUT32 = 0; };
-template <> struct Cfg<7> { static constexpr int SLOT = 64, W = 1, BX = 2, BY = 2, BZ = 2, CPB = 4, MINB = 5, CARVEOUT = 72, CARVEOUT32 = 58; };
-template <> struct Cfg<8> { static constexpr int SLOT = 64, W = 1, BX = 2, BY = 2, BZ = 2, CPB = 2, MINB = 3, CARVEOUT = 0, CARVEOUT32 = 0; };
+template <> struct Cfg<6> { static constexpr int SLOT = 64, W = WFX_P5_W, BX = WFX_P5_BX, BY = 2, BZ = 2, CPB = 4, MINB = WFX_P5_MINB, CARVEOUT = WFX_P5_CARVE, CARVEOUT32 = 0, GW = WFX_P5_GW; };
+template <> struct Cfg<7> { static constexpr int SLOT = 64, W = 1, BX = 2, BY = 2, BZ = 2, CPB = 4, MINB = WFX_P6_MINB, CARVEOUT = 72, CARVEOUT32 = 58, GW = WFX_P6_GW; };
+template <> struct Cfg<8> { static constexpr int SLOT = 64, W = 1, BX = 2, BY = 2, BZ = 2, CPB = 2, MINB = WFX_P7_MINB, CARVEOUT = 0, CARVEOUT32 = 0, GW = WFX_P7_GW; };
 
 struct LaunchCfg
 {
@@ -869,14 +1012,13 @@ struct wfx_stiffness
   double c0 = 0;
   bool use_pdl = true;
   double Dhost[WFX_MAXN * WFX_MAXN];
+  double Whost[WFX_MAXN]; // 1-D GLL weights
   // simple path
   CellColourPlan cplan;
   DevBuf<int32_t> d_cells, d_tdm;
   // brick path
   int ncolours = 0, nloc_pad = 0, W = 0, rounds_max = 0;
   int part_split = 0; // first execution colour of the interior part (distributed meshes)
-  int cur_part = -1;  // part selected by the running apply: -1 all, 0 interface, 1 interior
-  bool part0_launched = false; // the last apply was an interface part that launched kernels
   size_t smem_bytes = 0;
   std::vector<int32_t> colour_off;
   DevBuf<int64_t> d_dof_off;
@@ -886,6 +1028,13 @@ struct wfx_stiffness
   // regular-brick form (every batch a lattice brick): arithmetic positions, no staged dofmap
   int uni_nloc = 0, uni_nr = 0; // uniform plans: dof positions / rounds of every batch (else 0)
   int variant = 0; // 0 generic, 1 regular bricks, 2 regular bricks + the P4 fp64 conflict-free layout
+  bool affine = false; // every cell affine and every batch regular: the kernels that never read G6
+  // mixed plans: regular batches run the regular-brick kernel, the others the generic one (two
+  // launches per colour); lists of batch ids per colour
+  bool mixed = false;
+  int n_regular = 0, nbatches = 0;
+  std::vector<int32_t> reg_off, irr_off; // [ncolours+1] into d_reg_ids / d_irr_ids
+  DevBuf<int32_t> d_reg_ids, d_irr_ids;
   int Sx = 0, Sy = 0;
   size_t smem_bytes_reg = 0;
   DevBuf<uint16_t> d_slot_base;
@@ -915,14 +1064,16 @@ void launch_simple(wfx_stiffness* op, const T* x, T* y, cudaStream_t st)
 }
 
 template <typename T, int N>
-void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta, cudaStream_t st)
+void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta, int part, cudaStream_t st)
 {
   using C = Cfg<N>;
   using KernPtr = void (*)(BrickArgs<T>, DMat<T, N>, int);
   const int variant = op->variant;
-  KernPtr kern = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N>>;
+  const KernPtr kern_gen = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N>>;
+  KernPtr kern = kern_gen;
   size_t smem = op->smem_bytes;
   if (variant == 1) kern = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>>, smem = op->smem_bytes_reg;
+  if (variant == 1 && op->affine) kern = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>, true>;
   if constexpr (N == 5 && sizeof(T) == 8)
     if (variant == 2) kern = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutP4D>, smem = op->smem_bytes_reg;
   // experiment knob ("L1 is part of the budget"): extra dynamic shared memory per CTA
@@ -930,6 +1081,7 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   smem += smem_pad;
   DMat<T, N> Dm;
   for (int q = 0; q < N * N; ++q) Dm.d[q] = (T)op->Dhost[q];
+  for (int q = 0; q < N; ++q) Dm.w[q] = (T)op->Whost[q];
   BrickArgs<T> a;
   a.dof_off = op->d_dof_off.p;
   a.bdofs = op->d_bdofs.p;
@@ -937,6 +1089,7 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   a.slot_cell = op->d_slot_cell.p;
   a.ldm = op->d_ldm.p;
   a.G6 = (const T*)op->geom->G6;
+  a.Gc = (const T*)op->geom->Gc;
   a.x = x;
   a.y = y;
   a.scale = scale;
@@ -951,27 +1104,29 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   a.g_order = op->geom->g_colpos.empty() ? 0 : 1;
   a.uni_nloc = op->uni_nloc;
   a.uni_nr = op->uni_nr;
-  if (!beta && op->d_untouched.n && op->cur_part != 1)
+  a.batch_ids = nullptr;
+  if (!beta && op->d_untouched.n && part != 1)
   {
     const int n = (int)op->d_untouched.n;
     zero_entries_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(op->d_untouched.p, n, y);
   }
   // The interior part continues the apply its interface part started (same x, earlier in this
   // stream): its first launch may overlap that part's tail like any later colour.  Only if the
-  // interface part really launched something -- otherwise the kernel in front of us is x's producer.
-  bool first = !(op->cur_part == 1 && op->part0_launched);
-  if (op->cur_part != 1) op->part0_launched = false;
+  // interface part has batches at all -- otherwise the kernel in front of us is x's producer.
+  // (A property of the plan, not of the call history: the operator keeps no per-apply state and
+  // may be applied from several streams.)
+  const bool iface_nonempty = op->part_split > 0 && op->colour_off[op->part_split] > op->colour_off[0];
+  bool first = !(part == 1 && iface_nonempty);
   // execution colours of the requested part: interface batches [0, part_split), interior the rest
-  const int k0 = op->cur_part == 1 ? op->part_split : 0;
-  const int k1 = op->cur_part == 0 ? op->part_split : op->ncolours;
-  for (int k = k0; k < k1; ++k)
-  {
-    const int beg = op->colour_off[k], nb = op->colour_off[k + 1] - beg;
-    if (nb == 0) continue;
+  const int k0 = part == 1 ? op->part_split : 0;
+  const int k1 = part == 0 ? op->part_split : op->ncolours;
+  auto launch = [&](KernPtr kp, size_t smem_k, int beg, int nb, const int32_t* ids) {
+    if (nb == 0) return;
+    a.batch_ids = ids;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nb);
     cfg.blockDim = dim3(C::SLOT * C::W);
-    cfg.dynamicSmemBytes = smem;
+    cfg.dynamicSmemBytes = smem_k;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -980,11 +1135,21 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
     // the first colour must see everything earlier in the stream (x may have just been
     // produced); later colours overlap their staging with the previous colour's tail.
     cfg.numAttrs = (op->use_pdl && !first) ? 1 : 0;
-    WFX_CUDA(cudaLaunchKernelEx(&cfg, kern, a, Dm, beg));
+    WFX_CUDA(cudaLaunchKernelEx(&cfg, kp, a, Dm, beg));
     first = false;
-    if (op->cur_part == 0) op->part0_launched = true;
+  };
+  for (int k = k0; k < k1; ++k)
+  {
+    if (op->mixed)
+    {
+      // regular batches with the regular-brick kernel, the rest with the generic one; the two
+      // launches of a colour touch disjoint dofs and chain like colours do
+      launch(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>>, op->smem_bytes_reg + smem_pad,
+             op->reg_off[k], op->reg_off[k + 1] - op->reg_off[k], op->d_reg_ids.p);
+      launch(kern_gen, op->smem_bytes + smem_pad, op->irr_off[k], op->irr_off[k + 1] - op->irr_off[k], op->d_irr_ids.p);
+    }
+    else launch(kern, smem, op->colour_off[k], op->colour_off[k + 1] - op->colour_off[k], nullptr);
   }
-  if (op->cur_part == 1) op->part0_launched = false;
 }
 
 // opt in to the large dynamic shared-memory carve-out once per operator (per device)
@@ -996,6 +1161,8 @@ void configure_brick(wfx_stiffness* op)
   WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N>>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   if constexpr (N == 5 && sizeof(T) == 8)
     WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutP4D>,
@@ -1009,6 +1176,8 @@ void configure_brick(wfx_stiffness* op)
     WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N>>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>>,
+                                  cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>, true>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, carve));
   }
 }
@@ -1028,7 +1197,7 @@ void configure_any(wfx_stiffness* op)
 }
 
 template <typename T>
-void dispatch_apply(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta, cudaStream_t st)
+void dispatch_apply(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta, int part, cudaStream_t st)
 {
   if (op->mode == WFX_STIFF_CELL_COLOUR)
   {
@@ -1048,17 +1217,17 @@ void dispatch_apply(wfx_stiffness* op, const T* x, const T* scale, T* y, int bet
   }
   switch (op->N)
   {
-  case 3: launch_brick<T, 3>(op, x, scale, y, beta, st); break;
-  case 4: launch_brick<T, 4>(op, x, scale, y, beta, st); break;
-  case 5: launch_brick<T, 5>(op, x, scale, y, beta, st); break;
-  case 6: launch_brick<T, 6>(op, x, scale, y, beta, st); break;
-  case 7: launch_brick<T, 7>(op, x, scale, y, beta, st); break;
-  case 8: launch_brick<T, 8>(op, x, scale, y, beta, st); break;
+  case 3: launch_brick<T, 3>(op, x, scale, y, beta, part, st); break;
+  case 4: launch_brick<T, 4>(op, x, scale, y, beta, part, st); break;
+  case 5: launch_brick<T, 5>(op, x, scale, y, beta, part, st); break;
+  case 6: launch_brick<T, 6>(op, x, scale, y, beta, part, st); break;
+  case 7: launch_brick<T, 7>(op, x, scale, y, beta, part, st); break;
+  case 8: launch_brick<T, 8>(op, x, scale, y, beta, part, st); break;
   default: fail("stiffness: degree %d not supported", op->P);
   }
 }
 
-void apply_any(wfx_stiffness* op, const void* x, const void* scale, void* y, int beta, void* stream)
+void apply_any(wfx_stiffness* op, const void* x, const void* scale, void* y, int beta, void* stream, int part = -1)
 {
   if (!op) fail("stiffness operator is NULL");
   if (!x || !y) fail("stiffness: NULL vector");
@@ -1071,9 +1240,9 @@ void apply_any(wfx_stiffness* op, const void* x, const void* scale, void* y, int
   }
   ScopedDevice sd(op->ctx->device);
   if (op->dtype == WFX_F64)
-    dispatch_apply<double>(op, (const double*)x, (const double*)scale, (double*)y, beta, (cudaStream_t)stream);
+    dispatch_apply<double>(op, (const double*)x, (const double*)scale, (double*)y, beta, part, (cudaStream_t)stream);
   else
-    dispatch_apply<float>(op, (const float*)x, (const float*)scale, (float*)y, beta, (cudaStream_t)stream);
+    dispatch_apply<float>(op, (const float*)x, (const float*)scale, (float*)y, beta, part, (cudaStream_t)stream);
 }
 } // namespace
 
@@ -1157,6 +1326,10 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
   if (const char* e = std::getenv("WFX_PDL")) op->use_pdl = std::atoi(e) != 0;
   const LaunchCfg lc = launch_cfg(op->N);
   deriv_1d(op->P, op->Dhost, true);
+  {
+    double pts[WFX_MAXN];
+    gll_points_weights(op->P, pts, op->Whost);
+  }
   if (op->ncells > 0)
   {
     if (!dofmap_host) fail("dofmap is NULL");
@@ -1229,6 +1402,37 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
       op->smem_bytes_reg = (((size_t)op->nloc_pad * 2 * esz + tiles_reg + 15) & ~(size_t)15)
                            + (size_t)bp.rounds_max * lc.W * 6 + 32;
       if (op->variant && op->smem_bytes_reg > ctx->smem_optin) op->variant = 0;
+      op->n_regular = bp.n_regular;
+      op->nbatches = bp.nbatches;
+      // mixed plan: most batches are lattice bricks, some (unstructured patches, batches split for
+      // capacity) are not -- run each kind with its own kernel instead of dropping everything to
+      // the generic one
+      {
+        bool mixed = op->variant == 0 && bp.n_regular > 0 && 2 * bp.n_regular >= bp.nbatches
+                     && op->smem_bytes_reg <= ctx->smem_optin && bp.batch_regular.size() == (size_t)bp.nbatches;
+        if (const char* e = std::getenv("WFX_MIXED")) mixed = mixed && std::atoi(e) != 0;
+        if (const char* e = std::getenv("WFX_REGULAR")) mixed = mixed && std::atoi(e) != 0;
+        if (mixed)
+        {
+          std::vector<int32_t> reg_ids, irr_ids;
+          op->reg_off.assign(1, 0);
+          op->irr_off.assign(1, 0);
+          for (int k = 0; k < bp.ncolours; ++k)
+          {
+            for (int b = bp.colour_off[k]; b < bp.colour_off[k + 1]; ++b)
+              (bp.batch_regular[b] ? reg_ids : irr_ids).push_back(b);
+            op->reg_off.push_back((int32_t)reg_ids.size());
+            op->irr_off.push_back((int32_t)irr_ids.size());
+          }
+          // slack: the cross-CTA prefetch reads the id pf_stride entries ahead (guarded by gridDim)
+          op->d_reg_ids.upload(reg_ids);
+          op->d_irr_ids.upload(irr_ids);
+          op->mixed = true;
+        }
+      }
+      // structured fast path: every cell affine and every batch a lattice brick
+      op->affine = op->variant == 1 && geom->n_affine == op->ncells;
+      if (const char* e = std::getenv("WFX_AFFINE")) op->affine = op->affine && std::atoi(e) != 0;
       // variant 2 reads G in the lane order of its role K: reorder the geometry's columns once
       // (in place; every other consumer honours geom->g_colpos)
       if (op->variant == 2 && geom->g_colpos.empty())
@@ -1263,17 +1467,7 @@ extern "C" int wfx_stiffness_apply_part(wfx_stiffness* op, const void* x, const 
   if (part < -1 || part > 1) fail("part must be -1, 0 or 1");
   if (op->mode == WFX_STIFF_CELL_COLOUR && part >= 0) fail("stiffness: parts need the brick kernel");
   if (op->ncells == 0 && part == 1) return 0;
-  op->cur_part = part;
-  try
-  {
-    apply_any(op, x, scale, y, beta, stream);
-  }
-  catch (...)
-  {
-    op->cur_part = -1;
-    throw;
-  }
-  op->cur_part = -1;
+  apply_any(op, x, scale, y, beta, stream, part);
   WFX_API_END
 }
 
@@ -1335,10 +1529,27 @@ extern "C" int wfx_stiffness_info(wfx_stiffness* op, int64_t* num_cells, int* nu
   // sum-factorised count: 2 x 3 contractions of n MACs per point + symmetric 3x3 apply
   if (flops) *flops = (double)op->ncells * (12.0 * n * n * n * n + 18.0 * n * n * n);
   // algorithmic bytes: symmetric G + int32 dofmap per cell point; x, 1/m, y once
-  if (bytes) *bytes = (double)op->ncells * op->nd * (6 * s + 4) + (double)op->ndofs * 3 * s;
+  // (affine fast path: 6 scalars per CELL and no per-point dofmap)
+  if (bytes)
+    *bytes = op->affine ? (double)op->ncells * 6 * s + (double)op->ndofs * 3 * s
+                        : (double)op->ncells * op->nd * (6 * s + 4) + (double)op->ndofs * 3 * s;
   const int nc = op->mode == WFX_STIFF_CELL_COLOUR ? op->cplan.ncolours : op->ncolours;
   if (ncolours) *ncolours = nc;
   if (nlaunches) *nlaunches = nc;
+  WFX_API_END
+}
+
+extern "C" int wfx_stiffness_kernel_info(wfx_stiffness* op, int* variant, int* affine, int* mixed,
+                                         int* regular_batches, int* batches, int64_t* smem_bytes)
+{
+  WFX_API_BEGIN
+  if (!op) fail("stiffness operator is NULL");
+  if (variant) *variant = op->mode == WFX_STIFF_CELL_COLOUR ? -1 : op->variant;
+  if (affine) *affine = op->affine ? 1 : 0;
+  if (mixed) *mixed = op->mixed ? 1 : 0;
+  if (regular_batches) *regular_batches = op->n_regular;
+  if (batches) *batches = op->nbatches;
+  if (smem_bytes) *smem_bytes = (int64_t)(op->variant ? op->smem_bytes_reg : op->smem_bytes);
   WFX_API_END
 }
 

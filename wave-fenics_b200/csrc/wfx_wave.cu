@@ -192,15 +192,25 @@ extern "C" int wfx_wave_create(wfx_ctx* ctx, wfx_stiffness* stiff, wfx_mass* mas
   w->f0 = f0;
   w->p0 = p0;
   w->dtype = stiffness_dtype(stiff);
+  if (mass_dtype(mass) != w->dtype) fail("wave: mass operator dtype differs from the stiffness operator's");
+  if (bnd && boundary_dtype(bnd) != w->dtype) fail("wave: boundary operator dtype differs from the stiffness operator's");
   if (halo)
   {
-    // m.scatter_rev(add) (LinearGLL.hpp:110) and the same for the facet masses; both idempotent
-    // (they need an fp64 halo: an fp32 model must have assembled them beforehand)
-    if (halo_dtype(halo) == WFX_F64)
+    // every stage exchanges the model's right-hand side through this halo: same scalar type or
+    // the buffers are reinterpreted
+    if (halo_dtype(halo) != w->dtype) fail("wave: halo dtype differs from the model dtype");
+    // m.scatter_rev(add) (LinearGLL.hpp:110) and the same for the facet masses (both idempotent).
+    // They are summed in fp64: an fp64 model's halo serves, an fp32 model must have assembled them
+    // beforehand with a separate fp64 halo (wfx_mass_assemble / wfx_boundary_assemble).
+    if (w->dtype == WFX_F64)
     {
       if (wfx_mass_assemble(mass, halo)) fail("%s", wfx_last_error());
       if (bnd && wfx_boundary_assemble(bnd, halo)) fail("%s", wfx_last_error());
     }
+    if (!mass_assembled(mass))
+      fail("wave: distributed fp32 model needs the mass assembled first (wfx_mass_assemble with an fp64 halo)");
+    if (bnd && !boundary_assembled(bnd))
+      fail("wave: distributed fp32 model needs the facet masses assembled first (wfx_boundary_assemble with an fp64 halo)");
     // highest priority: the small pack / NCCL / unpack kernels must not queue behind the interior batches
     int prio_lo = 0, prio_hi = 0;
     WFX_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -247,6 +257,14 @@ extern "C" int wfx_wave_set_state(wfx_wave* w, const void* u, const void* v)
   ScopedDevice sd(w->ctx->device);
   if (u && w->u_.n) WFX_CUDA(cudaMemcpy(w->u_.p, u, w->u_.n, cudaMemcpyHostToDevice));
   if (v && w->v_.n) WFX_CUDA(cudaMemcpy(w->v_.p, v, w->v_.n, cudaMemcpyHostToDevice));
+  // u->scatter_fwd(), v->scatter_fwd() (LinearGLL.hpp:164,167): the stage kernels update ghost
+  // entries locally from then on, so the copies are made consistent once, here
+  if (w->halo && w->n)
+  {
+    if (u && wfx_halo_update_fwd(w->halo, w->u_.p, nullptr)) fail("%s", wfx_last_error());
+    if (v && wfx_halo_update_fwd(w->halo, w->v_.p, nullptr)) fail("%s", wfx_last_error());
+    WFX_CUDA(cudaDeviceSynchronize());
+  }
   WFX_API_END
 }
 

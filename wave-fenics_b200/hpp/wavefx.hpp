@@ -210,6 +210,8 @@ struct HaloSpec
   std::vector<std::int32_t> recv_ranks;   // source ranks of the forward scatter
   std::vector<std::int32_t> recv_offsets; // scatter_fwd_receive_offsets()
   std::vector<std::int32_t> recv_indices; // size_local + scatter_fwd_ghost_positions()[i]: local ghost slots
+  std::int64_t size_local = 0;            // index_map->size_local()
+  std::int64_t num_ghosts = 0;            // index_map->num_ghosts()
 };
 
 // The NCCL communicator that takes the place of the IndexMap's MPI neighbourhood communicators.
@@ -249,7 +251,7 @@ public:
   VectorUpdater(std::shared_ptr<Comm> comm, const HaloSpec& s) : _comm(std::move(comm))
   {
     check(wfx_halo_create(_comm->context()->get(), _comm->get(), std::is_same<T, double>::value ? WFX_F64 : WFX_F32,
-                          (int)s.send_ranks.size(), s.send_ranks.data(), s.send_offsets.data(), s.send_indices.data(),
+                          s.size_local, s.num_ghosts, (int)s.send_ranks.size(), s.send_ranks.data(), s.send_offsets.data(), s.send_indices.data(),
                           (int)s.recv_ranks.size(), s.recv_ranks.data(), s.recv_offsets.data(), s.recv_indices.data(),
                           &_h));
   }

@@ -99,6 +99,8 @@ HaloSpec make_halo_spec(const IndexMap& map, const std::vector<std::int32_t>& se
   s.recv_offsets.assign(roff.begin(), roff.end());
   const auto& gpos = map.scatter_fwd_ghost_positions();
   const std::int32_t size_local = map.size_local();
+  s.size_local = size_local;
+  s.num_ghosts = map.num_ghosts();
   // ghost i takes entry gpos[i] of the receive buffer (update_fwd_end gathers with these positions,
   // VectorUpdater.hpp:138-142, scatter.cu:5-10); wfx_halo_create wants the inverse: the local slot
   // filled by each receive-buffer entry

@@ -79,8 +79,12 @@ def _vertex_coords(n, lengths, origin, perturb, seed, global_n=None, offset=(0, 
 def cell_h(x, xdofs):
     """dolfinx mesh::h for hexahedra: largest vertex-vertex distance (SURVEY.md App. A.7)."""
     v = x[xdofs]  # [nc, 8, 3]
-    d = v[:, :, None, :] - v[:, None, :, :]
-    return np.sqrt((d * d).sum(-1)).reshape(len(xdofs), -1).max(axis=1)
+    best = np.zeros(len(xdofs))
+    for a in range(8):
+        for b in range(a + 1, 8):
+            d = v[:, a, :] - v[:, b, :]
+            np.maximum(best, np.einsum("ij,ij->i", d, d), out=best)
+    return np.sqrt(best)
 
 
 def create_box_hex(n, P, lengths=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), perturb=0.0, seed=1234,
@@ -115,14 +119,16 @@ def create_box_hex(n, P, lengths=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), pertur
     ndofs = M[0] * M[1] * M[2]
     if ndofs >= 2 ** 31:
         raise ValueError("more than 2^31 dofs on one rank")
-    gid = (((cx[:, None] * P + pa) * M[1] + (cy[:, None] * P + pb)) * M[2] + (cz[:, None] * P + pc))
+    # global lattice id of point t of cell c = id of the cell's origin corner + a per-point offset
+    base = ((cx * P) * M[1] + cy * P) * M[2] + cz * P
+    off = np.empty(nd, dtype=np.int64)
+    off[perm] = (pa * M[1] + pb) * M[2] + pc          # column perm[t] of the dofmap is tensor point t
     global_dofs = np.arange(ndofs, dtype=np.int64)
     if renumber is not None:
         new_of_old = np.random.default_rng(renumber).permutation(ndofs)
-        gid = new_of_old[gid]
-    dofmap = np.empty((nc, nd), dtype=np.int32)
-    dofmap[:, perm] = gid.astype(np.int32)
-    del gid
+        dofmap = new_of_old[base[:, None] + off[None, :]].astype(np.int32)
+    else:
+        dofmap = base.astype(np.int32)[:, None] + off.astype(np.int32)[None, :]
 
     fc, fl, ft = [], [], []
     # local facet on the low / high side of each axis

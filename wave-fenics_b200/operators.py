@@ -64,6 +64,18 @@ class Geometry:
                   V.ncells, x.shape[0], capi.f64p(x.reshape(-1)), capi.i32p(xd.reshape(-1)),
                   C.byref(self.handle))
 
+    def info(self):
+        nc, na = C.c_int64(), C.c_int64()
+        capi.call("wfx_geometry_info", self.handle, C.byref(nc), C.byref(na))
+        return dict(ncells=nc.value, n_affine=na.value)
+
+    def scale_cells(self, coeff):
+        """G[c] *= coeff[c]: a piecewise-constant coefficient, e.g. (c0[c] / c0_ref)^2."""
+        coeff = np.ascontiguousarray(coeff, dtype=np.float64)
+        if coeff.size != self.ncells:
+            raise capi.WfxError("one coefficient per cell expected")
+        capi.call("wfx_geometry_scale_cells", self.handle, capi.f64p(coeff))
+
     def get(self):
         """(G [ncells,nq,3,3], detJ [ncells,nq]) in the reference layout."""
         nq = (self.P + 1) ** 3
@@ -183,6 +195,14 @@ class StiffnessOperator(_Operator):
         return dict(num_cells=nc.value, num_dofs=nd.value, ndofs=ndofs.value, flops=fl.value,
                     bytes=by.value, ncolours=ncol.value, nlaunches=nl.value)
 
+    def kernel_info(self):
+        v, a, m, nr, nb, sm = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+        capi.call("wfx_stiffness_kernel_info", self.handle, C.byref(v), C.byref(a), C.byref(m), C.byref(nr),
+                  C.byref(nb), C.byref(sm))
+        names = {-1: "cell", 0: "brick-generic", 1: "brick-regular", 2: "brick-regular-p4d"}
+        return dict(variant=names.get(v.value, str(v.value)), affine=bool(a.value), mixed=bool(m.value),
+                    regular_batches=nr.value, batches=nb.value, smem_bytes=sm.value)
+
     def __del__(self):
         if getattr(self, "handle", None) and getattr(capi, "lib", None) is not None:
             capi.lib.wfx_stiffness_destroy(self.handle)
@@ -280,6 +300,10 @@ class BoundaryOperator(_Operator):
         capi.call("wfx_boundary_apply", self.handle, float(c0), float(g), C.c_void_p(vn.data_ptr()),
                   C.c_void_p(b.data_ptr()), _stream_ptr())
 
+    def assemble(self, halo):
+        """Distributed meshes: sum the facet masses over the ranks sharing a boundary dof (fp64 halo)."""
+        capi.call("wfx_boundary_assemble", self.handle, halo.handle)
+
     def facet_masses(self):
         m1, m2 = np.empty(self.ndofs), np.empty(self.ndofs)
         capi.call("wfx_boundary_get", self.handle, capi.f64p(m1), capi.f64p(m2))
@@ -298,7 +322,8 @@ class LinearGLLOpt:
     overrides them)."""
 
     def __init__(self, mesh, meshtags, degreeOfBasis, speedOfSound, sourceFrequency,
-                 pressureAmplitude, dtype=np.float64, ctx=None, halo=None, stiffness_mode=capi.STIFF_AUTO):
+                 pressureAmplitude, dtype=np.float64, ctx=None, halo=None, stiffness_mode=capi.STIFF_AUTO,
+                 setup_halo=None):
         self.ctx = ctx or Context.get()
         self.V = mesh
         if meshtags is not None:
@@ -316,7 +341,17 @@ class LinearGLLOpt:
         self.bnd_op = BoundaryOperator(mesh, self.k_, dtype, self.ctx)                   # :113-115
         self.halo = halo
         if halo is not None:
-            self.mass_op.assemble(halo)                                                  # :110
+            # the masses are summed over the ranks in fp64: an fp32 model needs a second, fp64 halo
+            # for this one-off set-up step (`setup_halo`, built here on the same mesh if not given)
+            if setup_halo is None:
+                if self.dtype == np.float64:
+                    setup_halo = halo
+                else:
+                    from .partition import Halo
+                    setup_halo = Halo(mesh, self.ctx, np.float64, comm=halo.comm)
+            self.setup_halo = setup_halo
+            self.mass_op.assemble(setup_halo)                                            # :110
+            self.bnd_op.assemble(setup_halo)
         self.handle = C.c_void_p()
         capi.call("wfx_wave_create", self.ctx.handle, self.stiff_op.handle, self.mass_op.handle,
                   self.bnd_op.handle, halo.handle if halo is not None else None, int(mesh.size_local),
@@ -349,7 +384,7 @@ class LinearGLLOpt:
     def rk4(self, startTime, finalTime, timeStep, max_steps=0, stream=None):
         steps, t_end = C.c_int64(), C.c_double()
         capi.call("wfx_wave_rk4", self.handle, float(startTime), float(finalTime), float(timeStep),
-                  int(max_steps), C.byref(steps), C.byref(t_end), stream)
+                  int(max_steps), C.byref(steps), C.byref(t_end), stream if stream is not None else _stream_ptr())
         return steps.value, t_end.value
 
     def __del__(self):

@@ -95,9 +95,12 @@ def create_box_hex_partition(gshape, P, lengths, grid, rank, origin=(0.0, 0.0, 0
     pos = lattice_pos(P)
     ta, tb, tc = np.meshgrid(np.arange(np1), np.arange(np1), np.arange(np1), indexing="ij")
     pa, pb, pc = pos[ta.reshape(-1)], pos[tb.reshape(-1)], pos[tc.reshape(-1)]
-    lat = ((cx[:, None] * P + pa) * M[1] + (cy[:, None] * P + pb)) * M[2] + (cz[:, None] * P + pc)
-    dofmap = np.empty((nc, nd), dtype=np.int32)
-    dofmap[:, perm] = local_of_lattice[lat].astype(np.int32)
+    # lattice index of point t of cell c = index of the cell's origin corner + a per-point offset
+    base = ((cx * P) * M[1] + cy * P) * M[2] + cz * P
+    off = np.empty(nd, dtype=np.int64)
+    off[perm] = (pa * M[1] + pb) * M[2] + pc          # column perm[t] of the dofmap is tensor point t
+    lut = local_of_lattice.astype(np.int32)
+    dofmap = lut[base[:, None] + off[None, :]]
 
     # boundary facets: only where this block touches the global boundary
     fc, fl, ft = [], [], []
@@ -157,24 +160,36 @@ class Halo:
     """NCCL ghost update for vectors on this partition (wfx_halo_*).  `group` is the
     torch.distributed process group used once to hand out the NCCL unique id."""
 
-    def __init__(self, mesh, ctx, dtype=np.float64, group=None):
+    def __init__(self, mesh, ctx, dtype=np.float64, group=None, comm=None):
+        """comm: the wfx_comm handle of another Halo on the same ranks (shared, not owned)."""
         import torch.distributed as dist
         self.ctx = ctx
-        rank, world = dist.get_rank(group), dist.get_world_size(group)
-        uid = [None]
-        if rank == 0:
-            buf = C.create_string_buffer(128)
-            capi.call("wfx_comm_unique_id", buf)
-            uid = [buf.raw]
-        dist.broadcast_object_list(uid, src=0, group=group)
-        self.comm = C.c_void_p()
-        capi.call("wfx_comm_create", ctx.handle, uid[0], world, rank, C.byref(self.comm))
+        self.owns_comm = comm is None
+        if comm is None:
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+            uid = [None]
+            if rank == 0:
+                buf = C.create_string_buffer(128)
+                capi.call("wfx_comm_unique_id", buf)
+                uid = [buf.raw]
+            dist.broadcast_object_list(uid, src=0, group=group)
+            comm = C.c_void_p()
+            capi.call("wfx_comm_create", ctx.handle, uid[0], world, rank, C.byref(comm))
+        self.comm = comm
         h = mesh.halo
         self.handle = C.c_void_p()
         capi.call("wfx_halo_create", ctx.handle, self.comm, capi.dtype_code(dtype),
+                  int(mesh.size_local), int(mesh.ndofs - mesh.size_local),
                   len(h["send_ranks"]), capi.i32p(h["send_ranks"]), capi.i32p(h["send_offsets"]),
                   capi.i32p(h["send_indices"]), len(h["recv_ranks"]), capi.i32p(h["recv_ranks"]),
                   capi.i32p(h["recv_offsets"]), capi.i32p(h["recv_indices"]), C.byref(self.handle))
+
+    @property
+    def transport(self):
+        """'p2p' (NVLink peer memory, one fused kernel) or 'nccl' for the fused ghost reduction"""
+        t = C.c_int()
+        capi.call("wfx_halo_transport", self.handle, C.byref(t))
+        return "p2p" if t.value else "nccl"
 
     def _run(self, name, x):
         import torch
@@ -199,7 +214,8 @@ class Halo:
     def __del__(self):
         if getattr(self, "handle", None) and getattr(capi, "lib", None) is not None:
             capi.lib.wfx_halo_destroy(self.handle)
-            capi.lib.wfx_comm_destroy(self.comm)
+            if self.owns_comm:
+                capi.lib.wfx_comm_destroy(self.comm)
             self.handle = None
 
 
