@@ -301,6 +301,22 @@ int wfx_wave_f1(wfx_wave* wave, double t, const void* u_dev, const void* v_dev, 
  * Returns steps taken and the final time. */
 int wfx_wave_rk4(wfx_wave* wave, double t0, double tf, double dt, int64_t max_steps,
                  int64_t* steps, double* t_end, void* stream);
+/* ---- solution output (the reference has none: it prints the solve time only,
+ * demo/cpu_planar3d/main.cpp:87-93) ------------------------------------------------------------
+ * Probes: after every completed time step the values u[dofs] are appended to a series kept on the
+ * device (at most max_records steps; later steps are not recorded).  get_probe_series copies the
+ * recorded times (the t reached after each step) and values [nrecords][nprobes] (model dtype) to the
+ * host; either pointer may be NULL.  init / set_state start a new series. */
+int wfx_wave_set_probes(wfx_wave* wave, int64_t nprobes, const int32_t* dofs_host, int64_t max_records);
+int wfx_wave_get_probe_series(wfx_wave* wave, int64_t* nrecords, double* t_host, void* values_host);
+/* Snapshots / checkpoints: every `every` completed steps (counted since init / set_state) u and v are
+ * copied device -> device on the stepping stream and device -> pinned host on a separate copy stream
+ * while the time stepping continues; `fn` then receives host pointers valid for the duration of the
+ * call (step number, time reached, u, v in the model dtype, ndofs entries each).  It runs on the
+ * thread that called wfx_wave_rk4, at the next snapshot or before rk4 returns.  A checkpoint is a
+ * snapshot fed back through wfx_wave_set_state.  every = 0 or fn = NULL switches snapshots off. */
+typedef void (*wfx_snapshot_fn)(void* user, int64_t step, double t, const void* u_host, const void* v_host);
+int wfx_wave_set_snapshot(wfx_wave* wave, int64_t every, wfx_snapshot_fn fn, void* user);
 int wfx_wave_destroy(wfx_wave* wave);
 
 #ifdef __cplusplus

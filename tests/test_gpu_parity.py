@@ -630,3 +630,51 @@ def test_right_hand_sides_f0_f1(wfx, orc, torch):
     assert torch.equal(res, vd)
     with pytest.raises(RuntimeError):
         eqn.f1(0.0, ud, vd, ud)
+
+
+# ---- f3: probes and snapshots ------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_probe_series_and_snapshots_match_oracle(wfx, orc, torch):
+    """Probe time series and periodic snapshots of the GPU run against the oracle stepped one time
+    step at a time; a snapshot fed back through set_state resumes the run bit for bit."""
+    P, c0, f0, p0 = 4, 1500.0, 0.5e6, 6e4
+    mesh = wfx.create_box_hex((6, 3, 3), P, (L * 6 / 8, L * 3 / 8, L * 3 / 8), perturb=0.1)
+    Go, detJ = orc.precompute_geometric_data(mesh, P)
+    m = np.zeros(mesh.ndofs)
+    orc.mass_apply(mesh, P, detJ, np.ones(mesh.ndofs), m)
+    m1, m2 = orc.boundary_facet_mass(mesh, P)
+    dt = wfx.cfl_timestep(mesh.h_min, c0, P, f0)
+    nsteps, every = 24, 8
+    probes = np.array([0, 17, mesh.ndofs // 2, mesh.ndofs - 1], dtype=np.int32)
+    uo, vo = np.zeros(mesh.ndofs), np.zeros(mesh.ndofs)
+    t, series, times, snaps_o = 0.0, [], [], {}
+    for k in range(nsteps):
+        s1, t = orc.rk4(mesh, P, Go, m, m1, m2, c0, f0, p0, t, 1.0, dt, uo, vo, max_steps=1, sumfact=True)
+        assert s1 == 1
+        series.append(uo[probes].copy())
+        times.append(t)
+        if (k + 1) % every == 0:
+            snaps_o[k + 1] = (uo.copy(), vo.copy())
+    eqn = wfx.LinearGLLOpt(mesh, None, P, c0, f0, p0)
+    eqn.init()
+    eqn.set_probes(probes, max_records=nsteps + 5)
+    snaps = {}
+    eqn.set_snapshot(every, lambda step, tt, u, v: snaps.__setitem__(step, (tt, u.copy(), v.copy())))
+    s, t_end = eqn.rk4(0.0, 1.0, dt, max_steps=10)
+    s2, t_end = eqn.rk4(t_end, 1.0, dt, max_steps=nsteps - 10)      # the series continues across calls
+    assert s + s2 == nsteps
+    tt, vals = eqn.probe_series()
+    assert vals.shape == (nsteps, len(probes)) and np.allclose(tt, times, rtol=1e-15, atol=0)
+    scale = np.abs(np.array(series)).max()
+    assert scale > 0 and np.abs(vals - np.array(series)).max() < 1e-11 * scale
+    assert sorted(snaps) == sorted(snaps_o)
+    for k in snaps:
+        assert snaps[k][0] == times[k - 1]
+        assert rel_l2(snaps[k][1], snaps_o[k][0]) < TOL64 and rel_l2(snaps[k][2], snaps_o[k][1]) < TOL64
+    # restart from the snapshot at step 16: same final state as the uninterrupted run, bitwise
+    u_end, v_end = eqn.get_state()
+    eqn2 = wfx.LinearGLLOpt(mesh, None, P, c0, f0, p0)
+    eqn2.set_state(snaps[16][1], snaps[16][2])
+    eqn2.rk4(snaps[16][0], 1.0, dt, max_steps=nsteps - 16)
+    u2, v2 = eqn2.get_state()
+    assert np.array_equal(u2, u_end) and np.array_equal(v2, v_end)

@@ -25,6 +25,9 @@ class WfxError(RuntimeError):
     pass
 
 
+SNAPSHOT_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p)
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise WfxError(
@@ -107,6 +110,9 @@ _SIG = {
     "wfx_wave_f0": [_vp, C.c_double, _vp, _vp, _vp, _vp],
     "wfx_wave_f1": [_vp, C.c_double, _vp, _vp, _vp, _vp],
     "wfx_wave_rk4": [_vp, C.c_double, C.c_double, C.c_double, C.c_int64, _c_i64p, _c_f64p, _vp],
+    "wfx_wave_set_probes": [_vp, C.c_int64, _c_i32p, C.c_int64],
+    "wfx_wave_get_probe_series": [_vp, _c_i64p, _c_f64p, _vp],
+    "wfx_wave_set_snapshot": [_vp, C.c_int64, _vp, _vp],
     "wfx_wave_destroy": [_vp],
     # debug helper (not in wavefx.h): host-only plan construction + verification
     "wfx_debug_plan_stats": [C.c_int, C.c_int64, C.c_int64, _c_i32p, C.POINTER(C.c_float), C.c_int,

@@ -1,7 +1,12 @@
 // Device context and raw buffers of the C ABI.
 #include "wfx_internal.h"
 
+#include <nvtx3/nvToolsExt.h>
+
 using namespace wfx;
+
+wfx::NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+wfx::NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 extern "C" int wfx_ctx_create(int device, wfx_ctx** out)
 {

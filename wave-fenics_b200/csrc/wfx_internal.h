@@ -112,6 +112,15 @@ int boundary_dtype(const struct ::wfx_boundary* op);
 void boundary_apply_dev(struct ::wfx_boundary* op, double c0, const double* g_dev, const void* vn, void* b,
                         cudaStream_t stream);
 
+// NVTX ranges around the phases of a time step (the reference marks its profiled regions the same
+// way: demo/gpu_scatter_mpi/main.cpp:101-121, demo/gpu_cg/CUDA/cg.hpp:74-113).  nvtx3 is header-only
+// and costs a few nanoseconds when no tool is attached.
+struct NvtxRange
+{
+  explicit NvtxRange(const char* name);
+  ~NvtxRange();
+};
+
 struct ScopedDevice
 {
   int prev = -1;

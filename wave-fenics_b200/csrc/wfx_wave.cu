@@ -40,8 +40,34 @@ struct wfx_wave
   DevBuf<double> g_dev;
   cudaStream_t own_stream = nullptr; // capture needs a non-legacy stream
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // time-stepping position (reset by init / set_state): steps completed and the time reached
+  int64_t steps_done = 0;
+  double t_now = 0;
+  // probes: u at selected dofs after every completed step, kept on the device until asked for
+  int64_t nprobes = 0, probe_cap = 0, probe_rec = 0;
+  DevBuf<int32_t> d_probe_idx;
+  DevBuf<unsigned char> d_probe_val;
+  std::vector<double> probe_t;
+  // snapshots: every `snap_every` steps u, v are copied device -> device on the work stream, then
+  // device -> pinned host on a copy stream while the time stepping goes on; the callback runs on the
+  // calling thread once the copy has landed (at the next snapshot or at the end of rk4)
+  int64_t snap_every = 0;
+  wfx_snapshot_fn snap_fn = nullptr;
+  void* snap_user = nullptr;
+  DevBuf<unsigned char> snap_u, snap_v;
+  void *snap_hu = nullptr, *snap_hv = nullptr; // pinned
+  cudaStream_t snap_stream = nullptr;
+  cudaEvent_t ev_snap_ready = nullptr, ev_snap_done = nullptr;
+  bool snap_pending = false;
+  int64_t snap_step = 0;
+  double snap_t = 0;
   ~wfx_wave()
   {
+    if (snap_hu) cudaFreeHost(snap_hu);
+    if (snap_hv) cudaFreeHost(snap_hv);
+    if (snap_stream) cudaStreamDestroy(snap_stream);
+    if (ev_snap_ready) cudaEventDestroy(ev_snap_ready);
+    if (ev_snap_done) cudaEventDestroy(ev_snap_done);
     if (step_graph) cudaGraphExecDestroy(step_graph);
     if (own_stream) cudaStreamDestroy(own_stream);
     if (ev_in) cudaEventDestroy(ev_in);
@@ -115,6 +141,56 @@ void launch_stage(int stage, int64_t n, const void* b, const void* minv, void* u
 #undef WFX_STAGE
   WFX_CUDA(cudaGetLastError());
 }
+template <typename T>
+__global__ void probe_kernel(int64_t n, const int32_t* __restrict__ idx, const T* __restrict__ u, T* __restrict__ out)
+{
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = u[idx[i]];
+}
+
+// the pending snapshot's copy has landed: hand it to the callback
+void flush_snapshot(wfx_wave* w)
+{
+  if (!w->snap_pending) return;
+  WFX_CUDA(cudaEventSynchronize(w->ev_snap_done));
+  w->snap_pending = false;
+  if (w->snap_fn) w->snap_fn(w->snap_user, w->snap_step, w->snap_t, w->snap_hu, w->snap_hv);
+}
+
+// after a completed step: probe record and, every snap_every steps, a snapshot
+void after_step(wfx_wave* w, cudaStream_t ws)
+{
+  const size_t esz = w->dtype == WFX_F64 ? 8 : 4;
+  if (w->nprobes && w->probe_rec < w->probe_cap)
+  {
+    const unsigned grid = (unsigned)((w->nprobes + 255) / 256);
+    unsigned char* out = w->d_probe_val.p + (size_t)w->probe_rec * w->nprobes * esz;
+    if (w->dtype == WFX_F64)
+      probe_kernel<double><<<grid, 256, 0, ws>>>(w->nprobes, w->d_probe_idx.p, (const double*)w->u_.p, (double*)out);
+    else
+      probe_kernel<float><<<grid, 256, 0, ws>>>(w->nprobes, w->d_probe_idx.p, (const float*)w->u_.p, (float*)out);
+    WFX_CUDA(cudaGetLastError());
+    w->probe_t.push_back(w->t_now);
+    w->probe_rec += 1;
+  }
+  if (w->snap_every > 0 && w->steps_done % w->snap_every == 0)
+  {
+    flush_snapshot(w); // the staging buffers are free again (usually long since)
+    const size_t nb = (size_t)w->n * esz;
+    WFX_CUDA(cudaMemcpyAsync(w->snap_u.p, w->u_.p, nb, cudaMemcpyDeviceToDevice, ws));
+    WFX_CUDA(cudaMemcpyAsync(w->snap_v.p, w->v_.p, nb, cudaMemcpyDeviceToDevice, ws));
+    WFX_CUDA(cudaEventRecord(w->ev_snap_ready, ws));
+    WFX_CUDA(cudaStreamWaitEvent(w->snap_stream, w->ev_snap_ready, 0));
+    WFX_CUDA(cudaMemcpyAsync(w->snap_hu, w->snap_u.p, nb, cudaMemcpyDeviceToHost, w->snap_stream));
+    WFX_CUDA(cudaMemcpyAsync(w->snap_hv, w->snap_v.p, nb, cudaMemcpyDeviceToHost, w->snap_stream));
+    WFX_CUDA(cudaEventRecord(w->ev_snap_done, w->snap_stream));
+    // the next snapshot's device copy must not overtake this one's read: ws waits for it then
+    w->snap_pending = true;
+    w->snap_step = w->steps_done;
+    w->snap_t = w->t_now;
+  }
+}
+
 __global__ void set_source_kernel(double* g_dev, double g0, double g1, double g2, double g3)
 {
   g_dev[0] = g0, g_dev[1] = g1, g_dev[2] = g2, g_dev[3] = g3;
@@ -132,15 +208,20 @@ void enqueue_step(wfx_wave* w, double dt, const double* g, bool g_from_dev, cuda
     if (g_from_dev) boundary_apply_dev(w->bnd, w->c0, w->g_dev.p + i, vn, w->b.p, st);
     else if (wfx_boundary_apply(w->bnd, w->c0, g[i], vn, w->b.p, st)) fail("%s", wfx_last_error()); // :175
   };
+  static const char* const stage_name[4] = {"wfx rk4 stage 0", "wfx rk4 stage 1", "wfx rk4 stage 2", "wfx rk4 stage 3"};
   for (int i = 0; i < 4; ++i)
   {
+    NvtxRange stage_range(stage_name[i]);
     // stage state: the solution itself at stage 0 (a_0 = 0), else un/vn
     const void* un = i == 0 ? w->u_.p : w->un.p;
     const void* vn = i == 0 ? w->v_.p : w->vn.p;
     // f1 (:151-192)
     if (!w->halo)
     {
-      if (wfx_stiffness_apply(w->stiff, un, w->b.p, 0, st)) fail("%s", wfx_last_error()); // :173-174
+      {
+        NvtxRange r("wfx stiffness apply");
+        if (wfx_stiffness_apply(w->stiff, un, w->b.p, 0, st)) fail("%s", wfx_last_error()); // :173-174
+      }
       boundary(i, vn);
     }
     else
@@ -151,15 +232,25 @@ void enqueue_step(wfx_wave* w, double dt, const double* g, bool g_from_dev, cuda
       // every copy of a dof after the reduction.
       static const bool overlap = [] { const char* e = std::getenv("WFX_WAVE_OVERLAP"); return !e || std::atoi(e) != 0; }();
       const bool split = overlap && stiffness_has_split(w->stiff);
-      if (wfx_stiffness_apply_part(w->stiff, un, nullptr, w->b.p, 0, split ? 0 : -1, st)) fail("%s", wfx_last_error());
+      {
+        NvtxRange r("wfx stiffness interface part");
+        if (wfx_stiffness_apply_part(w->stiff, un, nullptr, w->b.p, 0, split ? 0 : -1, st)) fail("%s", wfx_last_error());
+      }
       WFX_CUDA(cudaEventRecord(w->ev_iface, st));
       WFX_CUDA(cudaStreamWaitEvent(w->comm_stream, w->ev_iface, 0));
-      if (wfx_halo_update_rev_fwd(w->halo, w->b.p, w->comm_stream)) fail("%s", wfx_last_error());
+      {
+        NvtxRange r("wfx ghost reduction");
+        if (wfx_halo_update_rev_fwd(w->halo, w->b.p, w->comm_stream)) fail("%s", wfx_last_error());
+      }
       WFX_CUDA(cudaEventRecord(w->ev_halo, w->comm_stream));
-      if (split && wfx_stiffness_apply_part(w->stiff, un, nullptr, w->b.p, 0, 1, st)) fail("%s", wfx_last_error());
+      {
+        NvtxRange r("wfx stiffness interior part");
+        if (split && wfx_stiffness_apply_part(w->stiff, un, nullptr, w->b.p, 0, 1, st)) fail("%s", wfx_last_error());
+      }
       WFX_CUDA(cudaStreamWaitEvent(st, w->ev_halo, 0));
       boundary(i, vn);
     }
+    NvtxRange update_range("wfx fused stage update");
     if (w->dtype == WFX_F64)
       launch_stage<double>(i, w->n, w->b.p, w->minv, w->u_.p, w->v_.p, w->u0.p, w->v0.p, w->un.p,
                            w->vn.p, dt * b_runge[i], dt * a_runge[i + 1], st);
@@ -247,6 +338,10 @@ extern "C" int wfx_wave_init(wfx_wave* w)
     WFX_CUDA(cudaMemset(w->u_.p, 0, w->u_.n));
     WFX_CUDA(cudaMemset(w->v_.p, 0, w->v_.n));
   }
+  w->steps_done = 0;
+  w->t_now = 0;
+  w->probe_rec = 0;
+  w->probe_t.clear();
   WFX_API_END
 }
 
@@ -257,6 +352,10 @@ extern "C" int wfx_wave_set_state(wfx_wave* w, const void* u, const void* v)
   ScopedDevice sd(w->ctx->device);
   if (u && w->u_.n) WFX_CUDA(cudaMemcpy(w->u_.p, u, w->u_.n, cudaMemcpyHostToDevice));
   if (v && w->v_.n) WFX_CUDA(cudaMemcpy(w->v_.p, v, w->v_.n, cudaMemcpyHostToDevice));
+  w->steps_done = 0;
+  w->t_now = 0;
+  w->probe_rec = 0;
+  w->probe_t.clear();
   // u->scatter_fwd(), v->scatter_fwd() (LinearGLL.hpp:164,167): the stage kernels update ghost
   // entries locally from then on, so the copies are made consistent once, here
   if (w->halo && w->n)
@@ -350,6 +449,7 @@ extern "C" int wfx_wave_rk4(wfx_wave* w, double t0, double tf, double dt, int64_
   while (t < tf) // :241
   {
     if (max_steps > 0 && step >= max_steps) break;
+    NvtxRange step_range("wfx rk4 step");
     dt = std::min(dt, tf - t); // :242
     double g[4];
     for (int i = 0; i < 4; ++i)
@@ -387,6 +487,19 @@ extern "C" int wfx_wave_rk4(wfx_wave* w, double t0, double tf, double dt, int64_
     else enqueue_step(w, dt, g, false, ws);
     t += dt;
     step += 1;
+    w->steps_done += 1;
+    w->t_now = t;
+    if (w->nprobes || w->snap_every > 0)
+    {
+      if (w->snap_pending && w->snap_every > 0 && (w->steps_done % w->snap_every) == 0)
+        WFX_CUDA(cudaStreamWaitEvent(ws, w->ev_snap_done, 0));
+      after_step(w, ws);
+    }
+  }
+  if (w->snap_pending)
+  {
+    // deliver the last snapshot before returning (the callback may read solver state)
+    flush_snapshot(w);
   }
   if (ws != st)
   {
@@ -395,6 +508,67 @@ extern "C" int wfx_wave_rk4(wfx_wave* w, double t0, double tf, double dt, int64_
   }
   if (steps_out) *steps_out = step;
   if (t_end) *t_end = t;
+  WFX_API_END
+}
+
+extern "C" int wfx_wave_set_probes(wfx_wave* w, int64_t nprobes, const int32_t* dofs_host, int64_t max_records)
+{
+  WFX_API_BEGIN
+  if (!w) fail("wave model is NULL");
+  if (nprobes < 0 || max_records < 0 || (nprobes > 0 && !dofs_host)) fail("bad probe list");
+  for (int64_t i = 0; i < nprobes; ++i)
+    if (dofs_host[i] < 0 || dofs_host[i] >= w->n) fail("probe dof %d out of range", dofs_host[i]);
+  ScopedDevice sd(w->ctx->device);
+  w->nprobes = nprobes;
+  w->probe_cap = nprobes ? max_records : 0;
+  w->probe_rec = 0;
+  w->probe_t.clear();
+  if (nprobes)
+  {
+    w->d_probe_idx.upload(dofs_host, (size_t)nprobes);
+    w->d_probe_val.alloc((size_t)nprobes * (size_t)max_records * (w->dtype == WFX_F64 ? 8 : 4));
+  }
+  WFX_API_END
+}
+
+extern "C" int wfx_wave_get_probe_series(wfx_wave* w, int64_t* nrecords, double* t_host, void* values_host)
+{
+  WFX_API_BEGIN
+  if (!w) fail("wave model is NULL");
+  ScopedDevice sd(w->ctx->device);
+  if (nrecords) *nrecords = w->probe_rec;
+  if (t_host)
+    for (int64_t r = 0; r < w->probe_rec; ++r) t_host[r] = w->probe_t[r];
+  if (values_host && w->probe_rec)
+  {
+    WFX_CUDA(cudaDeviceSynchronize());
+    WFX_CUDA(cudaMemcpy(values_host, w->d_probe_val.p,
+                        (size_t)w->probe_rec * w->nprobes * (w->dtype == WFX_F64 ? 8 : 4), cudaMemcpyDeviceToHost));
+  }
+  WFX_API_END
+}
+
+extern "C" int wfx_wave_set_snapshot(wfx_wave* w, int64_t every, wfx_snapshot_fn fn, void* user)
+{
+  WFX_API_BEGIN
+  if (!w) fail("wave model is NULL");
+  if (every < 0) fail("snapshot interval must not be negative");
+  ScopedDevice sd(w->ctx->device);
+  flush_snapshot(w);
+  w->snap_every = fn ? every : 0;
+  w->snap_fn = fn;
+  w->snap_user = user;
+  if (w->snap_every > 0 && !w->snap_stream)
+  {
+    const size_t nb = (size_t)w->n * (w->dtype == WFX_F64 ? 8 : 4);
+    w->snap_u.alloc(nb);
+    w->snap_v.alloc(nb);
+    WFX_CUDA(cudaMallocHost(&w->snap_hu, nb ? nb : 1));
+    WFX_CUDA(cudaMallocHost(&w->snap_hv, nb ? nb : 1));
+    WFX_CUDA(cudaStreamCreateWithFlags(&w->snap_stream, cudaStreamNonBlocking));
+    WFX_CUDA(cudaEventCreateWithFlags(&w->ev_snap_ready, cudaEventDisableTiming));
+    WFX_CUDA(cudaEventCreateWithFlags(&w->ev_snap_done, cudaEventDisableTiming));
+  }
   WFX_API_END
 }
 

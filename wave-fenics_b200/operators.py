@@ -371,6 +371,39 @@ class LinearGLLOpt:
         capi.call("wfx_wave_get_state", self.handle, C.c_void_p(u.ctypes.data), C.c_void_p(v.ctypes.data))
         return u, v
 
+    def set_probes(self, dofs, max_records):
+        """Record u[dofs] after every completed time step (kept on the device, up to max_records)."""
+        dofs = np.ascontiguousarray(dofs, dtype=np.int32)
+        self._nprobes = len(dofs)
+        capi.call("wfx_wave_set_probes", self.handle, len(dofs), capi.i32p(dofs), int(max_records))
+
+    def probe_series(self):
+        """(t [nrec], u [nrec, nprobes]) recorded so far."""
+        n = C.c_int64()
+        capi.call("wfx_wave_get_probe_series", self.handle, C.byref(n), None, None)
+        t = np.empty(n.value)
+        vals = np.empty((n.value, getattr(self, "_nprobes", 0)), dtype=self.dtype)
+        capi.call("wfx_wave_get_probe_series", self.handle, C.byref(n), capi.f64p(t), C.c_void_p(vals.ctypes.data))
+        return t, vals
+
+    def set_snapshot(self, every, fn):
+        """fn(step, t, u, v) with numpy views of the pinned host copies (copy them to keep them), every
+        `every` completed steps; the device -> host copy overlaps the time stepping."""
+        if fn is None or not every:
+            self._snap_cb = None
+            capi.call("wfx_wave_set_snapshot", self.handle, 0, None, None)
+            return
+        n, dt = self.ndofs, self.dtype
+
+        def tramp(_user, step, t, up, vp):
+            ctype = C.c_double if dt == np.float64 else C.c_float
+            u = np.ctypeslib.as_array(C.cast(up, C.POINTER(ctype)), shape=(n,))
+            v = np.ctypeslib.as_array(C.cast(vp, C.POINTER(ctype)), shape=(n,))
+            fn(int(step), float(t), u, v)
+
+        self._snap_cb = capi.SNAPSHOT_FN(tramp)  # keep the trampoline alive
+        capi.call("wfx_wave_set_snapshot", self.handle, int(every), C.cast(self._snap_cb, C.c_void_p), None)
+
     def f0(self, t, u, v, result):
         """result = v (LinearGLL.hpp:141-144); device tensors."""
         capi.call("wfx_wave_f0", self.handle, float(t), C.c_void_p(u.data_ptr()), C.c_void_p(v.data_ptr()),
