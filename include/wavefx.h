@@ -169,6 +169,13 @@ int wfx_stiffness_apply_host(wfx_stiffness* op, const void* x_host, void* y_host
  * arrays (pinned or pageable); H2D copy of x, fused apply, D2H copy of y.  Synchronous. */
 int wfx_stiffness_mass_apply_host(wfx_stiffness* op, wfx_mass* mass, const void* x_host,
                                   void* y_host);
+/* The same for nvec host vectors (several right-hand sides, or one vector per time step of a
+ * host-driven loop): y_i = M^-1 (-c0^2 K x_i).  Copy-in, apply and copy-out of consecutive vectors are
+ * pipelined on three streams with two device buffer pairs, so that in the steady state a vector costs
+ * max(H2D, D2H) instead of H2D + apply + D2H.  Use pinned host memory, or the copies serialise.
+ * Synchronous: returns when every y_i is complete. */
+int wfx_stiffness_mass_apply_host_batch(wfx_stiffness* op, wfx_mass* mass, int nvec,
+                                        const void* const* x_hosts, void* const* y_hosts);
 /* num_cells / num_dofs / num_quads / flops as on the GPU operator classes
  * (common/cuda/mass.hpp:68-71); bytes = algorithmic bytes per apply. */
 int wfx_stiffness_info(wfx_stiffness* op, int64_t* num_cells, int* num_dofs_per_cell,

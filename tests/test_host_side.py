@@ -197,3 +197,34 @@ def test_brick_plan_invariants_on_random_connectivity(wfx):
         assert s["untouched"] == ndofs - len(np.unique(dofmap))
 
     run()
+
+
+def test_structured_coordinates_from_connectivity(wfx):
+    """The planner's integer cell coordinates come from the mesh connectivity, not the geometry:
+    exact for any cell order, independent of shear / grading; rejected for meshes that are not one
+    consistently oriented block."""
+    capi = wfx.capi
+    mesh = wfx.create_box_hex((5, 3, 4), 2, (1.0, 0.2, 3.0), perturb=0.2)
+    ok, ijk = capi.debug_structured_coords(mesh.xdofs, mesh.x.shape[0])
+    cx, cy, cz = np.meshgrid(np.arange(5), np.arange(3), np.arange(4), indexing="ij")
+    want = np.stack([cx.reshape(-1), cy.reshape(-1), cz.reshape(-1)], axis=-1)
+    assert ok and np.array_equal(ijk, want)
+    # any cell order
+    perm = np.random.default_rng(0).permutation(mesh.ncells)
+    ok, ijk = capi.debug_structured_coords(mesh.xdofs[perm], mesh.x.shape[0])
+    assert ok and np.array_equal(ijk, want[perm])
+    # a cell with mirrored local vertex order: not a consistently oriented block
+    bad = mesh.xdofs.copy()
+    bad[7] = bad[7][[1, 0, 3, 2, 5, 4, 7, 6]]
+    ok, _ = capi.debug_structured_coords(bad, mesh.x.shape[0])
+    assert not ok
+    # two disconnected blocks
+    two = np.concatenate([mesh.xdofs, mesh.xdofs + mesh.x.shape[0]])
+    ok, _ = capi.debug_structured_coords(two, 2 * mesh.x.shape[0])
+    assert not ok
+    # a large block stays fast (the neighbour search runs on the host's threads)
+    import time
+    big = wfx.create_box_hex(48, 1, (1.0,) * 3)
+    t0 = time.perf_counter()
+    ok, ijk = capi.debug_structured_coords(big.xdofs, big.x.shape[0])
+    assert ok and ijk.max() == 47 and time.perf_counter() - t0 < 20

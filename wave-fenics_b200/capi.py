@@ -70,6 +70,7 @@ _SIG = {
     "wfx_stiffness_apply_scaled": [_vp, _vp, _vp, _vp, _vp],
     "wfx_stiffness_apply_host": [_vp, _vp, _vp, C.c_int],
     "wfx_stiffness_mass_apply_host": [_vp, _vp, _vp, _vp],
+    "wfx_stiffness_mass_apply_host_batch": [_vp, _vp, C.c_int, _vpp, _vpp],
     "wfx_stiffness_info": [_vp, _c_i64p, C.POINTER(C.c_int), _c_i64p, _c_f64p, _c_f64p,
                            C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "wfx_stiffness_kernel_info": [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
@@ -114,6 +115,7 @@ _SIG = {
     "wfx_wave_get_probe_series": [_vp, _c_i64p, _c_f64p, _vp],
     "wfx_wave_set_snapshot": [_vp, C.c_int64, _vp, _vp],
     "wfx_wave_destroy": [_vp],
+    "wfx_debug_structured_coords": [C.c_int64, C.c_int64, _c_i32p, _c_i32p, C.POINTER(C.c_int)],
     # debug helper (not in wavefx.h): host-only plan construction + verification
     "wfx_debug_plan_stats": [C.c_int, C.c_int64, C.c_int64, _c_i32p, C.POINTER(C.c_float), C.c_int,
                              C.c_int, C.c_int, _c_i64p],
@@ -203,6 +205,16 @@ def tabulate_1d(P, q, derivative):
     table = np.empty((m.value, P + 1))
     call("wfx_tabulate_1d", P, q, derivative, f64p(table), C.byref(m))
     return table
+
+
+def debug_structured_coords(xdofs, npts):
+    """(ok, ijk [ncells, 3]) -- integer grid coordinates from the connectivity (host only)."""
+    xdofs = np.ascontiguousarray(xdofs, dtype=np.int32)
+    ijk = np.zeros((xdofs.shape[0], 3), dtype=np.int32)
+    ok = C.c_int()
+    call("wfx_debug_structured_coords", xdofs.shape[0], int(npts), i32p(xdofs.reshape(-1)), i32p(ijk.reshape(-1)),
+         C.byref(ok))
+    return bool(ok.value), ijk
 
 
 def debug_plan_stats(P, dofmap, ndofs, centroid=None, brick_edge=4, W=8, nloc_cap=65535):

@@ -7,6 +7,7 @@
 // depend on compiler contraction; G is stored symmetric (6 entries) in the layout the
 // stiffness kernel streams.
 #include "wfx_internal.h"
+#include "wfx_plan.h"
 
 #include <cmath>
 
@@ -266,6 +267,7 @@ extern "C" int wfx_geometry_create(wfx_ctx* ctx, int P, int dtype, int64_t ncell
       for (int v = 0; v < 8; ++v) s += x_host[3 * (int64_t)xdofs_host[8 * c + v] + a];
       g->centroid[3 * c + a] = (float)(s / 8);
     }
+  if (!std::getenv("WFX_NO_CONNECTIVITY_COORDS")) structured_cell_coords(ncells, npts, xdofs_host, g->cell_ijk);
   if (ncells > 0)
   {
     const size_t esz = dtype == WFX_F64 ? 8 : 4;

@@ -166,5 +166,8 @@ struct wfx_geom
   int64_t n_affine = 0;
   // cell centroids (host) for the locality-preserving batch plan
   std::vector<float> centroid; // [ncells][3]
+  // exact integer grid coordinates from the connectivity when the mesh is one structured block
+  // (wfx_plan.h structured_cell_coords), else empty
+  std::vector<int32_t> cell_ijk; // [ncells][3]
   ~wfx_geom();
 };

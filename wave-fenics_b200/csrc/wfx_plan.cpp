@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 namespace wfx
 {
@@ -79,6 +80,138 @@ Strides find_strides(int P, const BrickShape& brick, int word_bytes, bool tuned)
 }
 } // namespace
 
+void parallel_for(int64_t n, const std::function<void(int64_t, int64_t)>& fn)
+{
+  int nt = (int)std::thread::hardware_concurrency();
+  if (const char* e = std::getenv("WFX_HOST_THREADS")) nt = std::atoi(e);
+  nt = std::max(1, std::min(nt, 32));
+  if (n < 4096 || nt == 1)
+  {
+    fn(0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  std::vector<std::exception_ptr> err((size_t)nt);
+  const int64_t chunk = (n + nt - 1) / nt;
+  for (int t = 0; t < nt; ++t)
+  {
+    const int64_t b = t * chunk, e = std::min(n, b + chunk);
+    if (b >= e) break;
+    th.emplace_back([&, t, b, e] {
+      try { fn(b, e); }
+      catch (...) { err[t] = std::current_exception(); }
+    });
+  }
+  for (auto& x : th) x.join();
+  for (auto& e : err)
+    if (e) std::rethrow_exception(e);
+}
+
+bool structured_cell_coords(int64_t ncells, int64_t npts, const int32_t* xdofs, std::vector<int32_t>& ijk)
+{
+  if (ncells <= 0 || npts <= 0) return false;
+  // vertex -> cells (CSR)
+  std::vector<int32_t> voff((size_t)npts + 1, 0);
+  for (int64_t q = 0; q < ncells * 8; ++q) voff[xdofs[q] + 1]++;
+  for (int64_t v = 0; v < npts; ++v) voff[v + 1] += voff[v];
+  std::vector<int32_t> vcell((size_t)ncells * 8);
+  {
+    std::vector<int32_t> pos(voff.begin(), voff.end() - 1);
+    for (int64_t c = 0; c < ncells; ++c)
+      for (int v = 0; v < 8; ++v) vcell[pos[xdofs[8 * c + v]]++] = (int32_t)c;
+  }
+  // face neighbours: face (axis a, side s) = the 4 vertices whose bit a equals s
+  std::vector<int32_t> nbr((size_t)ncells * 6, -1);
+  std::vector<uint8_t> bad(1, 0);
+  parallel_for(ncells, [&](int64_t c0, int64_t c1) {
+    for (int64_t c = c0; c < c1 && !bad[0]; ++c)
+    {
+      const int32_t* xc = xdofs + 8 * c;
+      for (int a = 0; a < 3; ++a)
+        for (int s = 0; s < 2; ++s)
+        {
+          int fv[4], nf = 0;
+          for (int v = 0; v < 8; ++v)
+            if (((v >> a) & 1) == s) fv[nf++] = v;
+          const int32_t v0 = xc[fv[0]];
+          int32_t found = -1;
+          for (int32_t p = voff[v0]; p < voff[v0 + 1] && found < 0; ++p)
+          {
+            const int32_t n = vcell[p];
+            if (n == c) continue;
+            const int32_t* xn = xdofs + 8 * (int64_t)n;
+            int hits = 0;
+            for (int q = 0; q < 4; ++q)
+              for (int w = 0; w < 8; ++w)
+                if (xn[w] == xc[fv[q]]) { ++hits; break; }
+            if (hits == 4) found = n;
+          }
+          if (found >= 0)
+          {
+            // same orientation: my vertex v of the face is the neighbour's vertex v with bit a flipped
+            const int32_t* xn = xdofs + 8 * (int64_t)found;
+            for (int q = 0; q < 4; ++q)
+              if (xn[fv[q] ^ (1 << a)] != xc[fv[q]]) bad[0] = 1;
+          }
+          nbr[6 * c + 2 * a + s] = found;
+        }
+    }
+  });
+  if (bad[0]) return false;
+  // breadth-first coordinates
+  std::vector<int32_t> co((size_t)ncells * 3, 0);
+  std::vector<uint8_t> seen((size_t)ncells, 0);
+  std::vector<int32_t> queue;
+  queue.reserve((size_t)ncells);
+  queue.push_back(0);
+  seen[0] = 1;
+  for (size_t h = 0; h < queue.size(); ++h)
+  {
+    const int32_t c = queue[h];
+    for (int a = 0; a < 3; ++a)
+      for (int s = 0; s < 2; ++s)
+      {
+        const int32_t n = nbr[6 * (int64_t)c + 2 * a + s];
+        if (n < 0) continue;
+        int32_t want[3] = {co[3 * (int64_t)c], co[3 * (int64_t)c + 1], co[3 * (int64_t)c + 2]};
+        want[a] += s ? 1 : -1;
+        if (!seen[n])
+        {
+          seen[n] = 1;
+          for (int q = 0; q < 3; ++q) co[3 * (int64_t)n + q] = want[q];
+          queue.push_back(n);
+        }
+        else
+          for (int q = 0; q < 3; ++q)
+            if (co[3 * (int64_t)n + q] != want[q]) return false; // not a lattice (e.g. an O-grid)
+      }
+  }
+  if ((int64_t)queue.size() != ncells) return false; // more than one block
+  int32_t lo[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, hi[3] = {INT32_MIN, INT32_MIN, INT32_MIN};
+  for (int64_t c = 0; c < ncells; ++c)
+    for (int q = 0; q < 3; ++q)
+    {
+      lo[q] = std::min(lo[q], co[3 * c + q]);
+      hi[q] = std::max(hi[q], co[3 * c + q]);
+    }
+  for (int q = 0; q < 3; ++q)
+    if ((int64_t)hi[q] - lo[q] > 0xFFFF) return false;
+  // two cells must not share a coordinate triple (a periodic mesh would wrap around)
+  const int64_t e1 = hi[1] - lo[1] + 1, e2 = hi[2] - lo[2] + 1, e0 = hi[0] - lo[0] + 1;
+  if (e0 * e1 * e2 > 8 * ncells + 64) return false; // far from a block: do not allocate the check
+  std::vector<uint8_t> occ((size_t)(e0 * e1 * e2), 0);
+  for (int64_t c = 0; c < ncells; ++c)
+  {
+    const int64_t key = ((int64_t)(co[3 * c] - lo[0]) * e1 + (co[3 * c + 1] - lo[1])) * e2 + (co[3 * c + 2] - lo[2]);
+    if (occ[key]) return false;
+    occ[key] = 1;
+  }
+  for (int64_t c = 0; c < ncells; ++c)
+    for (int q = 0; q < 3; ++q) co[3 * c + q] -= lo[q];
+  ijk.swap(co);
+  return true;
+}
+
 void build_cell_colour_plan(int nd, int64_t ncells, int64_t ndofs, const int32_t* tdm,
                             CellColourPlan& plan)
 {
@@ -129,7 +262,8 @@ void verify_cell_colour_plan(const CellColourPlan& plan, int nd, int64_t ncells,
 
 void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
                       const float* centroid, BrickShape brick, int W, int nloc_cap,
-                      BrickPlan& plan, const uint8_t* dof_shared, int word_bytes, bool allow_tuned)
+                      BrickPlan& plan, const uint8_t* dof_shared, int word_bytes, bool allow_tuned,
+                      const int32_t* cell_ijk_in)
 {
   const int n = P + 1, nd = n * n * n;
   if (ndofs > (int64_t)BD_MASK) fail("brick plan: more than 2^30 local dofs");
@@ -151,7 +285,30 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
   std::vector<uint64_t> key((size_t)ncells);
   std::vector<uint32_t> parity((size_t)ncells, 0);
   std::vector<int32_t> cell_ijk; // integer grid coordinates of the cells (when centroids are given)
-  if (centroid && ncells > 0)
+  auto set_key = [&](int64_t c, const int64_t (&ia)[3]) {
+    uint64_t b[3], loc[3];
+    for (int a = 0; a < 3; ++a)
+    {
+      b[a] = (uint64_t)(ia[a] / brick.e[a]);
+      loc[a] = (uint64_t)(ia[a] % brick.e[a]);
+      cell_ijk[3 * c + a] = (int32_t)ia[a];
+    }
+    // brick coordinates in the high bits, in-brick position in the low bits
+    key[c] = (b[0] << 44) | (b[1] << 28) | (b[2] << 12) | (loc[0] << 8) | (loc[1] << 4) | loc[2];
+    parity[c] = (uint32_t)((b[0] & 1) | ((b[1] & 1) << 1) | ((b[2] & 1) << 2));
+  };
+  if (cell_ijk_in && ncells > 0)
+  {
+    cell_ijk.resize((size_t)ncells * 3);
+    for (int64_t c = 0; c < ncells; ++c)
+    {
+      const int64_t ia[3] = {cell_ijk_in[3 * c], cell_ijk_in[3 * c + 1], cell_ijk_in[3 * c + 2]};
+      for (int a = 0; a < 3; ++a)
+        if (ia[a] < 0 || ia[a] > 0xFFFF) fail("brick plan: cell coordinate out of range");
+      set_key(c, ia);
+    }
+  }
+  else if (centroid && ncells > 0)
   {
     cell_ijk.resize((size_t)ncells * 3);
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
@@ -171,19 +328,14 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
       h = std::cbrt((ext[0] + h) * (ext[1] + h) * (ext[2] + h) / (double)ncells);
     for (int64_t c = 0; c < ncells; ++c)
     {
-      uint64_t b[3], loc[3];
+      int64_t ia[3];
       for (int a = 0; a < 3; ++a)
       {
-        int64_t ia = (int64_t)std::floor((centroid[3 * c + a] - lo[a]) / h + 0.5);
-        if (ia < 0) ia = 0;
-        if (ia > 0xFFFF) ia = 0xFFFF;
-        b[a] = (uint64_t)(ia / brick.e[a]);
-        loc[a] = (uint64_t)(ia % brick.e[a]);
-        cell_ijk[3 * c + a] = (int32_t)ia;
+        ia[a] = (int64_t)std::floor((centroid[3 * c + a] - lo[a]) / h + 0.5);
+        if (ia[a] < 0) ia[a] = 0;
+        if (ia[a] > 0xFFFF) ia[a] = 0xFFFF;
       }
-      // brick coordinates in the high bits, in-brick position in the low bits
-      key[c] = (b[0] << 44) | (b[1] << 28) | (b[2] << 12) | (loc[0] << 8) | (loc[1] << 4) | loc[2];
-      parity[c] = (uint32_t)((b[0] & 1) | ((b[1] & 1) << 1) | ((b[2] & 1) << 2));
+      set_key(c, ia);
     }
   }
   else
@@ -490,7 +642,8 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
   if (lay.tuned && plan.n_regular != nb)
   {
     BrickPlan compact;
-    build_brick_plan(P, ncells, ndofs, tdm, centroid, brick, W, nloc_cap, compact, dof_shared, word_bytes, false);
+    build_brick_plan(P, ncells, ndofs, tdm, centroid, brick, W, nloc_cap, compact, dof_shared, word_bytes, false,
+                     cell_ijk_in);
     plan = std::move(compact);
   }
 }
@@ -580,6 +733,22 @@ void verify_brick_plan(const BrickPlan& plan, const int32_t* tdm, const uint8_t*
 //   stats[0]=cell colours  [1]=batches  [2]=batch colours  [3]=nloc_max  [4]=rounds
 //   [5]=padded slots  [6]=private (first&last) batch dofs  [7]=total batch dofs
 //   [8]=untouched dofs
+// Debug entry point: structured_cell_coords on host arrays.  *ok = 1 and ijk_out [ncells][3] filled
+// when the mesh is one consistently oriented structured block, else *ok = 0.
+extern "C" int wfx_debug_structured_coords(int64_t ncells, int64_t npts, const int32_t* xdofs_host,
+                                           int32_t* ijk_out, int* ok)
+{
+  WFX_API_BEGIN
+  using namespace wfx;
+  if (!xdofs_host || !ok) fail("NULL argument");
+  for (int64_t q = 0; q < ncells * 8; ++q)
+    if (xdofs_host[q] < 0 || xdofs_host[q] >= npts) fail("geometry dofmap entry out of range");
+  std::vector<int32_t> ijk;
+  *ok = structured_cell_coords(ncells, npts, xdofs_host, ijk) ? 1 : 0;
+  if (*ok && ijk_out) std::memcpy(ijk_out, ijk.data(), ijk.size() * sizeof(int32_t));
+  WFX_API_END
+}
+
 extern "C" int wfx_debug_plan_stats(int P, int64_t ncells, int64_t ndofs,
                                     const int32_t* dofmap_host, const float* centroid_host,
                                     int brick_edge, int W, int nloc_cap, int64_t* stats)

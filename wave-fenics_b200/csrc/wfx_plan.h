@@ -16,6 +16,7 @@
 #pragma once
 
 #include <cstdint>
+#include <functional>
 #include <vector>
 
 namespace wfx
@@ -69,17 +70,29 @@ struct BrickShape
   bool cubic() const { return e[0] == e[1] && e[1] == e[2]; }
 };
 
+// Integer grid coordinates of the cells of a structured hexahedral mesh from its CONNECTIVITY
+// (geometry dofmap, vertex v = ix + 2 iy + 4 iz): face neighbours are found through shared
+// vertices, orientations must agree, coordinates follow by breadth-first search.  Independent of the
+// geometry, so sheared, graded or curved structured meshes get exact coordinates.  Returns false (ijk
+// untouched) if the mesh is not one consistently oriented structured block.
+bool structured_cell_coords(int64_t ncells, int64_t npts, const int32_t* xdofs, std::vector<int32_t>& ijk);
+
+// runs fn(begin, end) on slices of [0, n) with the host's hardware threads
+void parallel_for(int64_t n, const std::function<void(int64_t, int64_t)>& fn);
+
 // tdm: tensor-ordered dofmap in the kernels' k-major point order, [ncells][nd]
 void build_cell_colour_plan(int nd, int64_t ncells, int64_t ndofs, const int32_t* tdm,
                             CellColourPlan& plan);
 
 // centroid: [ncells][3] or nullptr (then cells are batched in the given order).
+// cell_ijk: [ncells][3] exact integer grid coordinates (structured_cell_coords) or nullptr; preferred
+// over coordinates estimated from the centroids (which assume a roughly uniform axis-aligned grid).
 // brick: cells per brick along each axis (batch capacity = their product); nloc_cap: capacity of
 // the shared-memory dof arrays.
 void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
                       const float* centroid, BrickShape brick, int W, int nloc_cap,
                       BrickPlan& plan, const uint8_t* dof_shared = nullptr, int word_bytes = 8,
-                      bool allow_tuned = true);
+                      bool allow_tuned = true, const int32_t* cell_ijk = nullptr);
 
 // Checks every invariant the kernels rely on; throws wfx::Error on violation.
 void verify_brick_plan(const BrickPlan& plan, const int32_t* tdm, const uint8_t* dof_shared = nullptr);

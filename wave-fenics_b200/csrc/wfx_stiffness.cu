@@ -937,7 +937,7 @@ template <> struct Cfg<4> { static constexpr int SLOT = 16, W = 8, BX = 4, BY = 
 #define WFX_P4_CARVE 0
 #endif
 #ifndef WFX_P4_GW
-#define WFX_P4_GW 5
+#define WFX_P4_GW 3
 #endif
 #ifndef WFX_P5_GW
 #define WFX_P5_GW 3
@@ -1040,6 +1040,19 @@ struct wfx_stiffness
   DevBuf<uint16_t> d_slot_base;
   // host-call staging
   DevBuf<unsigned char> d_hx, d_hy;
+  // batched host calls: two buffer pairs, three streams (H2D | apply | D2H)
+  DevBuf<unsigned char> d_bx[2], d_by[2];
+  cudaStream_t bs_h2d = nullptr, bs_cmp = nullptr, bs_d2h = nullptr;
+  cudaEvent_t ev_x[2] = {nullptr, nullptr}, ev_y[2] = {nullptr, nullptr}, ev_fx[2] = {nullptr, nullptr},
+              ev_fy[2] = {nullptr, nullptr};
+  ~wfx_stiffness()
+  {
+    for (cudaStream_t st : {bs_h2d, bs_cmp, bs_d2h})
+      if (st) cudaStreamDestroy(st);
+    for (int q = 0; q < 2; ++q)
+      for (cudaEvent_t e : {ev_x[q], ev_y[q], ev_fx[q], ev_fy[q]})
+        if (e) cudaEventDestroy(e);
+  }
 };
 
 namespace
@@ -1360,7 +1373,8 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
       BrickPlan bp;
       build_brick_plan(op->P, op->ncells, ndofs, tdm.data(),
                        geom->centroid.empty() ? nullptr : geom->centroid.data(), be, lc.W, nloc_cap, bp,
-                       shared.empty() ? nullptr : shared.data(), (int)esz);
+                       shared.empty() ? nullptr : shared.data(), (int)esz, true,
+                       geom->cell_ijk.empty() ? nullptr : geom->cell_ijk.data());
       op->ncolours = bp.ncolours;
       op->part_split = bp.part_split;
       op->colour_off = bp.colour_off;
@@ -1513,6 +1527,56 @@ extern "C" int wfx_stiffness_mass_apply_host(wfx_stiffness* op, wfx_mass* mass, 
   apply_any(op, op->d_hx.p, minv, op->d_hy.p, 0, nullptr);
   WFX_CUDA(cudaMemcpyAsync(y_host, op->d_hy.p, nb, cudaMemcpyDeviceToHost, 0));
   WFX_CUDA(cudaStreamSynchronize(0));
+  WFX_API_END
+}
+
+extern "C" int wfx_stiffness_mass_apply_host_batch(wfx_stiffness* op, wfx_mass* mass, int nvec,
+                                                   const void* const* x_hosts, void* const* y_hosts)
+{
+  WFX_API_BEGIN
+  if (!op || !mass) fail("NULL operator");
+  if (nvec < 0 || (nvec > 0 && (!x_hosts || !y_hosts))) fail("bad vector list");
+  for (int i = 0; i < nvec; ++i)
+    if (!x_hosts[i] || !y_hosts[i]) fail("stiffness: NULL vector %d", i);
+  if (nvec == 0) return 0;
+  ScopedDevice sd(op->ctx->device);
+  const void* minv = nullptr;
+  if (wfx_mass_inverse_diagonal(mass, &minv)) fail("%s", wfx_last_error());
+  const size_t nb = (size_t)op->ndofs * (op->dtype == WFX_F64 ? 8 : 4);
+  if (!op->bs_h2d)
+  {
+    WFX_CUDA(cudaStreamCreateWithFlags(&op->bs_h2d, cudaStreamNonBlocking));
+    WFX_CUDA(cudaStreamCreateWithFlags(&op->bs_cmp, cudaStreamNonBlocking));
+    WFX_CUDA(cudaStreamCreateWithFlags(&op->bs_d2h, cudaStreamNonBlocking));
+    for (int q = 0; q < 2; ++q)
+      for (cudaEvent_t* e : {&op->ev_x[q], &op->ev_y[q], &op->ev_fx[q], &op->ev_fy[q]})
+        WFX_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
+  for (int q = 0; q < 2; ++q)
+  {
+    if (op->d_bx[q].n < nb) op->d_bx[q].alloc(nb);
+    if (op->d_by[q].n < nb) op->d_by[q].alloc(nb);
+  }
+  // vector i: H2D on one stream, the fused apply on a second, D2H on a third; buffer pair i % 2, so
+  // the copy-in of vector i+1 and the copy-out of vector i-1 run under the apply of vector i (PCIe is
+  // full duplex: the steady state costs max(H2D, D2H) per vector instead of their sum)
+  for (int i = 0; i < nvec; ++i)
+  {
+    const int q = i & 1;
+    if (i >= 2) WFX_CUDA(cudaStreamWaitEvent(op->bs_h2d, op->ev_fx[q], 0)); // apply i-2 has read d_bx[q]
+    WFX_CUDA(cudaMemcpyAsync(op->d_bx[q].p, x_hosts[i], nb, cudaMemcpyHostToDevice, op->bs_h2d));
+    WFX_CUDA(cudaEventRecord(op->ev_x[q], op->bs_h2d));
+    WFX_CUDA(cudaStreamWaitEvent(op->bs_cmp, op->ev_x[q], 0));
+    if (i >= 2) WFX_CUDA(cudaStreamWaitEvent(op->bs_cmp, op->ev_fy[q], 0)); // copy-out i-2 has read d_by[q]
+    apply_any(op, op->d_bx[q].p, minv, op->d_by[q].p, 0, op->bs_cmp);
+    WFX_CUDA(cudaEventRecord(op->ev_y[q], op->bs_cmp));
+    WFX_CUDA(cudaEventRecord(op->ev_fx[q], op->bs_cmp));
+    WFX_CUDA(cudaStreamWaitEvent(op->bs_d2h, op->ev_y[q], 0));
+    WFX_CUDA(cudaMemcpyAsync(y_hosts[i], op->d_by[q].p, nb, cudaMemcpyDeviceToHost, op->bs_d2h));
+    WFX_CUDA(cudaEventRecord(op->ev_fy[q], op->bs_d2h));
+  }
+  WFX_CUDA(cudaStreamSynchronize(op->bs_d2h));
+  WFX_CUDA(cudaStreamSynchronize(op->bs_cmp));
   WFX_API_END
 }
 
