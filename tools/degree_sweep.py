@@ -82,32 +82,52 @@ def main():
             x = torch.randn(mesh.ndofs, dtype=tdt, device="cuda")
             y = torch.empty_like(x)
             ms = time_ms(lambda: op.apply_scaled(x, mass.inverse_diagonal_ptr(), y), args.reps)
-            # comparator on a slab of the mesh that fits comfortably (dense tables: nd^2 per cell flops)
-            ncc = min(mesh.ncells, 32768)
+            # comparator on a slab of the mesh that fits comfortably (dense tables: nd^2 per cell flops);
+            # its G comes from a geometry object of the slab's cells only
+            ncc = min(mesh.ncells, 32768 if P <= 5 else 8192)
             dm = torch.from_numpy(mesh.dofmap[:ncc].astype(np.int64)).cuda()
-            G9, _ = geo.get() if mesh.ncells <= 300000 and P <= 4 else (None, None)
+            import copy
+            slab = copy.copy(mesh)
+            slab.xdofs = np.ascontiguousarray(mesh.xdofs[:ncc])
+            slab.dofmap = np.ascontiguousarray(mesh.dofmap[:ncc])
+            G9, _ = wfx.Geometry(slab, P, np.float64).get()
             tsmm = None
             if G9 is not None:
-                G9t = torch.from_numpy(G9[:ncc]).to("cuda", tdt)
+                G9t = torch.from_numpy(G9).to("cuda", tdt)
                 tabs = dense_tables(P, tdt)
                 y2 = torch.zeros_like(x)
                 ms_t = time_ms(lambda: tsmm_apply(x, y2, dm, tabs, G9t, -1500.0 ** 2), max(2, args.reps // 3))
                 tsmm = ncc * (P ** 3) / (ms_t * 1e-3) / 1e9  # dofs ~ P^3 per cell
-                del G9t, tabs, y2
+                # the comparator must compute the same thing: check it against the product kernel on the slab
+                sop = wfx.StiffnessOperator(slab, P, dtype=dt)
+                ys = torch.zeros_like(x)
+                sop.apply(x, ys, beta=0)
+                y2.zero_()
+                tsmm_apply(x, y2, dm, tabs, G9t, -1500.0 ** 2)
+                err = float((y2 - ys).norm() / ys.norm())
+                assert err < (1e-11 if dt == np.float64 else 1e-3), err
+                del G9t, tabs, y2, sop, ys
             gd = mesh.ndofs / (ms * 1e-3) / 1e9
             gbs = info["bytes"] / (ms * 1e-3) / 1e9
-            rows.append((P, N, mesh.ndofs, "f64" if dt == np.float64 else "f32", ms, gd, gbs, gbs / peak, info["flops"] / (ms * 1e-3) / 1e12, tsmm))
+            tf = info["flops"] / (ms * 1e-3) / 1e12
+            fp_peak = 37.2 if dt == np.float64 else 74.5   # 148 SMs x 64 (128) FMA/clk x 2 x 1.965 GHz
+            rows.append((P, N, mesh.ndofs, "f64" if dt == np.float64 else "f32", ms, gd, gbs, gbs / peak, tf, tsmm, tf / fp_peak))
             print(rows[-1], flush=True)
             del op, mass, geo, x, y
             torch.cuda.empty_cache()
     lines = ["# Degree sweep (BASELINE config 3), one B200, stiffness + mass apply, ~17 M dofs per case",
              "", f"HBM peak used for the fraction: {peak} GB/s (MEASURED_PEAKS.json). `TSMM` = dense-table batched GEMM",
              "comparator (torch.matmul/cuBLAS, gather + 6 GEMMs + G + atomic scatter) on a 32 768-cell slab, in GDoF/s.", "",
-             "| P | cells/axis | dofs | dtype | ms/apply | GDoF/s | algorithmic GB/s | frac of HBM peak | TFLOP/s (sum-fact count) | TSMM GDoF/s |",
-             "|---|---|---|---|---|---|---|---|---|---|"]
+             "`FP pipe` = sum-factorised flop rate / the FMA-pipe peak of the scalar type (37.2 TF fp64, 74.5 TF fp32): the",
+             "contraction is nowhere near compute-bound, so tensor cores are not used (north_star: only if a degree sweep shows",
+             "the contraction to be compute-bound); the dense-table GEMM formulation, which would map to tensor cores, loses by",
+             "the factor in the last column even with cuBLAS doing the GEMMs.", "",
+             "| P | cells/axis | dofs | dtype | ms/apply | GDoF/s | algorithmic GB/s | frac of HBM peak | TFLOP/s (sum-fact count) | FP pipe | tensor cores? | TSMM GDoF/s | sum-fact / TSMM |",
+             "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
     for r in rows:
         lines.append(f"| {r[0]} | {r[1]} | {r[2]} | {r[3]} | {r[4]:.3f} | {r[5]:.2f} | {r[6]:.0f} | {r[7]:.3f} | {r[8]:.2f} | "
-                     + (f"{r[9]:.2f}" if r[9] else "n/a") + " |")
+                     f"{100 * r[10]:.0f} % | no: FP pipe {100 * r[10]:.0f} % busy | "
+                     + (f"{r[9]:.2f} | {r[5] / r[9]:.0f}x" if r[9] else "n/a | n/a") + " |")
     text = "\n".join(lines) + "\n"
     print(text)
     if args.out:

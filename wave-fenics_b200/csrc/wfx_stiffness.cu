@@ -699,12 +699,27 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
     if constexpr (REG) sbase[v] = __ldg(a.slot_base + (int64_t)r0 * W + v);
   }
   // the batch's dofs: asynchronous gathers into xl (first pass from the indices loaded above)
+#ifdef WFX_STAGE_REG
+  // experiment: gather through registers with L2-only loads (no L1 lines held by the gathers)
+  {
+    T xv[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) xv[q] = e[q] != BD_HOLE ? __ldcg(a.x + (e[q] & BD_MASK)) : T(0);
+#pragma unroll
+    for (int q = 0; q < U; ++q)
+    {
+      if (e[q] != BD_HOLE) xl[tid + q * NT] = xv[q];
+      if (tid + q * NT < nloc) yl[tid + q * NT] = T(0);
+    }
+  }
+#else
 #pragma unroll
   for (int q = 0; q < U; ++q)
   {
     if (e[q] != BD_HOLE) cp_async_scalar(xl + tid + q * NT, a.x + (e[q] & BD_MASK));
     if (tid + q * NT < nloc) yl[tid + q * NT] = T(0);
   }
+#endif
   for (int base = tid + NT * U; base < nloc; base += NT * U)
   {
 #pragma unroll
