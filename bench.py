@@ -196,6 +196,8 @@ def run_b200(args):
     mass = wfx.MassOperator(mesh, P, ctx=ctx, geometry=geo)
     t_setup = time.perf_counter() - t_setup
     info = stiff.info()
+    kernel_info = stiff.kernel_info()
+    halo_transport = halo.transport if halo is not None else None
     if halo is not None:
         mass.assemble(halo)
     minv_ptr = mass.inverse_diagonal_ptr()
@@ -228,6 +230,13 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    def global_h_min(m):
+        """mesh::h minimum over all ranks (MPI_Reduce MIN + Bcast, demo/cpu_planar3d/main.cpp:57-58)"""
+        t = torch.tensor([m.h_min], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t.item())
 
     def max_over_ranks(vals):
         t = torch.tensor(vals, dtype=torch.float64, device=dev)
@@ -415,7 +424,7 @@ def run_b200(args):
         del x, y
         eqn = wfx.LinearGLLOpt(mesh, None, P, 1500.0, 0.5e6, 6e4, ctx=ctx, halo=halo)
         eqn.init()
-        dt_w = wfx.cfl_timestep(mesh.h_min, 1500.0, P, 0.5e6)
+        dt_w = wfx.cfl_timestep(global_h_min(mesh), 1500.0, P, 0.5e6)
         eqn.rk4(0.0, 1.0, dt_w, max_steps=2)
         k_rk = max(3, min(args.steps, 10))
         rk_local = []
@@ -438,6 +447,44 @@ def run_b200(args):
         rk4 = {"ms_per_step": ms_rk, "windows_ms_per_step": rk_ms, "steps": k_rk, "dofs_global": int(ndofs_global),
                "gdof_steps_per_s": ndofs_global / (ms_rk * 1e-3) / 1e9,
                "bytes_per_step_per_gpu": b_step, "achieved_gbs_per_gpu": b_step / (ms_rk * 1e-3) / 1e9}
+
+    # BASELINE configs[3] inside the default run, so that the driver's 1/2/4/8 series carries the
+    # strong-scaling numbers too: the full RK4 step on a FIXED 128^3-cell global mesh (135 M dofs) split
+    # over the N ranks.  At N = 8 with the default 64^3 cells per GPU it is the weak-scaling mesh itself.
+    strong = None
+    if not args.no_strong and not args.no_rk4 and args.scaling == "weak":
+        sshape = (args.global_cells,) * 3
+        if sshape == tuple(gshape) and rk4:
+            strong = {"global_cells": list(sshape), "dofs_global": int(ndofs_global), "rk4_ms_per_step": rk4["ms_per_step"],
+                      "note": "same mesh and run as the weak-scaling rk4 figure"}
+        elif all(sshape[a] % grid[a] == 0 for a in range(3)):
+            del eqn, stiff, mass, geo
+            torch.cuda.empty_cache()
+            if world == 1:
+                smesh, shalo = wfx.create_box_hex(sshape, P, (L, L, L), perturb=args.perturb), None
+            else:
+                smesh = partition.create_box_hex_partition(sshape, P, (L, L, L), grid, rank, perturb=args.perturb)
+                shalo = partition.Halo(smesh, ctx, np.float64, comm=halo.comm)
+            seqn = wfx.LinearGLLOpt(smesh, None, P, 1500.0, 0.5e6, 6e4, ctx=ctx, halo=shalo)
+            seqn.init()
+            dt_s = wfx.cfl_timestep(global_h_min(smesh), 1500.0, P, 0.5e6)
+            seqn.rk4(0.0, 1.0, dt_s, max_steps=2)
+            k_s = 5
+            loc = []
+            for w in range(3):
+                sync_all()
+                ev0.record()
+                seqn.rk4((2 + w * k_s) * dt_s, 1.0, dt_s, max_steps=k_s)
+                ev1.record()
+                sync_all()
+                loc.append(ev0.elapsed_time(ev1) / k_s)
+            s_ms = max_over_ranks(loc)
+            u_s, _ = seqn.get_state()
+            assert np.isfinite(u_s).all()
+            strong = {"global_cells": list(sshape), "dofs_global": int(smesh.ndofs_global),
+                      "rk4_ms_per_step": float(np.median(s_ms)), "windows_ms_per_step": s_ms,
+                      "cells_per_gpu": list(smesh.shape), "halo_transport": shalo.transport if shalo is not None else None}
+            del seqn, smesh
 
     if rank != 0:
         if world > 1:
@@ -493,12 +540,12 @@ def run_b200(args):
                        "dofmap": "brick-implicit (one int32 per brick dof, no per-point dofmap is read): see roofline.frac_no_dofmap",
                        "timing": f"median of {args.windows} windows of {args.steps} applies, max over ranks per window",
                        "partition": "x".join(map(str, grid)), "setup_s": round(t_setup, 2),
-                       "kernel": stiff.kernel_info(), "halo_transport": halo.transport if halo is not None else None},
+                       "kernel": kernel_info, "halo_transport": halo_transport},
             "windows_ms": win_ms, "window_ms_min": min(win_ms), "window_ms_max": max(win_ms),
             "clocks": clocks, "sustained": sustained, "parity": parity, "affine_fast_path": affine,
             "e2e": e2e,
             "gpu_launches": (args.windows * args.steps) * (info["nlaunches"] + (0 if halo is None else 5)),
-            "roofline": roofline, "cpu_baseline": cpu, "rk4": rk4}
+            "roofline": roofline, "cpu_baseline": cpu, "rk4": rk4, "strong_scaling": strong}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -522,6 +569,7 @@ def main():
     ap.add_argument("--no-rk4", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-affine", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the 128^3 strong-scaling RK4 sub-measurement")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 20 if args.impl == "b200" else 5

@@ -678,3 +678,38 @@ def test_probe_series_and_snapshots_match_oracle(wfx, orc, torch):
     eqn2.rk4(snaps[16][0], 1.0, dt, max_steps=nsteps - 16)
     u2, v2 = eqn2.get_state()
     assert np.array_equal(u2, u_end) and np.array_equal(v2, v_end)
+
+
+@pytest.mark.gpu
+def test_stiffness_repeatable_under_concurrent_load(wfx, torch):
+    """Race evidence without a sanitizer (compute-sanitizer is closed on the GPU pool): the apply is
+    repeated while an unrelated kernel stream perturbs the CTA scheduling; every result must equal
+    the first bit for bit (a shared-memory or write-back race would show as a changing bit pattern).
+    Covers the regular-brick, generic and affine kernels."""
+    P = 4
+    side = torch.cuda.Stream()
+    noise = torch.randn(2048, 2048, device="cuda")
+    for perturb, env in ((0.15, {}), (0.0, {}), (0.15, {"WFX_REGULAR": "0"})):
+        import os
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            mesh = _mesh(wfx, 12, P, perturb)
+            geo = wfx.Geometry(mesh, P)
+            op = wfx.StiffnessOperator(mesh, P, geometry=geo)
+            mass = wfx.MassOperator(mesh, P, geometry=geo)
+        finally:
+            for k, v in old.items():
+                os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+        x = torch.randn(mesh.ndofs, dtype=torch.float64, device="cuda")
+        ref = torch.empty_like(x)
+        op.apply_scaled(x, mass.inverse_diagonal_ptr(), ref)
+        for it in range(25):
+            if it % 2:
+                with torch.cuda.stream(side):
+                    for _ in range(3):
+                        noise = noise @ noise * 1e-3
+            y = torch.full_like(x, float("nan"))
+            op.apply_scaled(x, mass.inverse_diagonal_ptr(), y)
+            assert torch.equal(y, ref), f"apply {it} differs ({op.kernel_info()})"
+        side.synchronize()

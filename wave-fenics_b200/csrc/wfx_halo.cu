@@ -127,6 +127,7 @@ struct wfx_halo
   int dtype = WFX_F64;
   std::vector<int32_t> send_ranks, send_off, recv_ranks, recv_off;
   int64_t nsend = 0, nrecv = 0;
+  int64_t n = 0; // size_local + num_ghosts
   DevBuf<int32_t> d_send_idx, d_recv_idx;
   DevBuf<unsigned char> d_send_buf, d_recv_buf;
   // reverse accumulate: unique owned targets and their buffer positions
@@ -195,9 +196,26 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
 // data another GPU wrote into this GPU's memory: read at L2, never from a stale L1 line
 template <typename T> __device__ __forceinline__ T ld_peer_written(const T* p) { return __ldcg(p); }
 
+#ifdef WFX_CHECKED
+#define WFX_DEV_ASSERT(cond)                                                                          \
+  do                                                                                                  \
+  {                                                                                                   \
+    if (!(cond))                                                                                      \
+    {                                                                                                 \
+      printf("wfx check failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__,         \
+             (int)blockIdx.x, (int)threadIdx.x);                                                      \
+      __trap();                                                                                       \
+    }                                                                                                 \
+  } while (0)
+#else
+#define WFX_DEV_ASSERT(cond) ((void)0)
+#endif
+
 template <typename T>
 struct P2PArgs
 {
+  int64_t n;      // vector length (checked builds)
+  int64_t nsend;  // entries of the reverse receive buffer
   T* x;
   const T* scale; // nullable
   int n_recv_nbr, n_send_nbr;
@@ -234,7 +252,11 @@ halo_p2p_kernel(const P2PArgs<T> a)
   {
     const int beg = a.recv_off[n], end = a.recv_off[n + 1];
     T* dst = a.rbuf_dst[n];
-    for (int i = beg + cta * P2P_THREADS + tid; i < end; i += G * P2P_THREADS) dst[i - beg] = a.x[a.recv_idx[i]];
+    for (int i = beg + cta * P2P_THREADS + tid; i < end; i += G * P2P_THREADS)
+    {
+      WFX_DEV_ASSERT(a.recv_idx[i] >= 0 && a.recv_idx[i] < a.n);
+      dst[i - beg] = a.x[a.recv_idx[i]];
+    }
   }
   __threadfence_system();
   __syncthreads();
@@ -247,9 +269,14 @@ halo_p2p_kernel(const P2PArgs<T> a)
   for (int64_t j = cta * P2P_THREADS + tid; j < a.nuniq; j += (int64_t)G * P2P_THREADS)
   {
     const int32_t d = a.uniq[j];
+    WFX_DEV_ASSERT(d >= 0 && d < a.n);
     T s = a.x[d];
     const int64_t p0 = a.useg_off[j], p1 = a.useg_off[j + 1];
-    for (int64_t p = p0; p < p1; ++p) s += ld_peer_written(a.rbuf + a.useg_src[p]);
+    for (int64_t p = p0; p < p1; ++p)
+    {
+      WFX_DEV_ASSERT(a.useg_src[p] >= 0 && a.useg_src[p] < a.nsend);
+      s += ld_peer_written(a.rbuf + a.useg_src[p]);
+    }
     if (a.scale) s *= a.scale[d];
     a.x[d] = s;
     for (int64_t p = p0; p < p1; ++p)
@@ -277,6 +304,8 @@ template <typename T>
 void exchange_p2p(wfx_halo* h, T* x, cudaStream_t st, const T* scale)
 {
   P2PArgs<T> a;
+  a.n = h->n;
+  a.nsend = h->nsend;
   a.x = x;
   a.scale = scale;
   a.n_recv_nbr = (int)h->recv_ranks.size();
@@ -598,6 +627,7 @@ extern "C" int wfx_halo_create(wfx_ctx* ctx, wfx_comm* comm, int dtype, int64_t 
   else h->recv_off.assign(1, 0);
   h->nsend = h->send_off.back();
   h->nrecv = h->recv_off.back();
+  h->n = size_local + num_ghosts;
   {
     // a ghost slot is filled by exactly one owner
     std::vector<uint8_t> seen((size_t)num_ghosts, 0);

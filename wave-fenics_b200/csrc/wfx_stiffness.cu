@@ -126,6 +126,24 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Checked build (-DWFX_CHECKED): device-side bounds checks on every index the kernels form -- the
+// pool's compute-sanitizer is closed, so the memory-safety evidence comes from running the GPU test
+// suite against this build (profiles/r2_checked_build.md).  A violation prints and traps.
+#ifdef WFX_CHECKED
+#define WFX_DEV_ASSERT(cond)                                                                          \
+  do                                                                                                  \
+  {                                                                                                   \
+    if (!(cond))                                                                                      \
+    {                                                                                                 \
+      printf("wfx check failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__,         \
+             (int)blockIdx.x, (int)threadIdx.x);                                                      \
+      __trap();                                                                                       \
+    }                                                                                                 \
+  } while (0)
+#else
+#define WFX_DEV_ASSERT(cond) ((void)0)
+#endif
+
 template <int N> struct Cfg; // per-degree launch configuration (below)
 
 template <typename T, int N>
@@ -341,11 +359,10 @@ __device__ __forceinline__ void g_multiply(const T (&u)[N], typename Vec2<T>::ty
                                            const typename Vec2<T>::type* gnext)
 {
   constexpr int NP = ((N + GW - 1) / GW) * GW;
+  constexpr int NPW = NP;
 #pragma unroll
   for (int k = 0; k < NP; ++k)
   {
-    constexpr int dummy = 0;
-    (void)dummy;
     if (k < N)
     {
       T w2 = 0;
@@ -368,12 +385,12 @@ __device__ __forceinline__ void g_multiply(const T (&u)[N], typename Vec2<T>::ty
         for (int p = 0; p < 3; ++p) g[k % GW][p] = ld_stream(gcur + (t * 3 + p) * (N * N));
       }
     }
-    else if (t >= NP && t - NP < N)
+    else if (t >= NPW && t - NPW < N)
     {
       if (gnext)
       {
 #pragma unroll
-        for (int p = 0; p < 3; ++p) g[k % GW][p] = ld_stream(gnext + ((t - NP) * 3 + p) * (N * N));
+        for (int p = 0; p < 3; ++p) g[k % GW][p] = ld_stream(gnext + ((t - NPW) * 3 + p) * (N * N));
       }
     }
   }
@@ -589,6 +606,8 @@ struct BrickArgs
   int g_order;               // column order of G6 (see g_column)
   int uni_nloc, uni_nr;      // > 0: every batch has this many dof positions / rounds (no header loads)
   const int32_t* batch_ids;  // mixed plans: batch of CTA i is batch_ids[batch0 + i] (nullptr: batch0 + i)
+  int64_t ndofs, ncells;     // vector length / cell count (checked builds verify every index against them)
+  int nbatches;
 };
 
 // Shared memory of one CTA
@@ -641,6 +660,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   PhaseTimer tm;
   tm.start(threadIdx.x % 32 == 0);
   const int b = a.batch_ids ? __ldg(a.batch_ids + batch0 + blockIdx.x) : batch0 + (int)blockIdx.x;
+  WFX_DEV_ASSERT(b >= 0 && b < a.nbatches);
   // batch header: arithmetic when the plan is uniform (saves a memory round trip), else loaded
   const int64_t d0 = a.uni_nloc ? (int64_t)b * a.uni_nloc : __ldg(a.dof_off + b);
   const int nloc = a.uni_nloc ? a.uni_nloc : (int)(__ldg(a.dof_off + b + 1) - d0);
@@ -651,6 +671,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   const int gcol = g_column<L, N>(ro, lane_ok ? col : 0, a.g_order);
   const int r0 = a.uni_nr ? b * a.uni_nr : __ldg(a.round_off + b);
   const int nr = a.uni_nr ? a.uni_nr : __ldg(a.round_off + b + 1) - r0;
+  WFX_DEV_ASSERT(nloc >= 0 && nloc <= a.nloc_pad && nr >= 0 && nr <= a.rounds_max);
 
   // the batch's local dofmap: one TMA bulk copy, waited for after the dofs are staged
   if constexpr (!REG)
@@ -716,6 +737,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
 #pragma unroll
   for (int q = 0; q < U; ++q)
   {
+    WFX_DEV_ASSERT(e[q] == BD_HOLE || (int64_t)(e[q] & BD_MASK) < a.ndofs);
     if (e[q] != BD_HOLE) cp_async_scalar(xl + tid + q * NT, a.x + (e[q] & BD_MASK));
     if (tid + q * NT < nloc) yl[tid + q * NT] = T(0);
   }
@@ -727,6 +749,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
 #pragma unroll
     for (int q = 0; q < U; ++q)
     {
+      WFX_DEV_ASSERT(e[q] == BD_HOLE || (int64_t)(e[q] & BD_MASK) < a.ndofs);
       if (e[q] != BD_HOLE) cp_async_scalar(xl + base + q * NT, a.x + (e[q] & BD_MASK));
       if (base + q * NT < nloc) yl[base + q * NT] = T(0);
     }
@@ -760,6 +783,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   for (int r = 0; r < nr; ++r)
   {
     const int cell = scell[r * W + slot];
+    WFX_DEV_ASSERT(cell < a.ncells);
     const bool active = lane_ok && cell >= 0;
     const int cn = r + 1 < nr ? scell[(r + 1) * W + slot] : -1;
     bool g_requested = false; // next cell's G already requested inside part 1
@@ -785,6 +809,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
         constexpr int P0 = N - 1;
         const int am = m == 0 ? 0 : (m == 1 ? P0 : m - 1); // ascpos(m), compile-time after unrolling
         li[m] = base + offK + am;
+        WFX_DEV_ASSERT(!active || (li[m] >= 0 && li[m] < nloc && base + offJ + am * a.Sy < nloc && base + offI + am * a.Sx < nloc));
         u[m] = active ? xl[li[m]] : T(0);
         lj[m] = active ? xl[base + offJ + am * a.Sy] : T(0);
         lI[m] = active ? xl[base + offI + am * a.Sx] : T(0);
@@ -807,6 +832,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
       for (int k = 0; k < N; ++k)
       {
         li[k] = active ? (int)lrow[k * N2] : 0;
+        WFX_DEV_ASSERT(li[k] >= 0 && li[k] < nloc);
         u[k] = active ? xl[li[k]] : T(0);
         yv[k] = 0;
       }
@@ -898,6 +924,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
     {
       const bool ok = e[q] != BD_HOLE; // in range and a real dof (regular bricks have unused positions)
       const uint32_t dof = e[q] & BD_MASK;
+      WFX_DEV_ASSERT(!ok || (int64_t)dof < a.ndofs);
       v[q] = (ok && (!(e[q] & BD_FIRST) || a.beta)) ? __ldcg(a.y + dof) : T(0);
       sc[q] = (ok && (e[q] & BD_LAST) && a.scale) ? ld_once(a.scale + dof) : T(1);
     }
@@ -1133,6 +1160,9 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   a.uni_nloc = op->uni_nloc;
   a.uni_nr = op->uni_nr;
   a.batch_ids = nullptr;
+  a.ndofs = op->ndofs;
+  a.ncells = op->ncells;
+  a.nbatches = op->nbatches;
   if (!beta && op->d_untouched.n && part != 1)
   {
     const int n = (int)op->d_untouched.n;

@@ -19,6 +19,7 @@
 
 #include <array>
 #include <cstdint>
+#include <functional>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -93,6 +94,17 @@ public:
     detJ.resize((std::size_t)ncells * nq);
     check(wfx_geometry_get(_h, G.data(), detJ.data()));
   }
+  // cells whose G is w_q times one constant matrix (parallelepipeds): all of them => the stiffness
+  // operator takes the structured fast path (6 scalars of G per cell)
+  std::int64_t num_affine_cells() const
+  {
+    std::int64_t nc = 0, na = 0;
+    check(wfx_geometry_info(_h, &nc, &na));
+    return na;
+  }
+  // heterogeneous medium: G of cell c scaled by coeff[c], e.g. (c0[c] / c0_ref)^2 -- the coefficient
+  // the reference leaves as a TODO (common/LinearGLL.hpp:170, params ignored at operators.hpp:113-115)
+  void scale_cells(const std::vector<double>& coeff) { check(wfx_geometry_scale_cells(_h, coeff.data())); }
 
 private:
   std::shared_ptr<Context> _ctx;
@@ -141,6 +153,14 @@ public:
   std::size_t num_cells() const { return (std::size_t)info().ncells; }
   std::size_t num_dofs() const { return (std::size_t)info().nd; }
   double flops() const { return info().flops; }
+  // the structured fast path was selected (every cell affine, every batch a lattice brick)
+  bool affine_fast_path() const
+  {
+    int variant = 0, affine = 0, mixed = 0, nreg = 0, nb = 0;
+    std::int64_t smem = 0;
+    check(wfx_stiffness_kernel_info(_h, &variant, &affine, &mixed, &nreg, &nb, &smem));
+    return affine != 0;
+  }
   wfx_stiffness* get() const { return _h; }
 
 private:
@@ -199,6 +219,17 @@ private:
 };
 template <typename T>
 using MassOperatorCPU = MassOperator<T>;
+
+// y_i = M^-1 (-c0^2 K x_i) for several HOST vectors in one call: copy-in, fused apply and copy-out of
+// consecutive vectors are pipelined (use pinned memory), see wfx_stiffness_mass_apply_host_batch.
+template <typename T>
+void stiffness_mass_apply_batch(StiffnessOperator<T>& K, MassOperator<T>& M, const std::vector<const T*>& x,
+                                const std::vector<T*>& y)
+{
+  if (x.size() != y.size()) throw std::runtime_error("wavefx: x and y lists differ in length");
+  check(wfx_stiffness_mass_apply_host_batch(K.get(), M.get(), (int)x.size(), reinterpret_cast<const void* const*>(x.data()),
+                                            reinterpret_cast<void* const*>(y.data())));
+}
 
 // Index data of a ghost exchange, as VectorUpdater reads it from the IndexMap
 // (demo/gpu_scatter_mpi/VectorUpdater.hpp:31-59 and the neighbour ranks of :69-80).
@@ -321,6 +352,34 @@ public:
     _ctx->synchronize();
     return steps;
   }
+  // ---- output (the reference prints the solve time only, demo/cpu_planar3d/main.cpp:87-93) ----
+  // u at the given dofs after every completed step, kept on the device (at most max_records steps)
+  void set_probes(const std::vector<std::int32_t>& dofs, std::int64_t max_records)
+  {
+    _nprobes = (std::int64_t)dofs.size();
+    check(wfx_wave_set_probes(_wave, _nprobes, dofs.data(), max_records));
+  }
+  // times [nrec] and values [nrec][nprobes] recorded so far
+  void probe_series(std::vector<double>& t, std::vector<double>& values) const
+  {
+    std::int64_t n = 0;
+    check(wfx_wave_get_probe_series(_wave, &n, nullptr, nullptr));
+    t.resize((std::size_t)n);
+    values.resize((std::size_t)(n * _nprobes));
+    check(wfx_wave_get_probe_series(_wave, &n, t.data(), values.data()));
+  }
+  // fn(step, t, u, v) every `every` steps with pointers into pinned host copies (ndofs entries each);
+  // the device -> host copy overlaps the time stepping.  A checkpoint is a snapshot handed back to
+  // set_state.
+  void set_snapshot(std::int64_t every, std::function<void(std::int64_t, double, const double*, const double*)> fn)
+  {
+    _snap = std::move(fn);
+    check(wfx_wave_set_snapshot(_wave, _snap ? every : 0, _snap ? &LinearGLLOpt::snapshot_trampoline : nullptr, this));
+  }
+  void set_state(const std::vector<double>& u, const std::vector<double>& v)
+  {
+    check(wfx_wave_set_state(_wave, u.data(), v.data()));
+  }
   // u_n, v_n after the solve (:282-285), host copies
   void solution(std::vector<double>& u_n, std::vector<double>& v_n) const
   {
@@ -333,6 +392,13 @@ public:
   std::shared_ptr<StiffnessOperator<double>> stiff_op;
 
 private:
+  static void snapshot_trampoline(void* self, std::int64_t step, double t, const void* u, const void* v)
+  {
+    auto* me = static_cast<LinearGLLOpt*>(self);
+    if (me->_snap) me->_snap(step, t, static_cast<const double*>(u), static_cast<const double*>(v));
+  }
+  std::function<void(std::int64_t, double, const double*, const double*)> _snap;
+  std::int64_t _nprobes = 0;
   std::shared_ptr<Context> _ctx;
   std::shared_ptr<VectorUpdater<double>> _halo;
   std::shared_ptr<Geometry<double>> _geom;
