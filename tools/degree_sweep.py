@@ -65,6 +65,7 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--degrees", default="2,3,4,5,6,7")
+    ap.add_argument("--no-tsmm", action="store_true", help="skip the dense-GEMM comparator")
     args = ap.parse_args()
     peak = 6538.6
     pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
@@ -90,9 +91,9 @@ def main():
             slab = copy.copy(mesh)
             slab.xdofs = np.ascontiguousarray(mesh.xdofs[:ncc])
             slab.dofmap = np.ascontiguousarray(mesh.dofmap[:ncc])
-            G9, _ = wfx.Geometry(slab, P, np.float64).get()
+            G9 = None if args.no_tsmm else wfx.Geometry(slab, P, np.float64).get()[0]
             tsmm = None
-            if G9 is not None:
+            if G9 is not None and not args.no_tsmm:
                 G9t = torch.from_numpy(G9).to("cuda", tdt)
                 tabs = dense_tables(P, tdt)
                 y2 = torch.zeros_like(x)

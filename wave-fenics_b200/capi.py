@@ -125,8 +125,14 @@ lib.wfx_last_error.restype = C.c_char_p
 lib.wfx_last_error.argtypes = []
 lib.wfx_version.restype = C.c_int
 lib.wfx_version.argtypes = []
+_missing = set()
 for _name, _args in _SIG.items():
-    _f = getattr(lib, _name)
+    try:
+        _f = getattr(lib, _name)
+    except AttributeError:
+        # an older experiment build named by WFX_LIB: its missing entry points fail when called
+        _missing.add(_name)
+        continue
     _f.argtypes = _args
     _f.restype = C.c_int
 
@@ -137,6 +143,8 @@ def check(status):
 
 
 def call(name, *args):
+    if name in _missing:
+        raise WfxError(f"{LIB_PATH} does not export {name}")
     check(getattr(lib, name)(*args))
 
 

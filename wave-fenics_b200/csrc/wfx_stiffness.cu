@@ -605,7 +605,7 @@ struct BrickArgs
   int Sx, Sy;                // REG kernels: strides of the brick lattice in the shared arrays
   int g_order;               // column order of G6 (see g_column)
   int uni_nloc, uni_nr;      // > 0: every batch has this many dof positions / rounds (no header loads)
-  const int32_t* batch_ids;  // mixed plans: batch of CTA i is batch_ids[batch0 + i] (nullptr: batch0 + i)
+  const int32_t* batch_ids;  // IDS kernels (mixed plans): batch of CTA i is batch_ids[batch0 + i]
   int64_t ndofs, ncells;     // vector length / cell count (checked builds verify every index against them)
   int nbatches;
 };
@@ -621,7 +621,10 @@ struct BrickArgs
 // L1 -- do not grow it ("L1 is part of the budget").
 // AFF (with REG): every cell is affine -- G(q) = w_q A_cell, 6 scalars per cell from a.Gc; the
 // per-point array G6 is never read (structured fast path).
-template <typename T, int N, int SLOT, int W, int MINB, bool REG, typename L, bool AFF = false>
+// IDS: the batch of CTA i is a.batch_ids[batch0 + i] (mixed plans).  A separate instantiation: with
+// the indirection the batch index is a loaded value instead of a uniform expression of blockIdx, and
+// everything derived from it leaves the uniform datapath (measured: +25 % at P2 fp32).
+template <typename T, int N, int SLOT, int W, int MINB, bool REG, typename L, bool AFF = false, bool IDS = false>
 __global__ void __launch_bounds__(SLOT* W, MINB)
 stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
 {
@@ -630,7 +633,9 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   // loads are issued before the first is consumed (two dependent memory round trips per pass)
   constexpr int N2 = N * N, ND = N2 * N, NT = SLOT * W, NDP = ndp_of<N>();
   constexpr int U = 21;
-  constexpr int GW = Cfg<N>::GW; // planes of G held in registers (rotating window, see g_multiply)
+  // planes of G held in registers (rotating window, see g_multiply).  fp32 has the registers for the
+  // whole next cell and is faster with it (P4: 0.271 vs 0.307 ms); fp64 uses the per-degree window.
+  constexpr int GW = sizeof(T) == 4 ? N : Cfg<N>::GW;
   using V2 = typename Vec2<T>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* xl = reinterpret_cast<T*>(smem_raw);
@@ -659,7 +664,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   pdl_launch_dependents(); // the next colour may start staging; it waits before touching y
   PhaseTimer tm;
   tm.start(threadIdx.x % 32 == 0);
-  const int b = a.batch_ids ? __ldg(a.batch_ids + batch0 + blockIdx.x) : batch0 + (int)blockIdx.x;
+  const int b = IDS ? __ldg(a.batch_ids + batch0 + blockIdx.x) : batch0 + (int)blockIdx.x;
   WFX_DEV_ASSERT(b >= 0 && b < a.nbatches);
   // batch header: arithmetic when the plan is uniform (saves a memory round trip), else loaded
   const int64_t d0 = a.uni_nloc ? (int64_t)b * a.uni_nloc : __ldg(a.dof_off + b);
@@ -862,7 +867,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
       // cells' G, the batch's dof list and its local dofmap -- what that CTA waits for first.
       if (r == nr - 1 && col == 0 && (int)blockIdx.x + a.pf_stride < (int)gridDim.x)
       {
-        const int bn = a.batch_ids ? __ldg(a.batch_ids + batch0 + blockIdx.x + a.pf_stride) : b + a.pf_stride;
+        const int bn = IDS ? __ldg(a.batch_ids + batch0 + blockIdx.x + a.pf_stride) : b + a.pf_stride;
         const int r0n = a.uni_nr ? bn * a.uni_nr : __ldg(a.round_off + bn);
         if constexpr ((6 * ND * sizeof(T)) % 16 == 0 && !AFF)
         {
@@ -991,7 +996,13 @@ template <> struct Cfg<4> { static constexpr int SLOT = 16, W = 8, BX = 4, BY = 
 #define WFX_P7_GW 4
 #endif
 #ifndef WFX_P6_MINB
-#define WFX_P6_MINB 5
+#define WFX_P6_MINB 4 // five CTAs per SM cap the kernel at 168 registers and it spills ~100 B; four: 0 B, 0.606 -> 0.524 ms
+#endif
+#ifndef WFX_P7_BZ
+#define WFX_P7_BZ 2
+#endif
+#ifndef WFX_P6_BZ
+#define WFX_P6_BZ 2
 #endif
 #ifndef WFX_P7_MINB
 #define WFX_P7_MINB 3
@@ -1010,8 +1021,8 @@ template <> struct Cfg<5> { static constexpr int SLOT = 32, W = WFX_P4_W, BX = W
 #define WFX_P5_CARVE 58
 #endif
 template <> struct Cfg<6> { static constexpr int SLOT = 64, W = WFX_P5_W, BX = WFX_P5_BX, BY = 2, BZ = 2, CPB = 4, MINB = WFX_P5_MINB, CARVEOUT = WFX_P5_CARVE, CARVEOUT32 = 0, GW = WFX_P5_GW; };
-template <> struct Cfg<7> { static constexpr int SLOT = 64, W = 1, BX = 2, BY = 2, BZ = 2, CPB = 4, MINB = WFX_P6_MINB, CARVEOUT = 72, CARVEOUT32 = 58, GW = WFX_P6_GW; };
-template <> struct Cfg<8> { static constexpr int SLOT = 64, W = 1, BX = 2, BY = 2, BZ = 2, CPB = 2, MINB = WFX_P7_MINB, CARVEOUT = 0, CARVEOUT32 = 0, GW = WFX_P7_GW; };
+template <> struct Cfg<7> { static constexpr int SLOT = 64, W = 1, BX = 2, BY = 2, BZ = WFX_P6_BZ, CPB = 4, MINB = WFX_P6_MINB, CARVEOUT = 72, CARVEOUT32 = 58, GW = WFX_P6_GW; };
+template <> struct Cfg<8> { static constexpr int SLOT = 64, W = 1, BX = 2, BY = 2, BZ = WFX_P7_BZ, CPB = 2, MINB = WFX_P7_MINB, CARVEOUT = 0, CARVEOUT32 = 0, GW = WFX_P7_GW; };
 
 struct LaunchCfg
 {
@@ -1202,9 +1213,10 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
     {
       // regular batches with the regular-brick kernel, the rest with the generic one; the two
       // launches of a colour touch disjoint dofs and chain like colours do
-      launch(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>>, op->smem_bytes_reg + smem_pad,
+      launch(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>, false, true>, op->smem_bytes_reg + smem_pad,
              op->reg_off[k], op->reg_off[k + 1] - op->reg_off[k], op->d_reg_ids.p);
-      launch(kern_gen, op->smem_bytes + smem_pad, op->irr_off[k], op->irr_off[k + 1] - op->irr_off[k], op->d_irr_ids.p);
+      launch(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N>, false, true>, op->smem_bytes + smem_pad,
+             op->irr_off[k], op->irr_off[k + 1] - op->irr_off[k], op->d_irr_ids.p);
     }
     else launch(kern, smem, op->colour_off[k], op->colour_off[k + 1] - op->colour_off[k], nullptr);
   }
@@ -1221,6 +1233,10 @@ void configure_brick(wfx_stiffness* op)
   WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>, true>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>, false, true>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N>, false, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   if constexpr (N == 5 && sizeof(T) == 8)
     WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutP4D>,
