@@ -39,7 +39,10 @@ enum { WFX_F64 = 0, WFX_F32 = 1 };
 /* stiffness kernel selection (wfx_stiffness_create flags) */
 enum {
   WFX_STIFF_AUTO = 0,       /* brick-batched kernel when the plan supports it */
-  WFX_STIFF_CELL_COLOUR = 1 /* simple per-cell kernel, coloured cells, global read-modify-write */
+  WFX_STIFF_CELL_COLOUR = 1, /* simple per-cell kernel, coloured cells, global read-modify-write */
+  WFX_STIFF_NO_SPLIT = 2     /* (or-ed in) distributed meshes: do not schedule the interface batches as
+                                a part of their own; the apply is then one pass and the ghost reduction
+                                follows it (best when the reduction is cheap: NVLink peer memory) */
 };
 
 typedef struct wfx_ctx wfx_ctx;

@@ -61,6 +61,18 @@ def whole():
     stiff.apply_part(x, y, -1, beta=0, scale_ptr=minv)
 
 
+# the same operator without the interface / interior split: one pass, then the ghost reduction
+flat = wfx.StiffnessOperator(mesh, P, ctx=ctx, geometry=geo, split=False)
+
+
+def flat_all():
+    flat.apply_part(x, y, -1, beta=0, scale_ptr=minv)
+
+
+def flat_serial():
+    flat_all(); ghost()
+
+
 def timeit(f, n=20):
     for _ in range(5):
         f()
@@ -78,9 +90,10 @@ def timeit(f, n=20):
 
 info = stiff.info()
 res = {k: timeit(f) for k, f in [("interface", iface), ("interior", interior), ("ghost", ghost),
-                                 ("all batches, no halo", whole), ("serial", serial), ("overlapped", overlapped)]}
+                                 ("all batches, no halo", whole), ("serial", serial), ("overlapped", overlapped),
+                                 ("unsplit plan, no halo", flat_all), ("unsplit plan + ghost", flat_serial)]}
 if rank == 0:
-    print(f"ranks {world} grid {grid} launches {info['nlaunches']}")
+    print(f"ranks {world} grid {grid} launches {info['nlaunches']} halo transport {halo.transport}")
     for k, v in res.items():
         print(f"  {k:24s} {v * 1e3:8.1f} us")
 dist.destroy_process_group()

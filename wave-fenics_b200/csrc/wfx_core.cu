@@ -3,8 +3,31 @@
 
 #include <nvtx3/nvToolsExt.h>
 
+#include <chrono>
+#include <cstdlib>
+
 using namespace wfx;
 
+namespace
+{
+double wall_now()
+{
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+} // namespace
+wfx::SetupTimer::SetupTimer(const char* w) : what(w), last(wall_now())
+{
+  const char* e = std::getenv("WFX_VERBOSE");
+  on = e && std::atoi(e) != 0;
+}
+void wfx::SetupTimer::lap(const char* phase)
+{
+  if (!on) return;
+  cudaDeviceSynchronize();
+  const double t = wall_now();
+  std::fprintf(stderr, "[wfx setup] %-22s %-28s %8.3f s\n", what, phase, t - last);
+  last = t;
+}
 wfx::NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
 wfx::NvtxRange::~NvtxRange() { nvtxRangePop(); }
 

@@ -257,6 +257,7 @@ extern "C" int wfx_geometry_create(wfx_ctx* ctx, int P, int dtype, int64_t ncell
   g->nq = nq;
   g->dtype = dtype;
   g->ncells = ncells;
+  SetupTimer timer("geometry_create");
   for (int64_t i = 0; i < ncells * 8; ++i)
     if (xdofs_host[i] < 0 || xdofs_host[i] >= npts) fail("geometry dofmap entry out of range");
   g->centroid.resize((size_t)ncells * 3);
@@ -267,7 +268,9 @@ extern "C" int wfx_geometry_create(wfx_ctx* ctx, int P, int dtype, int64_t ncell
       for (int v = 0; v < 8; ++v) s += x_host[3 * (int64_t)xdofs_host[8 * c + v] + a];
       g->centroid[3 * c + a] = (float)(s / 8);
     }
+  timer.lap("checks + centroids");
   if (!std::getenv("WFX_NO_CONNECTIVITY_COORDS")) structured_cell_coords(ncells, npts, xdofs_host, g->cell_ijk);
+  timer.lap("connectivity coordinates");
   if (ncells > 0)
   {
     const size_t esz = dtype == WFX_F64 ? 8 : 4;
@@ -299,6 +302,7 @@ extern "C" int wfx_geometry_create(wfx_ctx* ctx, int P, int dtype, int64_t ncell
     std::vector<uint8_t> fl((size_t)ncells);
     WFX_CUDA(cudaMemcpy(fl.data(), g->affine, (size_t)ncells, cudaMemcpyDeviceToHost));
     for (uint8_t f : fl) g->n_affine += f;
+    timer.lap("G, detJ, affine detection");
   }
   *out = guard.release();
   WFX_API_END

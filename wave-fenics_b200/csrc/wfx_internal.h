@@ -121,6 +121,16 @@ struct NvtxRange
   ~NvtxRange();
 };
 
+// Set-up phase timer: WFX_VERBOSE=1 prints the seconds spent per phase of the create calls to stderr.
+struct SetupTimer
+{
+  explicit SetupTimer(const char* what);
+  void lap(const char* phase);
+  const char* what;
+  double last;
+  bool on;
+};
+
 struct ScopedDevice
 {
   int prev = -1;

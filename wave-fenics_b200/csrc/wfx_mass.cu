@@ -186,11 +186,14 @@ extern "C" int wfx_mass_create(wfx_ctx* ctx, wfx_geom* geom, int64_t ndofs,
     if (!dofmap_host) fail("dofmap is NULL");
     // m = M.1 (LinearGLL.hpp:102-110): m[dof(c,perm[t])] += detJ[c,t], cells in order.
     // The k-major tensor dofmap indexes dJw directly.
+    SetupTimer timer("mass_create");
     std::vector<int32_t> tdm;
     build_tensor_dofmap(geom->P, geom->ncells, ndofs, dofmap_host, tdm);
+    timer.lap("tensor dofmap");
     wfx_scatter_plan plan;
     plan.ctx = ctx;
     build_scatter_plan(&plan, (int64_t)tdm.size(), tdm.data(), ndofs);
+    timer.lap("scatter plan");
     segsum_kernel<double, double><<<(unsigned)((ndofs + 255) / 256), 256>>>(
         ndofs, plan.d_off.p, plan.d_src.p, geom->dJw, op->d_m64.p, 0);
     WFX_CUDA(cudaGetLastError());

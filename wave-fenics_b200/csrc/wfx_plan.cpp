@@ -80,12 +80,12 @@ Strides find_strides(int P, const BrickShape& brick, int word_bytes, bool tuned)
 }
 } // namespace
 
-void parallel_for(int64_t n, const std::function<void(int64_t, int64_t)>& fn)
+void parallel_for(int64_t n, const std::function<void(int64_t, int64_t)>& fn, int64_t min_parallel)
 {
   int nt = (int)std::thread::hardware_concurrency();
   if (const char* e = std::getenv("WFX_HOST_THREADS")) nt = std::atoi(e);
   nt = std::max(1, std::min(nt, 32));
-  if (n < 4096 || nt == 1)
+  if (n < min_parallel || nt == 1)
   {
     fn(0, n);
     return;
@@ -263,7 +263,7 @@ void verify_cell_colour_plan(const CellColourPlan& plan, int nd, int64_t ncells,
 void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
                       const float* centroid, BrickShape brick, int W, int nloc_cap,
                       BrickPlan& plan, const uint8_t* dof_shared, int word_bytes, bool allow_tuned,
-                      const int32_t* cell_ijk_in)
+                      const int32_t* cell_ijk_in, bool split_parts)
 {
   const int n = P + 1, nd = n * n * n;
   if (ndofs > (int64_t)BD_MASK) fail("brick plan: more than 2^30 local dofs");
@@ -281,6 +281,15 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
   plan.ncells = ncells;
   plan.ndofs = ndofs;
 
+  const bool verbose = std::getenv("WFX_VERBOSE") && std::atoi(std::getenv("WFX_VERBOSE")) > 1;
+  auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double tlast = tnow();
+  auto lap = [&](const char* what) {
+    if (!verbose) return;
+    const double t = tnow();
+    std::fprintf(stderr, "[wfx plan] %-28s %8.3f s\n", what, t - tlast);
+    tlast = t;
+  };
   // ---- 1. spatial keys -------------------------------------------------------
   std::vector<uint64_t> key((size_t)ncells);
   std::vector<uint32_t> parity((size_t)ncells, 0);
@@ -346,6 +355,7 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
 
+  lap("keys + sort");
   // ---- 2. batches: runs of equal brick key, capacity-limited --------------------
   struct Batch
   {
@@ -405,6 +415,7 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
   const int nb = (int)batches.size();
   plan.nbatches = nb;
 
+  lap("batches + capacity");
   // ---- 3. batch colouring (greedy; the brick-coordinate parity is tried first, which
   //         gives the optimal 8 colours on structured meshes) ------------------------
   std::vector<uint64_t> dofmask((size_t)ndofs, 0);
@@ -445,7 +456,7 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
   // batches) run first so that the halo exchange of those dofs can overlap the interior
   // batches.  Execution colour = part * ncol + colour, part 0 = interface, 1 = interior.
   plan.part_split = 0;
-  if (dof_shared)
+  if (dof_shared && split_parts)
   {
     for (auto& b : batches)
     {
@@ -468,27 +479,36 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
   for (auto& b : batches) plan.colour_off[b.colour + 1]++;
   for (int c = 0; c < ncol; ++c) plan.colour_off[c + 1] += plan.colour_off[c];
 
-  // first / last (execution) colour touching each dof
+  lap("batch colouring");
+  // first / last (execution) colour touching each dof.  Batches of one colour share no dof, so the
+  // batches of a colour are processed by several host threads without conflicts.
   std::vector<int16_t> cmin((size_t)ndofs, 32767), cmax((size_t)ndofs, -1);
-  for (auto& b : batches)
-    for (int64_t p = b.begin; p < b.end; ++p)
-    {
-      const int32_t* d = tdm + (int64_t)order[p] * nd;
-      for (int t = 0; t < nd; ++t)
+  for (int col = 0; col < ncol; ++col)
+    parallel_for(plan.colour_off[col + 1] - plan.colour_off[col], [&](int64_t q0, int64_t q1) {
+      for (int64_t q = q0; q < q1; ++q)
       {
-        cmin[d[t]] = std::min<int16_t>(cmin[d[t]], (int16_t)b.colour);
-        cmax[d[t]] = std::max<int16_t>(cmax[d[t]], (int16_t)b.colour);
+        const Batch& b = batches[plan.colour_off[col] + q];
+        for (int64_t p = b.begin; p < b.end; ++p)
+        {
+          const int32_t* d = tdm + (int64_t)order[p] * nd;
+          for (int t = 0; t < nd; ++t)
+          {
+            cmin[d[t]] = std::min<int16_t>(cmin[d[t]], (int16_t)b.colour);
+            cmax[d[t]] = std::max<int16_t>(cmax[d[t]], (int16_t)b.colour);
+          }
+        }
       }
-    }
+    }, 64);
   for (int64_t i = 0; i < ndofs; ++i)
     if (cmax[i] < 0) plan.untouched.push_back((int32_t)i);
 
+  lap("first / last colours");
   // ---- 4. per-batch dof lists, rounds and local dofmaps ---------------------------
+  // Again colour by colour on several host threads: the batches of a colour touch disjoint entries of
+  // the global -> local scratch map.  Every batch fills its own output; the plan arrays are the
+  // concatenation in batch order, so the result does not depend on the number of threads.
   plan.dof_off.assign(nb + 1, 0);
   plan.round_off.assign(nb + 1, 0);
-  std::vector<uint64_t> lmask;
-  std::vector<int> ccol, place;
-  std::vector<uint8_t> slot_used;
   const bool have_coords = !cell_ijk.empty();
   // Off by default: the 7 % padding pushes two resident CTAs over the 196 KB shared-memory
   // carve-out step, L1 shrinks from 60 to 28 KB and the kernel loses 20 % (measured, round 1) --
@@ -498,12 +518,23 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
   const Strides lay = have_coords ? find_strides(P, brick, word_bytes, want_tuned) : Strides();
   plan.Sx = lay.Sx;
   plan.Sy = lay.Sy;
-  for (int i = 0; i < nb; ++i)
+  struct BatchOut
   {
+    std::vector<uint32_t> bdofs;
+    std::vector<int32_t> slot_cell;
+    std::vector<uint16_t> slot_base, ldm;
+    int nrounds = 0, nslots = 0, n_private = 0;
+    uint8_t regular = 0;
+  };
+  std::vector<BatchOut> outs((size_t)nb);
+  const int ndp = plan.ndp;
+  auto process = [&](int i, std::vector<int32_t>& uq, std::vector<int>& place, std::vector<uint64_t>& lmask,
+                     std::vector<int>& ccol, std::vector<uint8_t>& slot_used) {
     const Batch& b = batches[i];
+    BatchOut& o = outs[i];
     const int nc = (int)(b.end - b.begin);
     // unique dofs, ascending
-    uniq.clear();
+    uq.clear();
     for (int64_t p = b.begin; p < b.end; ++p)
     {
       const int32_t* d = tdm + (int64_t)order[p] * nd;
@@ -511,13 +542,13 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
         if (g2l[d[t]] < 0)
         {
           g2l[d[t]] = 1;
-          uniq.push_back(d[t]);
+          uq.push_back(d[t]);
         }
     }
-    std::sort(uniq.begin(), uniq.end());
-    int nloc = (int)uniq.size();
+    std::sort(uq.begin(), uq.end());
+    int nloc = (int)uq.size();
     if (nloc > 65535) fail("brick plan: batch with %d dofs exceeds 16-bit local index", nloc);
-    for (int l = 0; l < nloc; ++l) g2l[uniq[l]] = l;
+    for (int l = 0; l < nloc; ++l) g2l[uq[l]] = l;
     // Placement of the batch dofs in the shared arrays.  Default: ascending global dof.  If the
     // batch is a regular brick (every dof gets one consistent lattice coordinate from the
     // integer cell coordinates and the tensor index of its points), place dof (X,Y,Z) at
@@ -525,12 +556,13 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
     // (one lane per (i,j)) is free of shared-memory bank conflicts; unused positions are holes.
     place.assign(nloc, -1);
     int nslots = nloc;
+    bool regular = false;
     if (have_coords && lay.ok)
     {
       int org[3] = {1 << 30, 1 << 30, 1 << 30};
       for (int64_t p = b.begin; p < b.end; ++p)
         for (int a = 0; a < 3; ++a) org[a] = std::min(org[a], cell_ijk[3 * (int64_t)order[p] + a]);
-      bool regular = true;
+      regular = true;
       for (int64_t p = b.begin; p < b.end && regular; ++p)
       {
         const int32_t c = order[p];
@@ -569,28 +601,24 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
         nslots = nloc;
         place.assign(nloc, -1);
       }
-      else plan.n_regular++;
-      plan.batch_regular.push_back(regular ? 1 : 0);
     }
-    else plan.batch_regular.push_back(0);
+    o.regular = regular ? 1 : 0;
     if (place.empty() || (nloc > 0 && place[0] < 0))
       for (int l = 0; l < nloc; ++l) place[l] = l;
-    plan.nloc_max = std::max(plan.nloc_max, nslots);
-    const size_t base = plan.bdofs.size();
-    plan.bdofs.resize(base + nslots, BD_HOLE);
+    o.nslots = nslots;
+    o.bdofs.assign((size_t)nslots, BD_HOLE);
     for (int l = 0; l < nloc; ++l)
     {
-      const int32_t d = uniq[l];
+      const int32_t d = uq[l];
       uint32_t e = (uint32_t)d;
       if (cmin[d] == b.colour) e |= BD_FIRST;
       // shared dofs are complete only after the halo sum: never LAST (no fused scaling) here
       if (cmax[d] == b.colour && !(dof_shared && dof_shared[d])) e |= BD_LAST;
-      if ((e & BD_FIRST) && (e & BD_LAST)) plan.n_private++;
-      plan.bdofs[base + place[l]] = e;
+      if ((e & BD_FIRST) && (e & BD_LAST)) o.n_private++;
+      o.bdofs[place[l]] = e;
       g2l[d] = place[l]; // local index used by the cells = position in the shared arrays
     }
     nloc = nslots;
-    plan.dof_off[i + 1] = (int64_t)plan.bdofs.size();
     // colour the batch's cells so that cells of one round share no local dof
     lmask.assign(nloc, 0);
     ccol.assign(nc, 0);
@@ -606,7 +634,6 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
       ccol[q] = col;
       nlc = std::max(nlc, col + 1);
     }
-    int nrounds = 0;
     for (int col = 0; col < nlc; ++col)
     {
       int filled = 0;
@@ -615,26 +642,61 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
         if (ccol[q] != col) continue;
         if (filled == 0)
         {
-          plan.slot_cell.resize(plan.slot_cell.size() + W, -1);
-          plan.slot_base.resize(plan.slot_base.size() + W, 0);
-          plan.ldm.resize(plan.ldm.size() + (size_t)W * plan.ndp, 0);
-          ++nrounds;
+          o.slot_cell.resize(o.slot_cell.size() + W, -1);
+          o.slot_base.resize(o.slot_base.size() + W, 0);
+          o.ldm.resize(o.ldm.size() + (size_t)W * ndp, 0);
+          ++o.nrounds;
         }
-        const size_t slot = plan.slot_cell.size() - W + filled;
+        const size_t slot = o.slot_cell.size() - W + filled;
         const int32_t cell = order[b.begin + q];
-        plan.slot_cell[slot] = cell;
+        o.slot_cell[slot] = cell;
         const int32_t* d = tdm + (int64_t)cell * nd;
-        for (int t = 0; t < nd; ++t) plan.ldm[slot * plan.ndp + t] = (uint16_t)g2l[d[t]];
+        for (int t = 0; t < nd; ++t) o.ldm[slot * ndp + t] = (uint16_t)g2l[d[t]];
         // position of the cell's origin corner (point i=j=k=0): for a regular brick every other
         // point of the cell is at a fixed offset from it (ascpos(i)*Sx + ascpos(j)*Sy + ascpos(k))
-        plan.slot_base[slot] = (uint16_t)g2l[d[0]];
+        o.slot_base[slot] = (uint16_t)g2l[d[0]];
         filled = (filled + 1) % W;
       }
     }
-    plan.round_off[i + 1] = plan.round_off[i] + nrounds;
-    plan.rounds_max = std::max(plan.rounds_max, nrounds);
-    for (int32_t d : uniq) g2l[d] = -1;
+    for (int32_t d : uq) g2l[d] = -1;
+  };
+  for (int col = 0; col < ncol; ++col)
+    parallel_for(plan.colour_off[col + 1] - plan.colour_off[col], [&](int64_t q0, int64_t q1) {
+      std::vector<int32_t> uq;
+      std::vector<int> place, ccol;
+      std::vector<uint64_t> lmask;
+      std::vector<uint8_t> slot_used;
+      for (int64_t q = q0; q < q1; ++q) process(plan.colour_off[col] + (int)q, uq, place, lmask, ccol, slot_used);
+    }, 64);
+  lap("per-batch lists (threads)");
+  // concatenate in batch order
+  {
+    size_t nbd = 0, nsl = 0;
+    for (const BatchOut& o : outs) nbd += o.bdofs.size(), nsl += o.slot_cell.size();
+    plan.bdofs.reserve(nbd + 4);
+    plan.slot_cell.reserve(nsl);
+    plan.slot_base.reserve(nsl);
+    plan.ldm.reserve(nsl * (size_t)ndp);
+    plan.batch_regular.reserve((size_t)nb);
+    for (int i = 0; i < nb; ++i)
+    {
+      BatchOut& o = outs[i];
+      plan.bdofs.insert(plan.bdofs.end(), o.bdofs.begin(), o.bdofs.end());
+      plan.slot_cell.insert(plan.slot_cell.end(), o.slot_cell.begin(), o.slot_cell.end());
+      plan.slot_base.insert(plan.slot_base.end(), o.slot_base.begin(), o.slot_base.end());
+      plan.ldm.insert(plan.ldm.end(), o.ldm.begin(), o.ldm.end());
+      plan.dof_off[i + 1] = (int64_t)plan.bdofs.size();
+      plan.round_off[i + 1] = plan.round_off[i] + o.nrounds;
+      plan.rounds_max = std::max(plan.rounds_max, o.nrounds);
+      plan.nloc_max = std::max(plan.nloc_max, o.nslots);
+      plan.n_private += o.n_private;
+      plan.n_regular += o.regular;
+      plan.batch_regular.push_back(have_coords && lay.ok ? o.regular : 0);
+      BatchOut().bdofs.swap(o.bdofs); // release as we go
+      std::vector<uint16_t>().swap(o.ldm);
+    }
   }
+  lap("concatenate");
   plan.nrounds_total = plan.round_off[nb];
   plan.n_slots_padded = plan.nrounds_total * W - ncells;
   // the tuned strides only pay off when every batch runs the regular-brick kernel; otherwise
@@ -643,7 +705,7 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
   {
     BrickPlan compact;
     build_brick_plan(P, ncells, ndofs, tdm, centroid, brick, W, nloc_cap, compact, dof_shared, word_bytes, false,
-                     cell_ijk_in);
+                     cell_ijk_in, split_parts);
     plan = std::move(compact);
   }
 }

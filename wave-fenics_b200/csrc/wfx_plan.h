@@ -78,13 +78,16 @@ struct BrickShape
 bool structured_cell_coords(int64_t ncells, int64_t npts, const int32_t* xdofs, std::vector<int32_t>& ijk);
 
 // runs fn(begin, end) on slices of [0, n) with the host's hardware threads
-void parallel_for(int64_t n, const std::function<void(int64_t, int64_t)>& fn);
+void parallel_for(int64_t n, const std::function<void(int64_t, int64_t)>& fn, int64_t min_parallel = 4096);
 
 // tdm: tensor-ordered dofmap in the kernels' k-major point order, [ncells][nd]
 void build_cell_colour_plan(int nd, int64_t ncells, int64_t ndofs, const int32_t* tdm,
                             CellColourPlan& plan);
 
 // centroid: [ncells][3] or nullptr (then cells are batched in the given order).
+// dof_shared: [ndofs] flags of dofs that also live on another rank: never marked LAST (their scaling
+// waits for the ghost reduction); with split_parts the batches touching them get their own, earlier
+// execution colours (interface part) so that the reduction can overlap the interior part.
 // cell_ijk: [ncells][3] exact integer grid coordinates (structured_cell_coords) or nullptr; preferred
 // over coordinates estimated from the centroids (which assume a roughly uniform axis-aligned grid).
 // brick: cells per brick along each axis (batch capacity = their product); nloc_cap: capacity of
@@ -92,7 +95,7 @@ void build_cell_colour_plan(int nd, int64_t ncells, int64_t ndofs, const int32_t
 void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
                       const float* centroid, BrickShape brick, int W, int nloc_cap,
                       BrickPlan& plan, const uint8_t* dof_shared = nullptr, int word_bytes = 8,
-                      bool allow_tuned = true, const int32_t* cell_ijk = nullptr);
+                      bool allow_tuned = true, const int32_t* cell_ijk = nullptr, bool split_parts = true);
 
 // Checks every invariant the kernels rely on; throws wfx::Error on violation.
 void verify_brick_plan(const BrickPlan& plan, const int32_t* tdm, const uint8_t* dof_shared = nullptr);

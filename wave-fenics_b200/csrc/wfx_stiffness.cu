@@ -1334,15 +1334,18 @@ void build_tensor_dofmap(int P, int64_t ncells, int64_t ndofs, const int32_t* do
   std::vector<int32_t> perm(nd);
   tensor_perm(P, perm.data());
   tdm.resize((size_t)ncells * nd);
-  for (int64_t c = 0; c < ncells; ++c)
-    for (int i = 0; i < n; ++i)
-      for (int j = 0; j < n; ++j)
-        for (int k = 0; k < n; ++k)
-        {
-          const int32_t d = dofmap[c * nd + perm[(i * n + j) * n + k]];
-          if (d < 0 || d >= ndofs) fail("dofmap entry %d out of range [0,%lld)", d, (long long)ndofs);
-          tdm[c * nd + k * n2 + i * n + j] = d;
-        }
+  int32_t* out = tdm.data();
+  parallel_for(ncells, [&](int64_t c0, int64_t c1) {
+    for (int64_t c = c0; c < c1; ++c)
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j)
+          for (int k = 0; k < n; ++k)
+          {
+            const int32_t d = dofmap[c * nd + perm[(i * n + j) * n + k]];
+            if (d < 0 || d >= ndofs) fail("dofmap entry %d out of range [0,%lld)", d, (long long)ndofs);
+            out[c * nd + k * n2 + i * n + j] = d;
+          }
+  });
 }
 } // namespace wfx
 
@@ -1384,7 +1387,10 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
   if (geom->ctx != ctx) fail("geometry belongs to another context");
   if (ndofs < 0) fail("negative ndofs");
   if (ndofs >= (1ll << 31)) fail("more than 2^31 local dofs");
+  bool split_parts = !(flags & WFX_STIFF_NO_SPLIT);
+  flags &= ~WFX_STIFF_NO_SPLIT;
   if (flags != WFX_STIFF_AUTO && flags != WFX_STIFF_CELL_COLOUR) fail("unknown stiffness flags %d", flags);
+  if (const char* e = std::getenv("WFX_SPLIT")) split_parts = std::atoi(e) != 0;
   ScopedDevice sd(ctx->device);
   auto op = std::make_unique<wfx_stiffness>();
   op->ctx = ctx;
@@ -1407,8 +1413,10 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
   if (op->ncells > 0)
   {
     if (!dofmap_host) fail("dofmap is NULL");
+    SetupTimer timer("stiffness_create");
     std::vector<int32_t> tdm;
     build_tensor_dofmap(op->P, op->ncells, ndofs, dofmap_host, tdm);
+    timer.lap("tensor dofmap");
     if (flags == WFX_STIFF_CELL_COLOUR)
     {
       build_cell_colour_plan(op->nd, op->ncells, ndofs, tdm.data(), op->cplan);
@@ -1435,7 +1443,8 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
       build_brick_plan(op->P, op->ncells, ndofs, tdm.data(),
                        geom->centroid.empty() ? nullptr : geom->centroid.data(), be, lc.W, nloc_cap, bp,
                        shared.empty() ? nullptr : shared.data(), (int)esz, true,
-                       geom->cell_ijk.empty() ? nullptr : geom->cell_ijk.data());
+                       geom->cell_ijk.empty() ? nullptr : geom->cell_ijk.data(), split_parts);
+      timer.lap("brick plan");
       op->ncolours = bp.ncolours;
       op->part_split = bp.part_split;
       op->colour_off = bp.colour_off;
@@ -1521,6 +1530,7 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
       if (!bp.untouched.empty()) op->d_untouched.upload(bp.untouched);
       if (op->dtype == WFX_F64) configure_any<double>(op.get());
       else configure_any<float>(op.get());
+      timer.lap("uploads + configure");
     }
   }
   *out = op.release();

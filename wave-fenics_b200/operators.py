@@ -141,7 +141,7 @@ class StiffnessOperator(_Operator):
     honour_params=True."""
 
     def __init__(self, V, degree, params=None, dtype=np.float64, ctx=None, geometry=None,
-                 mode=capi.STIFF_AUTO, honour_params=False):
+                 mode=capi.STIFF_AUTO, honour_params=False, split=True):
         self.ctx = ctx or Context.get()
         self.P = int(degree)
         self.dtype = np.dtype(dtype)
@@ -160,7 +160,9 @@ class StiffnessOperator(_Operator):
             shared = np.unique(np.concatenate([halo["send_indices"], halo["recv_indices"]])).astype(np.int32)
         self.nshared = 0 if shared is None else len(shared)
         capi.call("wfx_stiffness_create_partitioned", self.ctx.handle, self.geometry.handle, self.ndofs,
-                  capi.i32p(dm.reshape(-1)), c0, mode, self.nshared, capi.i32p(shared), C.byref(self.handle))
+                  capi.i32p(dm.reshape(-1)), c0, mode | (0 if split else capi.STIFF_NO_SPLIT), self.nshared,
+                  capi.i32p(shared), C.byref(self.handle))
+        self.split = bool(split) and self.nshared > 0
 
     def __call__(self, x, y):
         self.apply(x, y, beta=1)
