@@ -564,7 +564,8 @@ def test_stiffness_interface_interior_split(wfx, orc, torch):
 
 # ---- kernel variants behind environment switches stay correct -----------------------------------
 @pytest.mark.gpu
-@pytest.mark.parametrize("env", [{"WFX_REGULAR": "0"}, {"WFX_TUNED_STRIDES": "1"}, {"WFX_NO_UNIFORM": "1"}])
+@pytest.mark.parametrize("env", [{"WFX_REGULAR": "0"}, {"WFX_TUNED_STRIDES": "1"}, {"WFX_NO_UNIFORM": "1"},
+                                 {"WFX_PERSISTENT": "1"}, {"WFX_PERSISTENT": "1", "WFX_NO_UNIFORM": "1"}])
 def test_stiffness_kernel_variants(wfx, orc, torch, monkeypatch, env):
     """The generic (staged local dofmap) kernel, the conflict-free P4 layout with reordered G columns
     and the loaded batch headers are not the default on structured meshes: force each and compare
@@ -583,6 +584,21 @@ def test_stiffness_kernel_variants(wfx, orc, torch, monkeypatch, env):
     op = wfx.StiffnessOperator(mesh, P, {"c0": 1500.0}, geometry=geo)
     y = torch.full_like(y_ref, float("nan"))
     op.apply(dev(torch, x), y, beta=0)
+    if "WFX_PERSISTENT" in env:
+        assert op.info()["nlaunches"] == 1
+        # the single-launch form in a time loop (not graph-replayed: its epoch is a kernel argument)
+        eqn_a = wfx.LinearGLLOpt(mesh, None, P, 1500.0, 0.5e6, 6e4)
+        eqn_a.init()
+        dtw = wfx.cfl_timestep(mesh.h_min, 1500.0, P, 0.5e6)
+        eqn_a.rk4(0.0, 1.0, dtw, max_steps=12)
+        ua, va = eqn_a.get_state()
+        for k in env:
+            monkeypatch.delenv(k)
+        eqn_b = wfx.LinearGLLOpt(mesh, None, P, 1500.0, 0.5e6, 6e4)
+        eqn_b.init()
+        eqn_b.rk4(0.0, 1.0, dtw, max_steps=12)
+        ub, vb = eqn_b.get_state()
+        assert np.abs(ub).max() > 0 and np.array_equal(ua, ub) and np.array_equal(va, vb)
     if "WFX_TUNED_STRIDES" in env:
         assert rel_l2(y.cpu().numpy(), y_ref.cpu().numpy()) < 1e-14
         # the geometry's columns were reordered in place: the exported G must not change

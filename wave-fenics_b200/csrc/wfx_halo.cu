@@ -90,7 +90,7 @@ struct wfx_comm
 
 namespace
 {
-constexpr int P2P_CTAS = 32;     // CTAs of the fused exchange kernel = flags per neighbour and direction
+constexpr int P2P_CTAS = 64;     // CTAs of the fused exchange kernel = flags per neighbour and direction
 constexpr int P2P_THREADS = 256;
 constexpr int P2P_MAXR = 64;     // largest communicator the peer-memory transport handles
 
@@ -247,15 +247,29 @@ __global__ void __launch_bounds__(P2P_THREADS)
 halo_p2p_kernel(const P2PArgs<T> a)
 {
   const int cta = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
+  constexpr int U = 8; // independent elements per thread and pass: the index -> value -> store chains
+                       // are latency-bound, so all loads of a pass are issued before the first store
+  const int stride = G * P2P_THREADS;
   // 1. ghost partial sums -> their owners' receive buffers
   for (int n = 0; n < a.n_recv_nbr; ++n)
   {
     const int beg = a.recv_off[n], end = a.recv_off[n + 1];
     T* dst = a.rbuf_dst[n];
-    for (int i = beg + cta * P2P_THREADS + tid; i < end; i += G * P2P_THREADS)
+    for (int i0 = beg + cta * P2P_THREADS + tid; i0 < end; i0 += U * stride)
     {
-      WFX_DEV_ASSERT(a.recv_idx[i] >= 0 && a.recv_idx[i] < a.n);
-      dst[i - beg] = a.x[a.recv_idx[i]];
+      int32_t idx[U];
+      T v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) idx[u] = i0 + u * stride < end ? a.recv_idx[i0 + u * stride] : -1;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+      {
+        WFX_DEV_ASSERT(idx[u] < a.n);
+        v[u] = idx[u] >= 0 ? a.x[idx[u]] : T(0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (idx[u] >= 0) dst[i0 + u * stride - beg] = v[u];
     }
   }
   __threadfence_system();
@@ -266,24 +280,48 @@ halo_p2p_kernel(const P2PArgs<T> a)
     while ((int32_t)(ld_acquire_sys(a.rflags + f) - a.epoch) < 0) __nanosleep(32);
   __syncthreads();
   // 3. owner: add in neighbour order, scale, keep, and hand the finished value to every holder
-  for (int64_t j = cta * P2P_THREADS + tid; j < a.nuniq; j += (int64_t)G * P2P_THREADS)
+  for (int64_t j0 = cta * P2P_THREADS + tid; j0 < a.nuniq; j0 += (int64_t)U * stride)
   {
-    const int32_t d = a.uniq[j];
-    WFX_DEV_ASSERT(d >= 0 && d < a.n);
-    T s = a.x[d];
-    const int64_t p0 = a.useg_off[j], p1 = a.useg_off[j + 1];
-    for (int64_t p = p0; p < p1; ++p)
+    int32_t d[U];
+    int64_t p0[U], p1[U];
+    T s[U], sc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
     {
-      WFX_DEV_ASSERT(a.useg_src[p] >= 0 && a.useg_src[p] < a.nsend);
-      s += ld_peer_written(a.rbuf + a.useg_src[p]);
+      const int64_t j = j0 + (int64_t)u * stride;
+      const bool ok = j < a.nuniq;
+      d[u] = ok ? a.uniq[j] : -1;
+      p0[u] = ok ? a.useg_off[j] : 0;
+      p1[u] = ok ? a.useg_off[j + 1] : 0;
     }
-    if (a.scale) s *= a.scale[d];
-    a.x[d] = s;
-    for (int64_t p = p0; p < p1; ++p)
+#pragma unroll
+    for (int u = 0; u < U; ++u)
     {
-      const int32_t q = a.useg_src[p];
-      const int n = a.slot_nbr[q];
-      a.fbuf_dst[n][q - a.send_off[n]] = s;
+      WFX_DEV_ASSERT(d[u] < a.n);
+      s[u] = d[u] >= 0 ? a.x[d[u]] : T(0);
+      sc[u] = (d[u] >= 0 && a.scale) ? a.scale[d[u]] : T(1);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      for (int64_t p = p0[u]; p < p1[u]; ++p)
+      {
+        WFX_DEV_ASSERT(a.useg_src[p] >= 0 && a.useg_src[p] < a.nsend);
+        s[u] += ld_peer_written(a.rbuf + a.useg_src[p]); // neighbour order: bitwise equal to the NCCL path
+      }
+      s[u] *= sc[u];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      if (d[u] < 0) continue;
+      a.x[d[u]] = s[u];
+      for (int64_t p = p0[u]; p < p1[u]; ++p)
+      {
+        const int32_t q = a.useg_src[p];
+        const int n = a.slot_nbr[q];
+        a.fbuf_dst[n][q - a.send_off[n]] = s[u];
+      }
     }
   }
   __threadfence_system();
@@ -294,8 +332,21 @@ halo_p2p_kernel(const P2PArgs<T> a)
     while ((int32_t)(ld_acquire_sys(a.fflags + f) - a.epoch) < 0) __nanosleep(32);
   __syncthreads();
   // 5. unpack
-  for (int64_t i = cta * P2P_THREADS + tid; i < a.nrecv; i += (int64_t)G * P2P_THREADS)
-    a.x[a.recv_idx[i]] = ld_peer_written(a.fbuf + i);
+  for (int64_t i0 = cta * P2P_THREADS + tid; i0 < a.nrecv; i0 += (int64_t)U * stride)
+  {
+    int32_t idx[U];
+    T v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const int64_t i = i0 + (int64_t)u * stride;
+      idx[u] = i < a.nrecv ? a.recv_idx[i] : -1;
+      v[u] = i < a.nrecv ? ld_peer_written(a.fbuf + i) : T(0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (idx[u] >= 0) a.x[idx[u]] = v[u];
+  }
 }
 
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + 255) / 256); }

@@ -102,6 +102,7 @@ double clamp_m101(double v);                              // xt::isclose clamp t
 
 int stiffness_dtype(const struct ::wfx_stiffness* op);    // wfx_stiffness.cu
 bool stiffness_has_split(const struct ::wfx_stiffness* op); // interface/interior parts present
+bool stiffness_graph_safe(const struct ::wfx_stiffness* op); // its launches may be captured into a CUDA graph
 int halo_dtype(const struct ::wfx_halo* h);                // wfx_halo.cu
 bool mass_assembled(const struct ::wfx_mass* op);          // wfx_mass.cu: diagonal summed over the ranks
 int mass_dtype(const struct ::wfx_mass* op);

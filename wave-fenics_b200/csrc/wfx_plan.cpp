@@ -697,6 +697,30 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
     }
   }
   lap("concatenate");
+  // write-back dependencies (see wfx_plan.h): one pass over the dof lists in execution order
+  {
+    std::vector<int32_t> last_toucher((size_t)ndofs, -1);
+    plan.dep_off.assign(nb + 1, 0);
+    plan.dep_ids.clear();
+    std::vector<int32_t> deps;
+    for (int i = 0; i < nb; ++i)
+    {
+      deps.clear();
+      for (int64_t l = plan.dof_off[i]; l < plan.dof_off[i + 1]; ++l)
+      {
+        const uint32_t e = plan.bdofs[l];
+        if (e == BD_HOLE) continue;
+        int32_t& lt = last_toucher[e & BD_MASK];
+        if (lt >= 0 && (deps.empty() || deps.back() != lt)) deps.push_back(lt);
+        lt = i;
+      }
+      std::sort(deps.begin(), deps.end());
+      deps.erase(std::unique(deps.begin(), deps.end()), deps.end());
+      plan.dep_ids.insert(plan.dep_ids.end(), deps.begin(), deps.end());
+      plan.dep_off[i + 1] = (int32_t)plan.dep_ids.size();
+    }
+  }
+  lap("write-back dependencies");
   plan.nrounds_total = plan.round_off[nb];
   plan.n_slots_padded = plan.nrounds_total * W - ncells;
   // the tuned strides only pay off when every batch runs the regular-brick kernel; otherwise
@@ -779,6 +803,28 @@ void verify_brick_plan(const BrickPlan& plan, const int32_t* tdm, const uint8_t*
         }
     }
   if (cells_total != ncells) fail("brick plan: %lld of %lld cells covered", (long long)cells_total, (long long)ncells);
+  // write-back dependencies: only on earlier batches, and every pair of batches sharing a dof is
+  // ordered through the chain of last touchers
+  if (!plan.dep_off.empty())
+  {
+    if ((int)plan.dep_off.size() != nb + 1) fail("brick plan: dependency offsets inconsistent");
+    std::vector<int32_t> lt((size_t)ndofs, -1);
+    for (int b = 0; b < nb; ++b)
+    {
+      for (int32_t p = plan.dep_off[b]; p < plan.dep_off[b + 1]; ++p)
+        if (plan.dep_ids[p] < 0 || plan.dep_ids[p] >= b) fail("brick plan: batch %d depends on a later batch", b);
+      for (int64_t l = plan.dof_off[b]; l < plan.dof_off[b + 1]; ++l)
+      {
+        const uint32_t e = plan.bdofs[l];
+        if (e == BD_HOLE) continue;
+        const int32_t prev = lt[e & BD_MASK];
+        if (prev >= 0
+            && !std::binary_search(plan.dep_ids.begin() + plan.dep_off[b], plan.dep_ids.begin() + plan.dep_off[b + 1], prev))
+          fail("brick plan: batch %d misses its dependency on batch %d", b, prev);
+        lt[e & BD_MASK] = b;
+      }
+    }
+  }
   int64_t nunt = 0;
   for (int64_t d = 0; d < ndofs; ++d)
   {

@@ -52,6 +52,11 @@ struct BrickPlan
   std::vector<uint16_t> slot_base; // [nrounds_total*W] position of the cell's origin corner in the batch arrays
   std::vector<uint16_t> ldm;       // [nrounds_total*W][ndp] batch-local dof, k-major point order
   std::vector<int32_t> untouched;  // vector entries no cell references
+  // Write-back dependencies for the single-launch (persistent) kernel: batch b may add to y only
+  // after the batches dep_ids[dep_off[b] .. dep_off[b+1]) have written back -- for every dof of b the
+  // batch that touched it last before b (earlier in the colour-sorted order; its own predecessors are
+  // covered transitively)
+  std::vector<int32_t> dep_off, dep_ids;
   // statistics
   int64_t n_slots_padded = 0;
   int64_t n_private = 0;           // bdofs entries that are FIRST and LAST

@@ -144,6 +144,13 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 #define WFX_DEV_ASSERT(cond) ((void)0)
 #endif
 
+#ifndef WFX_PERSIST_UW
+#define WFX_PERSIST_UW 11
+#endif
+#ifndef WFX_PERSISTENT_DEFAULT
+#define WFX_PERSISTENT_DEFAULT 0
+#endif
+
 template <int N> struct Cfg; // per-degree launch configuration (below)
 
 template <typename T, int N>
@@ -942,6 +949,360 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   tm.flush(b * W + slot);
 }
 
+// ---- product kernel, single-launch form: one resident CTA walks many batches -----------------
+// The multi-launch kernel above pays, around the rounds of every batch, two dependent memory round
+// trips to stage the dofs and two more to write them back, with nothing of its own to overlap them.
+// Here a CTA processes the batches  blockIdx.x, blockIdx.x + gridDim.x, ...  of the colour-sorted
+// list in ONE cooperative launch per apply, and
+//  * as soon as the last round of batch t is done the shared x array is dead: the dof list of the
+//    CTA's next batch is loaded and its gather (cp.async) issued BEFORE batch t is written back, so
+//    the gather's round trip runs under the write-back's;
+//  * the G stream carries across batches (the last round requests the first cell of the next batch);
+//  * colours are ordered inside the launch by per-batch completion flags: a batch adds to y only
+//    after the batches that touched its dofs last (wfx_plan.h, dep_off / dep_ids) have written back
+//    -- a point-to-point wait, not a barrier per colour (the round-1 experiment with per-colour
+//    counters lost for that reason).  Dependencies point to earlier list positions only, every CTA
+//    walks its positions in increasing order and all CTAs are co-resident (cooperative launch), so
+//    the waits cannot deadlock.  Flags hold the apply's epoch and never need resetting.
+// Regular bricks only (REG data path, LayoutStd); the affine form shares it (AFF).
+struct PersistArgs
+{
+  const int32_t* dep_off;
+  const int32_t* dep_ids;
+  uint32_t* done;  // [nbatches] epoch of the last completed write-back
+  uint32_t epoch;
+  int nbatches;
+  uint32_t stagger_ns; // start delay of the second half of the grid (the second CTA of every SM)
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p)
+{
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v)
+{
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <typename T, int N, int SLOT, int W, int MINB, typename L, bool AFF>
+__global__ void __launch_bounds__(SLOT* W, MINB)
+stiff_brick_persist(const BrickArgs<T> a, const PersistArgs pa, const DMat<T, N> Dm)
+{
+  constexpr int N2 = N * N, ND = N2 * N, NT = SLOT * W;
+  constexpr int U = 21;
+  constexpr int GW = sizeof(T) == 4 ? N : Cfg<N>::GW;
+  using V2 = typename Vec2<T>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* xl = reinterpret_cast<T*>(smem_raw);
+  T* yl = xl + a.nloc_pad;
+  T* work = yl + a.nloc_pad;
+  const size_t meta_off = ((size_t)(2 * a.nloc_pad + W * L::SLOT_ELEMS) * sizeof(T) + 15) & ~(size_t)15;
+  int32_t* scell = reinterpret_cast<int32_t*>(smem_raw + meta_off);
+  uint16_t* sbase = reinterpret_cast<uint16_t*>(scell + (size_t)a.rounds_max * W);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + ((meta_off + (size_t)a.rounds_max * W * 6 + 7) & ~(size_t)7));
+#ifndef WFX_NO_SPLIT_BARRIER
+  constexpr bool SPLIT = SLOT <= 32 && (SLOT * W) % 32 == 0 && SLOT * W > 32;
+#else
+  constexpr bool SPLIT = false;
+#endif
+  uint64_t* rbar = bar + 1;
+  const int tid = threadIdx.x;
+  const int slot = tid / SLOT, col = tid % SLOT;
+  const bool lane_ok = col < N2;
+  const RoleOff ro = L::offsets(lane_ok ? col : 0);
+  const int gcol = g_column<L, N>(ro, lane_ok ? col : 0, a.g_order);
+  const int P1 = N - 1;
+  auto apos = [P1](int q) { return q == 0 ? 0 : (q == 1 ? P1 : q - 1); };
+  const int offK = apos(ro.iK) * a.Sx + apos(ro.jK) * a.Sy;
+  const int offJ = apos(ro.iJ) * a.Sx + apos(ro.kJ);
+  const int offI = apos(ro.jI) * a.Sy + apos(ro.kI);
+  T* tiles = work + slot * L::SLOT_ELEMS;
+  PhaseTimer tm;
+  tm.start(tid % 32 == 0);
+
+  if (SPLIT && tid == 0) mbar_init(rbar, NT / 32);
+  for (int l = tid; l < a.nloc_pad; l += NT) yl[l] = T(0); // kept zero by every write-back
+  __syncthreads();
+
+  // batch header: arithmetic when the plan is uniform, else loaded
+  auto header = [&](int b, int64_t& d0, int& nloc, int& r0, int& nr) {
+    d0 = a.uni_nloc ? (int64_t)b * a.uni_nloc : __ldg(a.dof_off + b);
+    nloc = a.uni_nloc ? a.uni_nloc : (int)(__ldg(a.dof_off + b + 1) - d0);
+    r0 = a.uni_nr ? b * a.uni_nr : __ldg(a.round_off + b);
+    nr = a.uni_nr ? a.uni_nr : __ldg(a.round_off + b + 1) - r0;
+    WFX_DEV_ASSERT(b >= 0 && b < pa.nbatches && nloc >= 0 && nloc <= a.nloc_pad && nr >= 0 && nr <= a.rounds_max);
+  };
+  // issue the staging of batch b: dof list -> registers -> asynchronous gather into xl; slot tables.
+  // Completion is awaited with cp.async.wait_all + __syncthreads at the top of the batch loop.
+  auto stage = [&](int b) {
+    int64_t d0;
+    int nloc, r0, nr;
+    header(b, d0, nloc, r0, nr);
+    uint32_t e[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) e[q] = tid + q * NT < nloc ? ld_once(a.bdofs + d0 + tid + q * NT) : BD_HOLE;
+    const int nslots = nr * W;
+    for (int v = tid; v < nslots; v += NT)
+    {
+      scell[v] = __ldg(a.slot_cell + (int64_t)r0 * W + v);
+      sbase[v] = __ldg(a.slot_base + (int64_t)r0 * W + v);
+    }
+#pragma unroll
+    for (int q = 0; q < U; ++q)
+    {
+      WFX_DEV_ASSERT(e[q] == BD_HOLE || (int64_t)(e[q] & BD_MASK) < a.ndofs);
+      if (e[q] != BD_HOLE) cp_async_scalar(xl + tid + q * NT, a.x + (e[q] & BD_MASK));
+    }
+    for (int base = tid + NT * U; base < nloc; base += NT * U)
+    {
+#pragma unroll
+      for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? ld_once(a.bdofs + d0 + base + q * NT) : BD_HOLE;
+#pragma unroll
+      for (int q = 0; q < U; ++q)
+        if (e[q] != BD_HOLE) cp_async_scalar(xl + base + q * NT, a.x + (e[q] & BD_MASK));
+    }
+  };
+
+  // The two CTAs of an SM must not walk their phases in lock step: one of them in its rounds while the
+  // other stages / writes back is what two CTAs per SM are for.  Separate launches desynchronise by
+  // themselves (a CTA starts when a slot frees); here the second half of the grid starts late.
+  if (pa.stagger_ns && blockIdx.x >= (gridDim.x + 1) / 2)
+  {
+    for (uint32_t w = 0; w < pa.stagger_ns; w += 1000) __nanosleep(1000);
+  }
+  int t = blockIdx.x;
+  V2 g[GW][3];
+  T ga[6], csk[N];
+  if constexpr (AFF)
+  {
+    T wi = 0, wj = 0;
+#pragma unroll
+    for (int q = 0; q < N; ++q)
+    {
+      if (q == ro.iK) wi = Dm.w[q];
+      if (q == ro.jK) wj = Dm.w[q];
+    }
+    const T wij = a.coeff * wi * wj;
+#pragma unroll
+    for (int k = 0; k < N; ++k) csk[k] = wij * Dm.w[k];
+  }
+  if (t < pa.nbatches)
+  {
+    int64_t d0;
+    int nloc, r0, nr;
+    header(t, d0, nloc, r0, nr);
+    const int c0 = nr > 0 ? __ldg(a.slot_cell + (int64_t)r0 * W + slot) : -1;
+    if constexpr (AFF)
+    {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) ga[q] = c0 >= 0 ? __ldg(a.Gc + (int64_t)c0 * 6 + q) : T(0);
+    }
+    else
+    {
+      if constexpr ((6 * ND * sizeof(T)) % 16 == 0)
+        if (col == 0 && c0 >= 0) l2_prefetch_bulk(a.G6 + (int64_t)c0 * (6 * ND), (uint32_t)(6 * ND * sizeof(T)));
+      if (lane_ok && c0 >= 0) load_G<T, N, GW>(a.G6 + (int64_t)c0 * (6 * ND), gcol, g);
+    }
+    stage(t);
+  }
+  uint32_t phase_base = 0; // round-barrier phases completed so far (one per round but the last of a batch)
+  for (; t < pa.nbatches; t += gridDim.x)
+  {
+    const int tn = t + gridDim.x;
+    int64_t d0;
+    int nloc, r0, nr;
+    header(t, d0, nloc, r0, nr);
+    // the first cells of this CTA's next batch (G stream and L2 prefetch carry across batches)
+    int r0n = 0, nrn = 0;
+    if (tn < pa.nbatches)
+    {
+      int64_t d0n;
+      int nlocn;
+      header(tn, d0n, nlocn, r0n, nrn);
+    }
+    const int cn_first = nrn > 0 ? __ldg(a.slot_cell + (int64_t)r0n * W + slot) : -1;
+    const int cn_second = nrn > 1 ? __ldg(a.slot_cell + (int64_t)(r0n + 1) * W + slot) : -1;
+    cp_async_wait_all();
+    __syncthreads(); // the staged dofs and slot tables of batch t are visible
+    tm.mark(0);
+    // the dof lists this CTA walks next (write-back of t, staging of tn): keep them in L2
+    if (tid == 0)
+    {
+      const int64_t dn = d0 & ~(int64_t)3;
+      l2_prefetch_bulk(a.bdofs + dn, (uint32_t)(((d0 + nloc + 3) & ~(int64_t)3) - dn) * 4u);
+    }
+    if (tid == 32 && tn < pa.nbatches)
+    {
+      int64_t d0n;
+      int nlocn, q0, q1;
+      header(tn, d0n, nlocn, q0, q1);
+      const int64_t dn = d0n & ~(int64_t)3;
+      l2_prefetch_bulk(a.bdofs + dn, (uint32_t)(((d0n + nlocn + 3) & ~(int64_t)3) - dn) * 4u);
+    }
+    // G of the second round to L2 (the first round's was requested by the previous batch)
+    if constexpr (!AFF && (6 * ND * sizeof(T)) % 16 == 0)
+      if (col == 0 && nr > 1)
+      {
+        const int c1 = scell[W + slot];
+        if (c1 >= 0) l2_prefetch_bulk(a.G6 + (int64_t)c1 * (6 * ND), (uint32_t)(6 * ND * sizeof(T)));
+      }
+
+    for (int r = 0; r < nr; ++r)
+    {
+      const int cell = scell[r * W + slot];
+      WFX_DEV_ASSERT(cell < a.ncells);
+      const bool active = lane_ok && cell >= 0;
+      const int cn = r + 1 < nr ? scell[(r + 1) * W + slot] : cn_first;
+      int li[N];
+      T u[N], yv[N], f2[N];
+      // (the G registers do not carry across the batch boundary: the write-back needs them; the next
+      // batch's first cell is requested right after it and is an L2 hit by then)
+      const V2* gnext = (!AFF && cn >= 0 && r + 1 < nr) ? reinterpret_cast<const V2*>(a.G6 + (int64_t)cn * (6 * ND)) + gcol : nullptr;
+      const V2* gcur = (!AFF && cell >= 0) ? reinterpret_cast<const V2*>(a.G6 + (int64_t)cell * (6 * ND)) + gcol : nullptr;
+      T gan[6];
+      if constexpr (AFF)
+      {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) gan[q] = cn >= 0 ? __ldg(a.Gc + (int64_t)cn * 6 + q) : T(0);
+      }
+      const int base = active ? (int)sbase[r * W + slot] : 0;
+      T lj[N], lI[N];
+#pragma unroll
+      for (int m = 0; m < N; ++m)
+      {
+        constexpr int P0 = N - 1;
+        const int am = m == 0 ? 0 : (m == 1 ? P0 : m - 1);
+        li[m] = base + offK + am;
+        WFX_DEV_ASSERT(!active || (li[m] >= 0 && li[m] < nloc && base + offJ + am * a.Sy < nloc && base + offI + am * a.Sx < nloc));
+        u[m] = active ? xl[li[m]] : T(0);
+        lj[m] = active ? xl[base + offJ + am * a.Sy] : T(0);
+        lI[m] = active ? xl[base + offI + am * a.Sx] : T(0);
+        yv[m] = 0;
+      }
+      if constexpr (AFF)
+      {
+        if constexpr (SLOT <= 32) cell_part1_reg_affine<T, N, L>(u, lj, lI, ga, csk, tiles, ro, Dm, active, WarpSync(), f2, tm);
+        else cell_part1_reg_affine<T, N, L>(u, lj, lI, ga, csk, tiles, ro, Dm, active, BlockSync(), f2, tm);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) ga[q] = gan[q];
+      }
+      else if constexpr (SLOT <= 32) cell_part1_reg<T, N, L, GW>(u, lj, lI, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2, tm, gcur, gnext);
+      else cell_part1_reg<T, N, L, GW>(u, lj, lI, g, tiles, ro, Dm, a.coeff, active, BlockSync(), f2, tm, gcur, gnext);
+      if constexpr (!AFF)
+      {
+        // a slot that was idle in this round has requested nothing: load the next cell's window now
+        if (lane_ok && cn >= 0 && !active && r + 1 < nr) load_G<T, N, GW>(a.G6 + (int64_t)cn * (6 * ND), gcol, g);
+        // keep the L2 prefetch PF_DIST rounds ahead of the register loads, across the batch boundary
+        if constexpr ((6 * ND * sizeof(T)) % 16 == 0)
+          if (col == 0)
+          {
+            const int rr = r + 1 + PF_DIST;
+            const int c2 = rr < nr ? scell[rr * W + slot] : (rr == nr ? cn_first : (rr == nr + 1 ? cn_second : -1));
+            if (c2 >= 0) l2_prefetch_bulk(a.G6 + (int64_t)c2 * (6 * ND), (uint32_t)(6 * ND * sizeof(T)));
+          }
+      }
+      tm.mark(4);
+      if constexpr (SLOT <= 32) cell_part2<T, N, L>(f2, tiles, ro, Dm, active, WarpSync(), yv, tm);
+      else cell_part2<T, N, L>(f2, tiles, ro, Dm, active, BlockSync(), yv, tm);
+      if constexpr (SPLIT)
+        if (r > 0) mbar_wait(rbar, (phase_base + r - 1) & 1);
+      if (active)
+      {
+#pragma unroll
+        for (int k = 0; k < N; ++k) yl[li[k]] += yv[k];
+      }
+      tm.mark(6);
+      if constexpr (SPLIT)
+      {
+        __syncwarp();
+        if (r + 1 < nr && tid % 32 == 0) mbar_arrive(rbar);
+      }
+      else __syncthreads();
+      tm.mark(7);
+    }
+    if constexpr (SPLIT)
+    {
+      __syncthreads();
+      if (nr > 0) phase_base += nr - 1;
+    }
+    // xl and the slot tables are dead.  Write this batch back and stage the next one in the same passes,
+    // the write-back's loads in front: issued behind the ~5000 scattered gather requests of a staging
+    // they would wait for those to drain (measured: the write-back took 4x longer that way).
+    int64_t d0n = 0;
+    int nlocn = 0;
+    if (tn < pa.nbatches)
+    {
+      int q0, q1;
+      header(tn, d0n, nlocn, q0, q1);
+      for (int v = tid; v < q1 * W; v += NT)
+      {
+        scell[v] = __ldg(a.slot_cell + (int64_t)q0 * W + v);
+        sbase[v] = __ldg(a.slot_base + (int64_t)q0 * W + v);
+      }
+    }
+    tm.mark(10);
+    // the batches that touched my dofs last have written back
+    {
+      const int q0 = __ldg(pa.dep_off + t), q1 = __ldg(pa.dep_off + t + 1);
+      for (int q = q0 + tid; q < q1; q += NT)
+      {
+        const uint32_t* f = pa.done + __ldg(pa.dep_ids + q);
+        while ((int32_t)(ld_acquire_gpu(f) - pa.epoch) < 0) __nanosleep(64);
+      }
+    }
+    __syncthreads();
+    tm.mark(8);
+    constexpr int UW = WFX_PERSIST_UW;
+    const int nmax = nloc > nlocn ? nloc : nlocn;
+    for (int base = tid; base < nmax; base += NT * UW)
+    {
+      uint32_t e[UW], en[UW];
+      T v[UW], sc[UW];
+#pragma unroll
+      for (int q = 0; q < UW; ++q)
+      {
+        e[q] = base + q * NT < nloc ? ld_once(a.bdofs + d0 + base + q * NT) : BD_HOLE;
+        en[q] = base + q * NT < nlocn ? ld_once(a.bdofs + d0n + base + q * NT) : BD_HOLE;
+      }
+#pragma unroll
+      for (int q = 0; q < UW; ++q)
+      {
+        const bool ok = e[q] != BD_HOLE;
+        const uint32_t dof = e[q] & BD_MASK;
+        WFX_DEV_ASSERT(!ok || (int64_t)dof < a.ndofs);
+        // y is written by other SMs inside this launch: read it at L2
+        v[q] = (ok && (!(e[q] & BD_FIRST) || a.beta)) ? __ldcg(a.y + dof) : T(0);
+        sc[q] = (ok && (e[q] & BD_LAST) && a.scale) ? ld_once(a.scale + dof) : T(1);
+      }
+#pragma unroll
+      for (int q = 0; q < UW; ++q)
+      {
+        WFX_DEV_ASSERT(en[q] == BD_HOLE || (int64_t)(en[q] & BD_MASK) < a.ndofs);
+        if (en[q] != BD_HOLE) cp_async_scalar(xl + base + q * NT, a.x + (en[q] & BD_MASK));
+      }
+#pragma unroll
+      for (int q = 0; q < UW; ++q)
+        if (base + q * NT < nloc)
+        {
+          if (e[q] != BD_HOLE) a.y[e[q] & BD_MASK] = (v[q] + yl[base + q * NT]) * sc[q];
+          yl[base + q * NT] = T(0);
+        }
+    }
+    if constexpr (!AFF)
+      if (lane_ok && cn_first >= 0) load_G<T, N, GW>(a.G6 + (int64_t)cn_first * (6 * ND), gcol, g);
+    __syncthreads(); // every thread's stores to y precede the flag; yl is zero for the next batch
+    tm.mark(9);
+    if (tid == 0)
+    {
+      __threadfence();
+      st_release_gpu(pa.done + t, pa.epoch);
+    }
+  }
+  tm.flush(blockIdx.x * W + slot);
+}
+
 template <typename T>
 __global__ void zero_entries_kernel(const int32_t* __restrict__ idx, int n, T* __restrict__ y)
 {
@@ -1088,6 +1449,12 @@ struct wfx_stiffness
   int n_regular = 0, nbatches = 0;
   std::vector<int32_t> reg_off, irr_off; // [ncolours+1] into d_reg_ids / d_irr_ids
   DevBuf<int32_t> d_reg_ids, d_irr_ids;
+  // single-launch (persistent) form: write-back dependencies, completion flags, apply counter
+  bool persistent = false;
+  int persist_grid = 0;
+  uint32_t epoch = 0;
+  DevBuf<int32_t> d_dep_off, d_dep_ids;
+  DevBuf<uint32_t> d_done;
   int Sx = 0, Sy = 0;
   size_t smem_bytes_reg = 0;
   DevBuf<uint16_t> d_slot_base;
@@ -1184,6 +1551,36 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   // interface part has batches at all -- otherwise the kernel in front of us is x's producer.
   // (A property of the plan, not of the call history: the operator keeps no per-apply state and
   // may be applied from several streams.)
+  // single-launch form: whole applies of all-regular plans (not the interface / interior parts)
+  if (op->persistent && part == -1 && variant == 1)
+  {
+    using PK = void (*)(BrickArgs<T>, PersistArgs, DMat<T, N>);
+    PK pk = op->affine ? (PK)stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N>, true>
+                       : (PK)stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N>, false>;
+    if (op->persist_grid == 0)
+    {
+      int occ = 0;
+      WFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pk, C::SLOT * C::W, op->smem_bytes_reg));
+      if (occ < 1) fail("stiffness: the single-launch kernel does not fit on an SM");
+      op->persist_grid = std::min(op->nbatches, occ * op->ctx->num_sms);
+      if (const char* e = std::getenv("WFX_PERSIST_GRID")) op->persist_grid = std::min(op->persist_grid, std::atoi(e));
+      if (std::getenv("WFX_VERBOSE"))
+        std::fprintf(stderr, "[wfx] single-launch kernel: %d CTAs per SM, grid %d, %d batches, %zu B shared memory\n", occ,
+                     op->persist_grid, op->nbatches, op->smem_bytes_reg);
+    }
+    PersistArgs pa;
+    pa.dep_off = op->d_dep_off.p;
+    pa.dep_ids = op->d_dep_ids.p;
+    pa.done = op->d_done.p;
+    pa.epoch = ++op->epoch;
+    pa.nbatches = op->nbatches;
+    static const uint32_t stagger = std::getenv("WFX_STAGGER_NS") ? (uint32_t)std::atoi(std::getenv("WFX_STAGGER_NS")) : 15000u;
+    pa.stagger_ns = stagger;
+    void* args[] = {(void*)&a, (void*)&pa, (void*)&Dm};
+    WFX_CUDA(cudaLaunchCooperativeKernel((void*)pk, dim3(op->persist_grid), dim3(C::SLOT * C::W), args,
+                                         op->smem_bytes_reg, st));
+    return;
+  }
   const bool iface_nonempty = op->part_split > 0 && op->colour_off[op->part_split] > op->colour_off[0];
   bool first = !(part == 1 && iface_nonempty);
   // execution colours of the requested part: interface batches [0, part_split), interior the rest
@@ -1238,6 +1635,10 @@ void configure_brick(wfx_stiffness* op)
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N>, false, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N>, false>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N>, true>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   if constexpr (N == 5 && sizeof(T) == 8)
     WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutP4D>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
@@ -1252,6 +1653,10 @@ void configure_brick(wfx_stiffness* op)
     WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>, true>,
+                                  cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N>, false>,
+                                  cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N>, true>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, carve));
   }
 }
@@ -1325,6 +1730,8 @@ namespace wfx
 {
 int stiffness_dtype(const wfx_stiffness* op) { return op->dtype; }
 bool stiffness_has_split(const wfx_stiffness* op) { return op->part_split > 0; }
+// the single-launch form passes a per-apply epoch as a kernel argument: not replayable from a graph
+bool stiffness_graph_safe(const wfx_stiffness* op) { return !op->persistent; }
 
 // tensor-ordered dofmap in the kernels' k-major point order
 void build_tensor_dofmap(int P, int64_t ncells, int64_t ndofs, const int32_t* dofmap,
@@ -1514,6 +1921,17 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
           op->mixed = true;
         }
       }
+      // single-launch form (all-regular plans): dependencies and completion flags
+      op->d_dep_off.upload(bp.dep_off);
+      op->d_dep_ids.upload(bp.dep_ids);
+      op->d_done.alloc((size_t)std::max(1, bp.nbatches));
+      WFX_CUDA(cudaMemset(op->d_done.p, 0, op->d_done.n * sizeof(uint32_t)));
+      {
+        int coop = 0;
+        WFX_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+        op->persistent = op->variant == 1 && coop != 0 && WFX_PERSISTENT_DEFAULT;
+        if (const char* e = std::getenv("WFX_PERSISTENT")) op->persistent = op->variant == 1 && coop != 0 && std::atoi(e) != 0;
+      }
       // structured fast path: every cell affine and every batch a lattice brick
       op->affine = op->variant == 1 && geom->n_affine == op->ncells;
       if (const char* e = std::getenv("WFX_AFFINE")) op->affine = op->affine && std::atoi(e) != 0;
@@ -1670,7 +2088,7 @@ extern "C" int wfx_stiffness_info(wfx_stiffness* op, int64_t* num_cells, int* nu
                         : (double)op->ncells * op->nd * (6 * s + 4) + (double)op->ndofs * 3 * s;
   const int nc = op->mode == WFX_STIFF_CELL_COLOUR ? op->cplan.ncolours : op->ncolours;
   if (ncolours) *ncolours = nc;
-  if (nlaunches) *nlaunches = nc;
+  if (nlaunches) *nlaunches = (op->persistent && op->mode != WFX_STIFF_CELL_COLOUR) ? 1 : nc;
   WFX_API_END
 }
 

@@ -435,7 +435,7 @@ extern "C" int wfx_wave_rk4(wfx_wave* w, double t0, double tf, double dt, int64_
   // Graph replay (one rank only: the distributed step spans two streams and NCCL).  A capture
   // cannot run on the legacy default stream: such callers are moved to an internal stream that
   // is ordered after and before the caller's stream by events.
-  const bool graph_ok = w->use_graph && !w->halo;
+  const bool graph_ok = w->use_graph && !w->halo && stiffness_graph_safe(w->stiff);
   cudaStream_t ws = st;
   if (graph_ok && (st == nullptr || st == cudaStreamLegacy))
   {
