@@ -544,7 +544,9 @@ def run_b200(args):
             "windows_ms": win_ms, "window_ms_min": min(win_ms), "window_ms_max": max(win_ms),
             "clocks": clocks, "sustained": sustained, "parity": parity, "affine_fast_path": affine,
             "e2e": e2e,
-            "gpu_launches": (args.windows * args.steps) * (info["nlaunches"] + (0 if halo is None else 5)),
+            # per apply: the colour launches of the brick kernel + the ghost reduction (one fused kernel over
+            # peer memory; pack, unpack-add, pack, unpack around two NCCL groups otherwise)
+            "gpu_launches": (args.windows * args.steps) * (info["nlaunches"] + (0 if halo is None else (1 if halo_transport == "p2p" else 4))),
             "roofline": roofline, "cpu_baseline": cpu, "rk4": rk4, "strong_scaling": strong}
     print(json.dumps(line))
     if world > 1:

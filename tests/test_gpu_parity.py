@@ -293,6 +293,43 @@ def test_ragged_mesh_mixed_plan_vs_oracle(wfx, orc, torch, N):
     assert torch.equal(y, y2)
 
 
+def test_config5_size_ragged_rim_vs_oracle(wfx, orc, torch):
+    """BASELINE config 5's per-GPU size, 133^3 cells (151 M dofs; 133 = 33 * 4 + 1: full bricks plus a
+    one-cell ragged rim per axis), at full size.  The whole mesh does not fit the CPU oracle's memory, so
+    the comparison is exact where it can be: the reference's dense skernel is applied to the slab of the
+    last five cell layers in x (which contains the ragged rim and full bricks), and every dof strictly
+    inside that slab -- touched by no cell outside it -- must agree with the GPU apply of the whole mesh."""
+    import copy
+    P, N = 4, 133
+    mesh = wfx.create_box_hex(N, P, (L, L, L), perturb=0.15)
+    assert mesh.ndofs == 151419437
+    geo = wfx.Geometry(mesh, P)
+    op = wfx.StiffnessOperator(mesh, P, geometry=geo)
+    ki = op.kernel_info()
+    assert ki["variant"] == "brick-regular" and ki["regular_batches"] == ki["batches"] == 34 ** 3
+    g = torch.Generator(device="cuda").manual_seed(42)
+    xd = torch.randn(mesh.ndofs, dtype=torch.float64, device="cuda", generator=g)
+    y = torch.full((mesh.ndofs,), float("nan"), dtype=torch.float64, device="cuda")
+    op.apply(xd, y, beta=0)
+    del geo
+    x = xd.cpu().numpy()
+    yg = y.cpu().numpy()
+    del xd, y, op
+    torch.cuda.empty_cache()
+    cx0 = 128
+    sel = np.arange(cx0 * N * N, N * N * N)                    # cells c = (cx*N + cy)*N + cz with cx >= 128
+    sub = copy.copy(mesh)
+    sub.xdofs = np.ascontiguousarray(mesh.xdofs[sel])
+    sub.dofmap = np.ascontiguousarray(mesh.dofmap[sel])
+    Go, _ = orc.precompute_geometric_data(sub, P)
+    yo = np.zeros(mesh.ndofs)
+    orc.stiffness_apply(sub, P, Go, x, yo, dense=True, nthreads=_host_threads())
+    M = P * N + 1
+    inside = np.arange((cx0 * P + 1) * M * M, mesh.ndofs)      # lattice planes X > 4 * 128 (lexicographic dofs)
+    assert np.isfinite(yg).all()
+    assert rel_l2(yg[inside], yo[inside]) < TOL64
+
+
 # ---- f2: affine / structured fast path -------------------------------------------------------------
 @pytest.mark.parametrize("P,N,dtype", [(4, 8, np.float64), (2, 16, np.float64), (3, 8, np.float64), (5, 4, np.float64),
                                        (4, 8, np.float32)])
