@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and the
 cpu_baseline / --impl reference legs of bench.py.  Never imported by the product package.
-PARITY UNPINNED (see the header of wave_oracle.c).
+PARITY UNPINNED for the C restatement (see the header of wave_oracle.c); the reference's own CUDA
+primitives, the one part of the path that compiles here, are available through ref_cuda().
 """
 import ctypes as C
 import hashlib
@@ -83,6 +84,26 @@ def lib(fast=False):
             f.restype, f.argtypes = res, args
         _libs[fast] = L
     return _libs[fast]
+
+
+def ref_cuda():
+    """ctypes handle of oracle/_ref/libwfref_cuda.so -- the REFERENCE's own CUDA primitives (gather,
+    atomic scatter, transform1; common/cuda/scatter.cu, transform.cu) compiled from /root/reference by
+    oracle/build_ref.py -- or None when it has not been built.  Device pointers, default stream,
+    synchronous (the reference calls cudaDeviceSynchronize after every launch)."""
+    from . import build_ref
+    path = build_ref.build()
+    if not path or not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    vp, i32 = C.c_void_p, C.c_int32
+    for name in ("ref_gather_f64", "ref_gather_f32", "ref_scatter_f64", "ref_scatter_f32"):
+        getattr(L, name).argtypes = [i32, vp, vp, vp]
+        getattr(L, name).restype = None
+    for name in ("ref_transform1_f64", "ref_transform1_f32"):
+        getattr(L, name).argtypes = [i32, vp, vp, vp]
+        getattr(L, name).restype = None
+    return L
 
 
 def _f(a):

@@ -766,3 +766,63 @@ def test_stiffness_repeatable_under_concurrent_load(wfx, torch):
             op.apply_scaled(x, mass.inverse_diagonal_ptr(), y)
             assert torch.equal(y, ref), f"apply {it} differs ({op.kernel_info()})"
         side.synchronize()
+
+
+# ---- the reference's own CUDA primitives (oracle/_ref, compiled from /root/reference) ----------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_primitives_against_the_reference_cuda_kernels(wfx, orc, torch, dtype):
+    """wfx_gather, wfx_scatter_add and the diagonal mass apply against the REFERENCE's kernels themselves:
+    gather / scatter (common/cuda/scatter.cu) and SpectralMassOperator::apply = gather -> transform1 ->
+    scatter (common/cuda/spectral_mass.hpp:84-89), compiled from the reference sources into oracle/_ref."""
+    import ctypes as C
+    ref = orc.ref_cuda()
+    if ref is None:
+        pytest.skip("oracle/_ref/libwfref_cuda.so was not built (needs /root/reference at build time)")
+    sfx = "f64" if dtype == np.float64 else "f32"
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    code = wfx.capi.dtype_code(dtype)
+    capi, ctx = wfx.capi, wfx.Context.get()
+    P = 4
+    mesh = _mesh(wfx, 6, P, 0.15, renumber=4)
+    tdm = np.ascontiguousarray(wfx.capi.reorder_dofmap(mesh.dofmap, P).reshape(-1), dtype=np.int32)  # permute.hpp:10-28
+    n = tdm.size
+    idx = torch.from_numpy(tdm).cuda()
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(mesh.ndofs, dtype=tdt, device="cuda", generator=g)
+    # gather: bit-identical
+    xe_ref, xe = torch.empty(n, dtype=tdt, device="cuda"), torch.empty(n, dtype=tdt, device="cuda")
+    getattr(ref, "ref_gather_" + sfx)(n, ptr(idx), ptr(x), ptr(xe_ref))
+    capi.call("wfx_gather", ctx.handle, code, n, ptr(idx), ptr(x), ptr(xe), None)
+    torch.cuda.synchronize()
+    assert torch.equal(xe, xe_ref)
+    # scatter-add: the reference adds with atomicAdd in arbitrary order -- exact for integer-valued data,
+    # to rounding for random data
+    plan = C.c_void_p()
+    capi.call("wfx_scatter_plan_create", ctx.handle, n, capi.i32p(tdm), mesh.ndofs, C.byref(plan))
+    for vals, exact in ((torch.randint(-8, 9, (n,), device="cuda", generator=g).to(tdt), True),
+                        (torch.randn(n, dtype=tdt, device="cuda", generator=g), False)):
+        y_ref = torch.zeros(mesh.ndofs, dtype=tdt, device="cuda")
+        y = torch.zeros_like(y_ref)
+        getattr(ref, "ref_scatter_" + sfx)(n, ptr(idx), ptr(vals), ptr(y_ref))
+        capi.call("wfx_scatter_add", plan, code, ptr(vals), ptr(y), 1, None)
+        torch.cuda.synchronize()
+        if exact:
+            assert torch.equal(y, y_ref)
+        else:
+            assert float((y - y_ref).norm() / y_ref.norm()) < (1e-15 if dtype == np.float64 else 1e-6)
+    capi.call("wfx_scatter_plan_destroy", plan)
+    # the reference's GPU mass operator: y += scatter(detJ .* gather(x)) in tensor-product dof order
+    geo = wfx.Geometry(mesh, P, dtype=dtype)
+    mass = wfx.MassOperator(mesh, P, dtype=dtype, geometry=geo)
+    _, detJ = orc.precompute_geometric_data(mesh, P)            # [cell][tensor point], = detJ * w (precomputation.hpp:95)
+    dj = torch.from_numpy(np.ascontiguousarray(detJ.reshape(-1))).to("cuda", tdt)
+    y_ref = torch.zeros(mesh.ndofs, dtype=tdt, device="cuda")
+    getattr(ref, "ref_gather_" + sfx)(n, ptr(idx), ptr(x), ptr(xe_ref))
+    getattr(ref, "ref_transform1_" + sfx)(n, ptr(xe_ref), ptr(dj), ptr(xe_ref))
+    getattr(ref, "ref_scatter_" + sfx)(n, ptr(idx), ptr(xe_ref), ptr(y_ref))
+    y = torch.zeros_like(y_ref)
+    mass(x, y)
+    torch.cuda.synchronize()
+    assert float((y - y_ref).norm() / y_ref.norm()) < (1e-14 if dtype == np.float64 else 2e-6)
