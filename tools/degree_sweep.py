@@ -66,23 +66,39 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--degrees", default="2,3,4,5,6,7")
     ap.add_argument("--no-tsmm", action="store_true", help="skip the dense-GEMM comparator")
+    ap.add_argument("--mode", default="auto", choices=("auto", "cell"),
+                    help="cell: the simple cell-colour kernel + a separate 1/m pass (experiment)")
+    ap.add_argument("--cells", default="", help="override cells per axis, e.g. 5:52,7:36")
     args = ap.parse_args()
     peak = 6538.6
     pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peak = json.load(open(pk))["hbm_gbs"]
     rows = []
+    cells = dict(CELLS)
+    for kv in filter(None, args.cells.split(",")):
+        cells[int(kv.split(":")[0])] = int(kv.split(":")[1])
     for P in [int(p) for p in args.degrees.split(",")]:
-        N = CELLS[P]
+        N = cells[P]
         mesh = wfx.create_box_hex(N, P, (L, L, L), perturb=0.15)
         for dt, tdt in ((np.float64, torch.float64), (np.float32, torch.float32)):
             geo = wfx.Geometry(mesh, P, dt)
-            op = wfx.StiffnessOperator(mesh, P, dtype=dt, geometry=geo)
+            op = wfx.StiffnessOperator(mesh, P, dtype=dt, geometry=geo,
+                                       mode=wfx.capi.STIFF_CELL_COLOUR if args.mode == "cell" else wfx.capi.STIFF_AUTO)
             mass = wfx.MassOperator(mesh, P, dtype=dt, geometry=geo)
             info = op.info()
             x = torch.randn(mesh.ndofs, dtype=tdt, device="cuda")
             y = torch.empty_like(x)
-            ms = time_ms(lambda: op.apply_scaled(x, mass.inverse_diagonal_ptr(), y), args.reps)
+            if args.mode == "cell":
+                b = torch.empty_like(x)
+
+                def run():
+                    b.zero_()
+                    op.apply(x, b, beta=1)
+                    mass.apply_inverse(b, y)
+                ms = time_ms(run, args.reps)
+            else:
+                ms = time_ms(lambda: op.apply_scaled(x, mass.inverse_diagonal_ptr(), y), args.reps)
             # comparator on a slab of the mesh that fits comfortably (dense tables: nd^2 per cell flops);
             # its G comes from a geometry object of the slab's cells only
             ncc = min(mesh.ncells, 32768 if P <= 5 else 8192)
