@@ -40,9 +40,12 @@ enum { WFX_F64 = 0, WFX_F32 = 1 };
 enum {
   WFX_STIFF_AUTO = 0,       /* brick-batched kernel when the plan supports it */
   WFX_STIFF_CELL_COLOUR = 1, /* simple per-cell kernel, coloured cells, global read-modify-write */
-  WFX_STIFF_NO_SPLIT = 2     /* (or-ed in) distributed meshes: do not schedule the interface batches as
+  WFX_STIFF_NO_SPLIT = 2,    /* (or-ed in) distributed meshes: do not schedule the interface batches as
                                 a part of their own; the apply is then one pass and the ghost reduction
                                 follows it (best when the reduction is cheap: NVLink peer memory) */
+  WFX_STIFF_CELL_STREAM = 4  /* streamed-cell kernel: coloured cells, software-pipelined gather, FIRST / LAST
+                                flags in the per-point dofmap (fused scaling, no memset); single-rank meshes.
+                                WFX_STIFF_AUTO takes it by itself at the degrees where it measured faster */
 };
 
 typedef struct wfx_ctx wfx_ctx;

@@ -93,12 +93,17 @@ CASES = [(2, 4, 0.15, None), (2, 9, 0.15, 3), (3, 5, 0.15, None), (4, 4, 0.0, No
          (4, 6, 0.15, 17), (5, 3, 0.15, None), (6, 2, 0.15, 1), (7, 2, 0.15, None)]
 
 
-@pytest.mark.parametrize("mode", ["brick", "cell_colour"])
+@pytest.mark.parametrize("mode", ["brick", "cell_colour", "brick_stream", "colour_stream"])
 @pytest.mark.parametrize("P,N,perturb,renumber", CASES)
-def test_stiffness_matches_dense_reference_kernel(wfx, orc, torch, mode, P, N, perturb, renumber):
+def test_stiffness_matches_dense_reference_kernel(wfx, orc, torch, monkeypatch, mode, P, N, perturb, renumber):
     mesh = _mesh(wfx, N, P, perturb, renumber=renumber)
-    flag = wfx.capi.STIFF_AUTO if mode == "brick" else wfx.capi.STIFF_CELL_COLOUR
+    flag = {"brick": wfx.capi.STIFF_AUTO, "cell_colour": wfx.capi.STIFF_CELL_COLOUR,
+            "brick_stream": wfx.capi.STIFF_CELL_STREAM, "colour_stream": wfx.capi.STIFF_CELL_STREAM}[mode]
+    if mode == "colour_stream":
+        monkeypatch.setenv("WFX_STREAM_ORDER", "colour")
     op = wfx.StiffnessOperator(mesh, P, {"c0": 1500.0}, mode=flag)
+    assert op.kernel_info()["variant"] == {"brick": op.kernel_info()["variant"], "cell_colour": "cell",
+                                           "brick_stream": "brick-streamed", "colour_stream": "cell-streamed"}[mode]
     Go, _ = orc.precompute_geometric_data(mesh, P)
     rng = np.random.default_rng(42)
     x, y0 = rng.standard_normal(mesh.ndofs), rng.standard_normal(mesh.ndofs)
@@ -146,6 +151,51 @@ def test_stiffness_fused_mass_inverse(wfx, orc, torch):
     y = torch.full((mesh.ndofs,), float("nan"), dtype=torch.float64, device="cuda")
     op.apply_scaled(dev(torch, x), mass.inverse_diagonal_ptr(), y)
     assert rel_l2(y.cpu().numpy(), want) < TOL64
+
+
+@pytest.mark.parametrize("order,renumber", [("brick", None), ("brick", 11), ("colour", None), ("colour", 11)])
+@pytest.mark.parametrize("P,N,dtype,cps", [(7, 3, np.float64, 1), (7, 5, np.float64, 4), (6, 3, np.float64, 3),
+                                           (5, 4, np.float64, 2), (4, 5, np.float64, 4), (4, 9, np.float64, 4),
+                                           (7, 3, np.float32, 4), (6, 3, np.float32, 2), (2, 7, np.float64, 5),
+                                           (3, 9, np.float32, 3)])
+def test_streamed_cell_kernel_fused_apply(wfx, orc, torch, monkeypatch, P, N, dtype, cps, order, renumber):
+    """The streamed-cell kernel (stiff_cell2_kernel) through the fused stiffness + mass call, in both cell
+    orders (batches of a brick plan with a round barrier; global colours): FIRST flags (NaN-filled output is
+    never read), LAST flags (1/m applied exactly once per dof), every pipeline depth, ragged meshes (partial
+    bricks, ragged colours), lexicographic dofs (relabelled tensor axes, private G copy) and renumbered dofs
+    (identity axes), a vector with unreferenced entries."""
+    import copy
+    monkeypatch.setenv("WFX_CELL2_CPS", str(cps))
+    monkeypatch.setenv("WFX_STREAM_ORDER", order)
+    mesh = copy.copy(_mesh(wfx, (N, N + 1, N), P, renumber=renumber))
+    mesh.ndofs += 5                                          # entries no cell references
+    geo = wfx.Geometry(mesh, P, dtype)
+    op = wfx.StiffnessOperator(mesh, P, dtype=dtype, geometry=geo, mode=wfx.capi.STIFF_CELL_STREAM)
+    assert op.kernel_info()["variant"] == ("brick-streamed" if order == "brick" else "cell-streamed")
+    Go, _ = orc.precompute_geometric_data(mesh, P)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    tol = TOL64 if dtype == np.float64 else TOL32
+    x = np.random.default_rng(8).standard_normal(mesh.ndofs).astype(dtype)
+    b = np.zeros(mesh.ndofs)
+    orc.stiffness_apply(mesh, P, Go, x.astype(np.float64), b, dense=False)
+    sc = np.random.default_rng(9).uniform(0.5, 2.0, mesh.ndofs).astype(dtype)
+    y = torch.full((mesh.ndofs,), float("nan"), dtype=tdt, device="cuda")
+    scd = dev(torch, sc)
+    op.apply_scaled(dev(torch, x), scd.data_ptr(), y)
+    yh = y.cpu().numpy()
+    assert np.isfinite(yh).all() and (yh[-5:] == 0).all()
+    assert rel_l2(yh, b * sc.astype(np.float64)) < tol
+    y2 = dev(torch, np.ones(mesh.ndofs, dtype=dtype))
+    op(dev(torch, x), y2)                                    # y += A x
+    assert rel_l2(y2.cpu().numpy() - 1.0, b) < (tol if dtype == np.float64 else 1e-3)
+    y3 = torch.full_like(y, float("nan"))
+    op.apply_scaled(dev(torch, x), scd.data_ptr(), y3)       # bitwise repeatable
+    assert torch.equal(y, y3)
+    # against the brick kernel on the same inputs
+    ob = wfx.StiffnessOperator(mesh, P, dtype=dtype, geometry=geo)
+    y4 = torch.full_like(y, float("nan"))
+    ob.apply_scaled(dev(torch, x), scd.data_ptr(), y4)
+    assert rel_l2(yh, y4.cpu().numpy().astype(np.float64)) < tol
 
 
 def test_stiffness_ghost_only_entries_and_errors(wfx, orc, torch):
@@ -563,12 +613,15 @@ def test_planar3d_demo_full_run_matches_oracle(wfx, orc, torch):
     assert rel_l2(u, uo) < TOL64 and rel_l2(v, vo) < TOL64
 
 
-def test_stiffness_interface_interior_split(wfx, orc, torch):
+@pytest.mark.parametrize("streamed", [False, True])
+def test_stiffness_interface_interior_split(wfx, orc, torch, monkeypatch, streamed):
     """The distributed-mesh schedule on one GPU: with an (artificial) set of rank-shared dofs the
     interface part followed by the interior part equals the plain apply, and the fused scaling
-    skips exactly the shared dofs."""
+    skips exactly the shared dofs.  Same for the brick-ordered streamed-cell kernel."""
     import copy
     P = 4
+    if streamed:
+        monkeypatch.setenv("WFX_CELL2", "1")
     mesh = copy.copy(_mesh(wfx, 6, P))
     M = P * 6 + 1
     shared = (np.arange(M * M) + (M // 2) * M * M).astype(np.int32)  # the lattice plane x = L/2
@@ -576,6 +629,7 @@ def test_stiffness_interface_interior_split(wfx, orc, torch):
     geo = wfx.Geometry(mesh, P)
     op = wfx.StiffnessOperator(mesh, P, geometry=geo)
     assert op.nshared == len(shared) and op.info()["ncolours"] == 16
+    assert (op.kernel_info()["variant"] == "brick-streamed") == streamed
     mass = wfx.MassOperator(mesh, P, geometry=geo)
     Go, _ = orc.precompute_geometric_data(mesh, P)
     x = np.random.default_rng(5).standard_normal(mesh.ndofs)

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("WFX_LIB") or os.path.join(HERE, "libwavefx.so")
 
 F64, F32 = 0, 1
-STIFF_AUTO, STIFF_CELL_COLOUR, STIFF_NO_SPLIT = 0, 1, 2
+STIFF_AUTO, STIFF_CELL_COLOUR, STIFF_NO_SPLIT, STIFF_CELL_STREAM = 0, 1, 2, 4
 
 _c_i32p = C.POINTER(C.c_int32)
 _c_i64p = C.POINTER(C.c_int64)

@@ -195,15 +195,24 @@ struct BlockSync
 // conflicts for 64-bit words (16 banks of 8 bytes per half-warp).  For N = 5 the layout was
 // found by search (rows of AT at offsets {0,20,7,26,13} inside a 33-word plane); other
 // degrees use the plain layout.
+// RS = stride between the rows of a plane.  It is odd: roles J / I have every lane walk its own row,
+// so lane l reads word l * RS + m, and an even RS folds the 16 lanes of a half-warp onto a few 64-bit
+// banks (N = 8 unpadded: two banks, every row access an 8-way conflict).
 template <int N>
 struct Tiles
 {
-  static constexpr int PS_A = N * N, PS_T = N * N;
-  __host__ __device__ static constexpr int boff(int j) { return j * N; }
+#ifndef WFX_NO_ROW_PAD
+  static constexpr int RS = (N % 2 == 0) ? N + 1 : N;
+#else
+  static constexpr int RS = N;
+#endif
+  static constexpr int PS_A = N * RS, PS_T = N * RS;
+  __host__ __device__ static constexpr int boff(int j) { return j * RS; }
 };
 template <>
 struct Tiles<5>
 {
+  static constexpr int RS = 5;
   static constexpr int PS_A = 25, PS_T = 33;
   __host__ __device__ static constexpr int boff(int j)
   {
@@ -227,9 +236,9 @@ __device__ __forceinline__ RoleOff role_offsets(int lane)
 {
   const int hi = lane / N, lo = lane % N;
   RoleOff o;
-  o.kA = hi * N + lo;                       // role K: i = hi, j = lo
+  o.kA = hi * Tiles<N>::RS + lo;            // role K: i = hi, j = lo
   o.kT = Tiles<N>::boff(lo) + hi;
-  o.rA = hi * Tiles<N>::PS_A + lo * N;      // role J: k = hi, i = lo, row over j
+  o.rA = hi * Tiles<N>::PS_A + lo * Tiles<N>::RS; // role J: k = hi, i = lo, row over j
   o.rT = hi * Tiles<N>::PS_T + Tiles<N>::boff(lo); // role I: k = hi, j = lo, row over i
   o.colK = lane;
   o.iK = hi, o.jK = lo, o.kJ = hi, o.iJ = lo, o.kI = hi, o.jI = lo;
@@ -587,6 +596,177 @@ stiff_cell_kernel(const int32_t* __restrict__ cells, int ncl, const int32_t* __r
 #pragma unroll
     for (int k = 0; k < N; ++k) y[dof[k]] += yv[k];
   }
+}
+
+// ---- streamed-cell kernel: coloured cells, no shared-memory dof arrays ------------------------
+// At high degree a batch of the brick kernel degenerates: a 2x2x2 brick of P7 cells already fills
+// the shared memory two CTAs can have, its eight cells all touch each other (W = 1, one cell at a
+// time) and an SM ends up with six warps.  Per cell, though, there is plenty of work (N^3 points) and
+// little sharing (N^3 points on (N-1)^3 dofs), so the dofs need not be staged at all: cells are
+// coloured (no two cells of a colour share a dof), a slot of SLOT threads walks `cps` consecutive
+// cells of its colour, gathers x straight from global memory, and updates y with a plain
+// read-modify-write.  What the brick kernel gets from its batch arrays is recovered with flags in the
+// per-point dofmap: FIRST (lowest colour touching the dof: overwrite, no memset, no read of y) and
+// LAST (highest colour: apply the fused diagonal scaling), so the fused stiffness + mass apply is
+// still one pass.  Software pipeline of a slot: the next cell's dof indices are loaded a cell ahead,
+// its x values are gathered into the registers of u as soon as the G multiply has consumed u, its G
+// planes roll into the register window inside the G multiply (g_multiply) and the cell after that
+// goes to L2 by bulk prefetch.  Colours are consecutive launches chained by programmatic dependent
+// launch; only the first access to y waits for the previous colour.
+template <typename T>
+struct Cell2Args
+{
+  const int32_t* cells;  // cell ids sorted by colour
+  const uint32_t* tdmf;  // [ncells][ND] k-major point order: global dof | BD_FIRST | BD_LAST
+  const T* G6;
+  const T* x;
+  T* y;
+  const T* scale; // nullable: applied on the LAST touch of a dof
+  T coeff;
+  int beta;    // 0: FIRST touch overwrites y; 1: accumulates into y
+  int g_order; // column order of G6 (see g_column)
+  int cps;     // cells per slot (colour-ordered form)
+  int64_t ndofs, ncells;
+  // brick-ordered form (BRICK): one CTA per batch of the brick plan, one iteration per round
+  const int32_t* round_off; // [nbatches+1]
+  const int32_t* slot_cell; // [nrounds_total*CPB] cell id or -1
+  int uni_nr;               // > 0: every batch has this many rounds
+};
+
+struct SlotBarSync
+{
+  int id, nthr; // named barrier of the slot's warps (id 0 is __syncthreads)
+  __device__ __forceinline__ void operator()() const
+  {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthr) : "memory");
+  }
+};
+
+// BRICK: the cells come in the order of the brick plan instead -- one CTA per batch (a spatially
+// compact brick of cells), iteration r = round r of the batch (its cells share no dof), CPB = the plan's
+// W slots; consecutive rounds DO share dofs, so the update of y in round r waits (mbarrier, split
+// arrive / wait like the brick kernel's) until every warp has finished round r-1's.  The batch's dofs
+// are then touched by one SM within a few microseconds: x gathers hit L1 / L2 and the read-modify-write
+// of y stays in L2, so DRAM sees what the brick kernel's staging moves -- without the shared-memory dof
+// arrays (two CTAs per SM at P4, three at P7), without the staging / write-back phases that keep a CTA
+// of that kernel waiting on memory for a third of its life, and with L1 nearly whole.  Batches of one
+// (execution) colour share no dof; FIRST / LAST follow the order (colour, round).
+template <typename T, int N, int SLOT, int CPB, int MINB, int GW, bool BRICK>
+__global__ void __launch_bounds__(SLOT* CPB, MINB)
+stiff_cell2_kernel(const Cell2Args<T> a, const DMat<T, N> Dm, int cell0, int ncl)
+{
+  constexpr int N2 = N * N, ND = N2 * N, NT = SLOT * CPB;
+  using V2 = typename Vec2<T>::type;
+  using L = LayoutStd<N>;
+  static_assert(SLOT <= 32 ? (32 % SLOT == 0) : (SLOT % 32 == 0), "a slot is a fraction or a multiple of a warp");
+  static_assert(SLOT <= 32 || CPB <= 15, "one named barrier per slot");
+  static_assert(!BRICK || NT % 32 == 0, "whole warps");
+  __shared__ __align__(16) T s_w[CPB][L::SLOT_ELEMS];
+  __shared__ __align__(8) uint64_t s_rbar;
+  constexpr bool RB = BRICK && NT > 32; // round barrier needed (one warp: program order suffices)
+  if (RB && threadIdx.x == 0) mbar_init(&s_rbar, NT / 32); // one arrival per warp and round
+  pdl_launch_dependents(); // the next colour may start gathering; it waits before touching y
+  const int slot = threadIdx.x / SLOT, col = threadIdx.x % SLOT;
+  const bool lane_ok = col < N2;
+  const RoleOff ro = L::offsets(lane_ok ? col : 0);
+  const int gcol = g_column<L, N>(ro, lane_ok ? col : 0, a.g_order);
+  // colour-ordered: this slot's cells are a.cps consecutive entries of the colour's list;
+  // brick-ordered: cell0 + blockIdx.x is the batch, its rounds are the iterations
+  int first = 0, r0 = 0, niter = a.cps;
+  if constexpr (BRICK)
+  {
+    const int b = cell0 + (int)blockIdx.x;
+    r0 = a.uni_nr ? b * a.uni_nr : __ldg(a.round_off + b);
+    niter = a.uni_nr ? a.uni_nr : __ldg(a.round_off + b + 1) - r0;
+  }
+  else first = ((int)blockIdx.x * CPB + slot) * a.cps;
+  auto cell_at = [&](int i) -> int {
+    if constexpr (BRICK) return i < niter ? __ldg(a.slot_cell + (int64_t)(r0 + i) * CPB + slot) : -1;
+    else return (i < a.cps && first + i < ncl) ? __ldg(a.cells + cell0 + first + i) : -1;
+  };
+  if constexpr (RB) __syncthreads(); // the barrier is initialised before anyone arrives
+  auto sync = [&]() {
+    if constexpr (SLOT <= 32) __syncwarp();
+    else SlotBarSync{slot + 1, SLOT}();
+  };
+  int cell = cell_at(0), cn = cell_at(1);
+  WFX_DEV_ASSERT(cell < a.ncells && cn < a.ncells);
+  uint32_t dof[N];
+  T u[N];
+  V2 g[GW][3];
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+    dof[k] = (lane_ok && cell >= 0) ? ld_once(a.tdmf + (int64_t)cell * ND + k * N2 + col) : BD_HOLE;
+  if (lane_ok && cell >= 0) load_G<T, N, GW>(a.G6 + (int64_t)cell * (6 * ND), gcol, g);
+  if constexpr ((6 * ND * sizeof(T)) % 16 == 0)
+    if (col == 0 && cn >= 0) l2_prefetch_bulk(a.G6 + (int64_t)cn * (6 * ND), (uint32_t)(6 * ND * sizeof(T)));
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+  {
+    WFX_DEV_ASSERT(dof[k] == BD_HOLE || (int64_t)(dof[k] & BD_MASK) < a.ndofs);
+    u[k] = dof[k] != BD_HOLE ? __ldg(a.x + (dof[k] & BD_MASK)) : T(0);
+  }
+  bool waited = false;
+  T* tiles = s_w[slot];
+  PhaseTimer tm;
+  tm.start(false);
+  for (int it = 0; it < niter; ++it)
+  {
+    const bool active = lane_ok && cell >= 0;
+    const int cnn = cell_at(it + 2);
+    WFX_DEV_ASSERT(cnn < a.ncells);
+    uint32_t dofn[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      dofn[k] = (lane_ok && cn >= 0) ? ld_once(a.tdmf + (int64_t)cn * ND + k * N2 + col) : BD_HOLE;
+    if constexpr ((6 * ND * sizeof(T)) % 16 == 0)
+      if (col == 0 && cnn >= 0) l2_prefetch_bulk(a.G6 + (int64_t)cnn * (6 * ND), (uint32_t)(6 * ND * sizeof(T)));
+    const V2* gcur = active ? reinterpret_cast<const V2*>(a.G6 + (int64_t)cell * (6 * ND)) + gcol : nullptr;
+    const V2* gnext = (lane_ok && cn >= 0) ? reinterpret_cast<const V2*>(a.G6 + (int64_t)cn * (6 * ND)) + gcol : nullptr;
+    T f2[N], yv[N];
+    if constexpr (SLOT <= 32) cell_part1<T, N, L, GW>(u, g, tiles, ro, Dm, a.coeff, active, WarpSync(), f2, tm, gcur, gnext);
+    else cell_part1<T, N, L, GW>(u, g, tiles, ro, Dm, a.coeff, active, SlotBarSync{slot + 1, SLOT}, f2, tm, gcur, gnext);
+    // u is consumed: its registers take the next cell's x values, in flight during part 2
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+    {
+      WFX_DEV_ASSERT(dofn[k] == BD_HOLE || (int64_t)(dofn[k] & BD_MASK) < a.ndofs);
+      u[k] = dofn[k] != BD_HOLE ? __ldg(a.x + (dofn[k] & BD_MASK)) : T(0);
+    }
+    if constexpr (SLOT <= 32) cell_part2<T, N, L>(f2, tiles, ro, Dm, active, WarpSync(), yv, tm);
+    else cell_part2<T, N, L>(f2, tiles, ro, Dm, active, SlotBarSync{slot + 1, SLOT}, yv, tm);
+    if (!waited)
+    {
+      pdl_wait(); // earlier colours have finished their writes to y
+      waited = true;
+    }
+    if constexpr (RB)
+      if (it > 0) mbar_wait(&s_rbar, (it - 1) & 1); // every warp has finished round it-1's update of y
+    if (active)
+    {
+      T yo[N], sc[N];
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+      {
+        const uint32_t e = dof[k];
+        yo[k] = (!(e & BD_FIRST) || a.beta) ? __ldcg(a.y + (e & BD_MASK)) : T(0);
+        sc[k] = ((e & BD_LAST) && a.scale) ? ld_once(a.scale + (e & BD_MASK)) : T(1);
+      }
+#pragma unroll
+      for (int k = 0; k < N; ++k) a.y[dof[k] & BD_MASK] = (yo[k] + yv[k]) * sc[k];
+    }
+    sync(); // part 2's reads of the tiles precede the next cell's writes
+    if constexpr (RB)
+    {
+      __syncwarp();
+      if (it + 1 < niter && threadIdx.x % 32 == 0) mbar_arrive(&s_rbar); // (release: the warp's stores to y)
+    }
+    cell = cn;
+    cn = cnn;
+#pragma unroll
+    for (int k = 0; k < N; ++k) dof[k] = dofn[k];
+  }
+  if (!waited) pdl_wait();
 }
 
 // ---- product kernel: one CTA per batch ------------------------------------------------
@@ -1385,6 +1565,164 @@ template <> struct Cfg<6> { static constexpr int SLOT = 64, W = WFX_P5_W, BX = W
 template <> struct Cfg<7> { static constexpr int SLOT = 64, W = 1, BX = 2, BY = 2, BZ = WFX_P6_BZ, CPB = 4, MINB = WFX_P6_MINB, CARVEOUT = 72, CARVEOUT32 = 58, GW = WFX_P6_GW; };
 template <> struct Cfg<8> { static constexpr int SLOT = 64, W = 1, BX = 2, BY = 2, BZ = WFX_P7_BZ, CPB = 2, MINB = WFX_P7_MINB, CARVEOUT = 0, CARVEOUT32 = 0, GW = WFX_P7_GW; };
 
+// per-degree configuration of the streamed-cell kernel (stiff_cell2_kernel): cells per CTA, min CTAs
+// per SM, planes of G in the register window (fp64; fp32 holds a whole cell).  The slot width is
+// Cfg<N>::SLOT.
+#ifndef WFX_C2_P5_CPB
+#define WFX_C2_P5_CPB 4
+#endif
+#ifndef WFX_C2_P5_MINB
+#define WFX_C2_P5_MINB 2
+#endif
+#ifndef WFX_C2_P5_GW
+#define WFX_C2_P5_GW 3
+#endif
+#ifndef WFX_C2_P6_CPB
+#define WFX_C2_P6_CPB 4
+#endif
+#ifndef WFX_C2_P6_MINB
+#define WFX_C2_P6_MINB 2
+#endif
+#ifndef WFX_C2_P6_GW
+#define WFX_C2_P6_GW 2
+#endif
+#ifndef WFX_C2_P7_CPB
+#define WFX_C2_P7_CPB 4
+#endif
+#ifndef WFX_C2_P7_MINB
+#define WFX_C2_P7_MINB 2
+#endif
+#ifndef WFX_C2_P7_GW
+#define WFX_C2_P7_GW 2
+#endif
+// smallest N = P + 1 for which WFX_STIFF_AUTO takes the streamed-cell kernel, per scalar type
+#ifndef WFX_CELL2_MIN_N64
+#define WFX_CELL2_MIN_N64 99
+#endif
+#ifndef WFX_CELL2_MIN_N32
+#define WFX_CELL2_MIN_N32 99
+#endif
+template <int N> struct Cfg2;
+template <> struct Cfg2<3> { static constexpr int CPB = 16, MINB = 2, GW = 3; };
+template <> struct Cfg2<4> { static constexpr int CPB = 16, MINB = 2, GW = 4; };
+template <> struct Cfg2<5> { static constexpr int CPB = 8, MINB = 2, GW = 3; };
+template <> struct Cfg2<6> { static constexpr int CPB = WFX_C2_P5_CPB, MINB = WFX_C2_P5_MINB, GW = WFX_C2_P5_GW; };
+template <> struct Cfg2<7> { static constexpr int CPB = WFX_C2_P6_CPB, MINB = WFX_C2_P6_MINB, GW = WFX_C2_P6_GW; };
+template <> struct Cfg2<8> { static constexpr int CPB = WFX_C2_P7_CPB, MINB = WFX_C2_P7_MINB, GW = WFX_C2_P7_GW; };
+
+// brick-ordered form of the streamed-cell kernel: slots per CTA (= cells per round) and brick shape.
+// No shared-memory dof arrays, so the brick is free: it only has to offer W cells per colour class.
+#ifndef WFX_C3_P4_W
+#define WFX_C3_P4_W 8
+#endif
+#ifndef WFX_C3_P4_BX
+#define WFX_C3_P4_BX 4
+#endif
+#ifndef WFX_C3_P4_BY
+#define WFX_C3_P4_BY 4
+#endif
+#ifndef WFX_C3_P4_BZ
+#define WFX_C3_P4_BZ 4
+#endif
+#ifndef WFX_C3_P4_MINB
+#define WFX_C3_P4_MINB 2
+#endif
+#ifndef WFX_C3_HI_W
+#define WFX_C3_HI_W 4
+#endif
+#ifndef WFX_C3_HI_BX
+#define WFX_C3_HI_BX 4
+#endif
+#ifndef WFX_C3_HI_BY
+#define WFX_C3_HI_BY 4
+#endif
+#ifndef WFX_C3_HI_BZ
+#define WFX_C3_HI_BZ 2
+#endif
+#ifndef WFX_C3_HI_MINB
+#define WFX_C3_HI_MINB 2
+#endif
+template <int N> struct Cfg3;
+template <> struct Cfg3<3> { static constexpr int W = 16, BX = 8, BY = 8, BZ = 8, MINB = 2; };
+template <> struct Cfg3<4> { static constexpr int W = 16, BX = 8, BY = 8, BZ = 4, MINB = 2; };
+template <> struct Cfg3<5> { static constexpr int W = WFX_C3_P4_W, BX = WFX_C3_P4_BX, BY = WFX_C3_P4_BY, BZ = WFX_C3_P4_BZ, MINB = WFX_C3_P4_MINB; };
+template <> struct Cfg3<6> { static constexpr int W = WFX_C3_HI_W, BX = WFX_C3_HI_BX, BY = WFX_C3_HI_BY, BZ = WFX_C3_HI_BZ, MINB = WFX_C3_HI_MINB; };
+template <> struct Cfg3<7> { static constexpr int W = WFX_C3_HI_W, BX = WFX_C3_HI_BX, BY = WFX_C3_HI_BY, BZ = WFX_C3_HI_BZ, MINB = WFX_C3_HI_MINB; };
+template <> struct Cfg3<8> { static constexpr int W = WFX_C3_HI_W, BX = WFX_C3_HI_BX, BY = WFX_C3_HI_BY, BZ = WFX_C3_HI_BZ, MINB = WFX_C3_HI_MINB; };
+
+struct Cfg3Rt
+{
+  int W, BX, BY, BZ;
+};
+Cfg3Rt cfg3_rt(int N)
+{
+  switch (N)
+  {
+  case 3: return {Cfg3<3>::W, Cfg3<3>::BX, Cfg3<3>::BY, Cfg3<3>::BZ};
+  case 4: return {Cfg3<4>::W, Cfg3<4>::BX, Cfg3<4>::BY, Cfg3<4>::BZ};
+  case 5: return {Cfg3<5>::W, Cfg3<5>::BX, Cfg3<5>::BY, Cfg3<5>::BZ};
+  case 6: return {Cfg3<6>::W, Cfg3<6>::BX, Cfg3<6>::BY, Cfg3<6>::BZ};
+  case 7: return {Cfg3<7>::W, Cfg3<7>::BX, Cfg3<7>::BY, Cfg3<7>::BZ};
+  case 8: return {Cfg3<8>::W, Cfg3<8>::BX, Cfg3<8>::BY, Cfg3<8>::BZ};
+  }
+  fail("stiffness: degree %d not supported (2..7)", N - 1);
+}
+
+// G6 of every cell with the tensor axes relabelled: kernel axis a' is mesh axis s[a'], so
+// G'(a', b') = G(s[a'], s[b']) at the same physical point, stored in the kernel's plane / column order
+// of the primed indices.  The operator is invariant under the relabelling (same 1-D matrices on all
+// axes); what changes is which index runs along the lanes of the gather / update instructions.
+template <typename T>
+__global__ void permute_g_axes_kernel(int n, int64_t ncells, int s0, int s1, int s2, const T* __restrict__ in,
+                                      T* __restrict__ out)
+{
+  using V2 = typename Vec2<T>::type;
+  const int n2 = n * n;
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (gid >= ncells * n * n2) return;
+  const int64_t c = gid / (n * n2);
+  const int r = (int)(gid % (n * n2));
+  const int kp = r / n2, colp = r % n2, ip = colp / n, jp = colp % n;
+  int sidx[3];
+  sidx[s0] = ip, sidx[s1] = jp, sidx[s2] = kp; // the point's indices on the mesh's own axes
+  const V2* src = reinterpret_cast<const V2*>(in) + ((c * n + sidx[2]) * 3) * (int64_t)n2 + sidx[0] * n + sidx[1];
+  const V2 p0 = src[0], p1 = src[n2], p2 = src[2 * n2];
+  const T G[3][3] = {{p0.x, p0.y, p1.x}, {p0.y, p1.y, p2.x}, {p1.x, p2.x, p2.y}};
+  V2* dst = reinterpret_cast<V2*>(out) + ((c * n + kp) * 3) * (int64_t)n2 + colp;
+  V2 q;
+  q.x = G[s0][s0], q.y = G[s0][s1];
+  dst[0] = q;
+  q.x = G[s0][s2], q.y = G[s1][s1];
+  dst[n2] = q;
+  q.x = G[s1][s2], q.y = G[s2][s2];
+  dst[2 * n2] = q;
+}
+
+// Which tensor axis of the cells runs along consecutive dof numbers (lexicographic numberings of
+// structured meshes: the fastest grid axis)?  The streamed-cell kernel wants that axis on the fast lane
+// index (j'), so that a gather / update instruction touches few sectors: returns s with s[1] = that
+// axis, or the identity when no axis is contiguous (unstructured or renumbered dofs).
+void detect_axis_perm(int n, int64_t ncells, const int32_t* tdm, int (&s)[3])
+{
+  const int n2 = n * n, nd = n2 * n;
+  int64_t votes[3] = {0, 0, 0};
+  const int64_t ns = std::min<int64_t>(ncells, 256), step = std::max<int64_t>(1, ncells / ns);
+  int64_t seen = 0;
+  for (int64_t c = 0; c < ncells; c += step, ++seen)
+  {
+    // tensor point (i,j,k) is entry k*n2 + i*n + j; 1-D index 0 is lattice position 0, index 2 position 1
+    const int32_t* d = tdm + c * nd;
+    const int32_t o = d[0];
+    if (std::abs(d[2 * n + 0] - o) == 1) ++votes[0];  // (2,0,0)
+    if (std::abs(d[2] - o) == 1) ++votes[1];          // (0,2,0)
+    if (std::abs(d[2 * n2] - o) == 1) ++votes[2];     // (0,0,2)
+  }
+  s[0] = 0, s[1] = 1, s[2] = 2;
+  if (n < 3) return;
+  if (2 * votes[2] > seen) s[0] = 1, s[1] = 2, s[2] = 0;
+  else if (2 * votes[0] > seen) s[0] = 2, s[1] = 0, s[2] = 1;
+}
+
 struct LaunchCfg
 {
   int SLOT, W, BX, BY, BZ, CPB;
@@ -1430,6 +1768,13 @@ struct wfx_stiffness
   // simple path
   CellColourPlan cplan;
   DevBuf<int32_t> d_cells, d_tdm;
+  // streamed-cell path (shares the colour plan): per-point dofmap with FIRST / LAST flags
+  bool cell2 = false;
+  bool cell2_brick = false; // cells in the order of a brick plan (one CTA per batch) instead of global colours
+  int cell2_cps = 4; // colour order: cells a slot walks per launch
+  int axis_perm[3] = {0, 1, 2}; // kernel axis a' is the mesh's tensor axis axis_perm[a'] (see detect_axis_perm)
+  DevBuf<uint32_t> d_tdmf;
+  DevBuf<unsigned char> d_G6perm; // private copy of G6 in the permuted axis order (empty: identity)
   // brick path
   int ncolours = 0, nloc_pad = 0, W = 0, rounds_max = 0;
   int part_split = 0; // first execution colour of the interior part (distributed meshes)
@@ -1494,6 +1839,76 @@ void launch_simple(wfx_stiffness* op, const T* x, T* y, cudaStream_t st)
         op->geom->g_colpos.empty() ? 0 : 1);
   }
   WFX_CUDA(cudaGetLastError());
+}
+
+template <typename T, int N>
+void launch_cell2(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta, int part, cudaStream_t st)
+{
+  using C = Cfg<N>;
+  using C2 = Cfg2<N>;
+  using C3 = Cfg3<N>;
+  constexpr int GW = sizeof(T) == 4 ? N : C2::GW;
+  DMat<T, N> Dm;
+  for (int q = 0; q < N * N; ++q) Dm.d[q] = (T)op->Dhost[q];
+  for (int q = 0; q < N; ++q) Dm.w[q] = (T)op->Whost[q];
+  Cell2Args<T> a;
+  a.cells = op->d_cells.p;
+  a.tdmf = op->d_tdmf.p;
+  a.G6 = op->d_G6perm.n ? (const T*)op->d_G6perm.p : (const T*)op->geom->G6;
+  a.x = x;
+  a.y = y;
+  a.scale = scale;
+  a.coeff = (T)(-1.0 * op->c0 * op->c0);
+  a.beta = beta;
+  a.g_order = op->geom->g_colpos.empty() ? 0 : 1;
+  a.cps = op->cell2_cps;
+  a.ndofs = op->ndofs;
+  a.ncells = op->ncells;
+  a.round_off = op->d_round_off.p;
+  a.slot_cell = op->d_slot_cell.p;
+  a.uni_nr = op->uni_nr;
+  if (!beta && op->d_untouched.n && part != 1)
+  {
+    const int n = (int)op->d_untouched.n;
+    zero_entries_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(op->d_untouched.p, n, y);
+  }
+  // the first launch must see everything earlier in the stream (x may be fresh); later launches chain
+  // by programmatic dependent launch.  The interior part continues the interface part (launch_brick).
+  const bool iface_nonempty = op->cell2_brick && op->part_split > 0 && op->colour_off[op->part_split] > op->colour_off[0];
+  bool first = !(part == 1 && iface_nonempty);
+  auto launch = [&](auto kern, int threads, int grid, int i0, int i1) {
+    if (grid == 0) return;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (op->use_pdl && !first) ? 1 : 0;
+    WFX_CUDA(cudaLaunchKernelEx(&cfg, kern, a, Dm, i0, i1));
+    first = false;
+  };
+  if (op->cell2_brick)
+  {
+    if (op->W != C3::W) fail("stiffness: plan built for %d slots, kernel has %d", op->W, C3::W);
+    const int k0 = part == 1 ? op->part_split : 0;
+    const int k1 = part == 0 ? op->part_split : op->ncolours;
+    for (int k = k0; k < k1; ++k)
+      launch(stiff_cell2_kernel<T, N, C::SLOT, C3::W, C3::MINB, GW, true>, C::SLOT * C3::W,
+             op->colour_off[k + 1] - op->colour_off[k], op->colour_off[k], 0);
+    return;
+  }
+  if (part >= 0) fail("stiffness: colour-ordered streamed cells have no interface / interior parts");
+  for (int k = 0; k < op->cplan.ncolours; ++k)
+  {
+    const int beg = op->cplan.colour_off[k], ncl = op->cplan.colour_off[k + 1] - beg;
+    const int per_cta = C2::CPB * op->cell2_cps;
+    launch(stiff_cell2_kernel<T, N, C::SLOT, C2::CPB, C2::MINB, GW, false>, C::SLOT * C2::CPB,
+           (ncl + per_cta - 1) / per_cta, beg, ncl);
+  }
 }
 
 template <typename T, int N>
@@ -1694,6 +2109,20 @@ void dispatch_apply(wfx_stiffness* op, const T* x, const T* scale, T* y, int bet
     }
     return;
   }
+  if (op->cell2)
+  {
+    switch (op->N)
+    {
+    case 3: launch_cell2<T, 3>(op, x, scale, y, beta, part, st); break;
+    case 4: launch_cell2<T, 4>(op, x, scale, y, beta, part, st); break;
+    case 5: launch_cell2<T, 5>(op, x, scale, y, beta, part, st); break;
+    case 6: launch_cell2<T, 6>(op, x, scale, y, beta, part, st); break;
+    case 7: launch_cell2<T, 7>(op, x, scale, y, beta, part, st); break;
+    case 8: launch_cell2<T, 8>(op, x, scale, y, beta, part, st); break;
+    default: fail("stiffness: degree %d not supported", op->P);
+    }
+    return;
+  }
   switch (op->N)
   {
   case 3: launch_brick<T, 3>(op, x, scale, y, beta, part, st); break;
@@ -1796,7 +2225,8 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
   if (ndofs >= (1ll << 31)) fail("more than 2^31 local dofs");
   bool split_parts = !(flags & WFX_STIFF_NO_SPLIT);
   flags &= ~WFX_STIFF_NO_SPLIT;
-  if (flags != WFX_STIFF_AUTO && flags != WFX_STIFF_CELL_COLOUR) fail("unknown stiffness flags %d", flags);
+  if (flags != WFX_STIFF_AUTO && flags != WFX_STIFF_CELL_COLOUR && flags != WFX_STIFF_CELL_STREAM)
+    fail("unknown stiffness flags %d", flags);
   if (const char* e = std::getenv("WFX_SPLIT")) split_parts = std::atoi(e) != 0;
   ScopedDevice sd(ctx->device);
   auto op = std::make_unique<wfx_stiffness>();
@@ -1824,11 +2254,122 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
     std::vector<int32_t> tdm;
     build_tensor_dofmap(op->P, op->ncells, ndofs, dofmap_host, tdm);
     timer.lap("tensor dofmap");
+    // Streamed-cell kernel: on request, or by degree where it measured faster than the brick kernel
+    // (profiles/r2_degree_sweep.md); whole-mesh applies only (no interface / interior parts) and not
+    // on all-affine meshes, which have their own brick kernels.
+    bool cell2 = flags == WFX_STIFF_CELL_STREAM;
+    if (flags == WFX_STIFF_AUTO && geom->n_affine != op->ncells)
+      cell2 = op->N >= (op->dtype == WFX_F64 ? WFX_CELL2_MIN_N64 : WFX_CELL2_MIN_N32);
+    if (const char* e = std::getenv("WFX_CELL2"))
+      if (flags == WFX_STIFF_AUTO) cell2 = std::atoi(e) != 0 && geom->n_affine != op->ncells;
     if (flags == WFX_STIFF_CELL_COLOUR)
     {
       build_cell_colour_plan(op->nd, op->ncells, ndofs, tdm.data(), op->cplan);
       op->d_cells.upload(op->cplan.cells);
       op->d_tdm.upload(tdm);
+    }
+    else if (cell2)
+    {
+      if (ndofs > (int64_t)BD_MASK) fail("stiffness: more than 2^30 local dofs");
+      const int nd = op->nd, n = op->N, n2 = n * n;
+      // order of the cells: batches of a brick plan (default) or global cell colours
+      op->cell2_brick = true;
+      if (const char* e = std::getenv("WFX_STREAM_ORDER")) op->cell2_brick = std::strcmp(e, "colour") != 0;
+      if (nshared > 0 && !op->cell2_brick) fail("stiffness: colour-ordered streamed cells do not take partitioned meshes");
+      // key[c]: position of cell c in the execution order (launch, iteration); cells with equal keys
+      // share no dof.  FIRST / LAST of a point: its cell has the lowest / highest key at that dof.
+      std::vector<uint32_t> key((size_t)op->ncells, 0);
+      if (op->cell2_brick)
+      {
+        const Cfg3Rt c3 = cfg3_rt(op->N);
+        BrickPlan bp;
+        build_brick_plan(op->P, op->ncells, ndofs, tdm.data(),
+                         geom->centroid.empty() ? nullptr : geom->centroid.data(), BrickShape(c3.BX, c3.BY, c3.BZ),
+                         c3.W, 65535, bp, shared.empty() ? nullptr : shared.data(), op->dtype == WFX_F64 ? 8 : 4,
+                         false, geom->cell_ijk.empty() ? nullptr : geom->cell_ijk.data(), split_parts);
+        timer.lap("brick plan");
+        op->ncolours = bp.ncolours;
+        op->part_split = bp.part_split;
+        op->colour_off = bp.colour_off;
+        op->W = bp.W;
+        op->nbatches = bp.nbatches;
+        op->rounds_max = bp.rounds_max;
+        bool ur = bp.nbatches > 0;
+        for (int b = 0; b < bp.nbatches; ++b) ur = ur && bp.round_off[b + 1] - bp.round_off[b] == bp.round_off[1];
+        op->uni_nr = ur ? bp.round_off[1] : 0;
+        for (int k = 0; k < bp.ncolours; ++k)
+          for (int b = bp.colour_off[k]; b < bp.colour_off[k + 1]; ++b)
+            for (int r = bp.round_off[b]; r < bp.round_off[b + 1]; ++r)
+              for (int w = 0; w < bp.W; ++w)
+              {
+                const int32_t c = bp.slot_cell[(size_t)r * bp.W + w];
+                if (c >= 0) key[c] = (uint32_t)k * 65536u + (uint32_t)(r - bp.round_off[b]);
+              }
+        op->d_round_off.upload(bp.round_off);
+        op->d_slot_cell.upload(bp.slot_cell);
+      }
+      else
+      {
+        build_cell_colour_plan(nd, op->ncells, ndofs, tdm.data(), op->cplan);
+        timer.lap("cell colour plan");
+        for (int k = 0; k < op->cplan.ncolours; ++k)
+          for (int32_t p = op->cplan.colour_off[k]; p < op->cplan.colour_off[k + 1]; ++p)
+            key[op->cplan.cells[p]] = (uint32_t)k;
+        op->d_cells.upload(op->cplan.cells);
+        if (const char* e = std::getenv("WFX_CELL2_CPS")) op->cell2_cps = std::max(1, std::atoi(e));
+      }
+      std::vector<uint32_t> kmin((size_t)ndofs, 0xffffffffu), kmax((size_t)ndofs, 0);
+      for (int64_t c = 0; c < op->ncells; ++c)
+        for (int t = 0; t < nd; ++t)
+        {
+          const int32_t d = tdm[c * nd + t];
+          kmin[d] = std::min(kmin[d], key[c]);
+          kmax[d] = std::max(kmax[d], key[c]);
+        }
+      // axis order of the kernel: the contiguous axis of the dof numbering on the fast lane index
+      detect_axis_perm(n, op->ncells, tdm.data(), op->axis_perm);
+      if (const char* e = std::getenv("WFX_AXIS_PERM"))
+        if (std::atoi(e) == 0) op->axis_perm[0] = 0, op->axis_perm[1] = 1, op->axis_perm[2] = 2;
+      if (!geom->g_colpos.empty()) op->axis_perm[0] = 0, op->axis_perm[1] = 1, op->axis_perm[2] = 2;
+      const int s0 = op->axis_perm[0], s1 = op->axis_perm[1], s2 = op->axis_perm[2];
+      // per-point dofmap in the kernel's (primed) point order k'*n2 + i'*n + j' with the flags; dofs
+      // that also live on another rank are never LAST (their scaling waits for the ghost reduction)
+      std::vector<uint32_t> tdmf((size_t)op->ncells * nd);
+      parallel_for(op->ncells, [&](int64_t cb, int64_t ce) {
+        for (int64_t c = cb; c < ce; ++c)
+          for (int kp = 0; kp < n; ++kp)
+            for (int ip = 0; ip < n; ++ip)
+              for (int jp = 0; jp < n; ++jp)
+              {
+                int sidx[3];
+                sidx[s0] = ip, sidx[s1] = jp, sidx[s2] = kp;
+                const int32_t d = tdm[c * nd + sidx[2] * n2 + sidx[0] * n + sidx[1]];
+                uint32_t e = (uint32_t)d;
+                if (key[c] == kmin[d]) e |= BD_FIRST;
+                if (key[c] == kmax[d] && (shared.empty() || !shared[d])) e |= BD_LAST;
+                tdmf[c * nd + kp * n2 + ip * n + jp] = e;
+              }
+      });
+      std::vector<int32_t> untouched;
+      for (int64_t d = 0; d < ndofs; ++d)
+        if (kmin[d] == 0xffffffffu) untouched.push_back((int32_t)d);
+      op->d_tdmf.upload(tdmf);
+      if (!untouched.empty()) op->d_untouched.upload(untouched);
+      if (s0 != 0 || s1 != 1)
+      {
+        const size_t esz = op->dtype == WFX_F64 ? 8 : 4;
+        op->d_G6perm.alloc((size_t)op->ncells * nd * 6 * esz);
+        const int64_t npts = op->ncells * nd;
+        const unsigned grid = (unsigned)((npts + 255) / 256);
+        if (op->dtype == WFX_F64)
+          permute_g_axes_kernel<double><<<grid, 256>>>(n, op->ncells, s0, s1, s2, (const double*)geom->G6, (double*)op->d_G6perm.p);
+        else
+          permute_g_axes_kernel<float><<<grid, 256>>>(n, op->ncells, s0, s1, s2, (const float*)geom->G6, (float*)op->d_G6perm.p);
+        WFX_CUDA(cudaGetLastError());
+        WFX_CUDA(cudaDeviceSynchronize());
+      }
+      op->cell2 = true;
+      timer.lap("flags + uploads");
     }
     else
     {
@@ -2086,7 +2627,7 @@ extern "C" int wfx_stiffness_info(wfx_stiffness* op, int64_t* num_cells, int* nu
   if (bytes)
     *bytes = op->affine ? (double)op->ncells * 6 * s + (double)op->ndofs * 3 * s
                         : (double)op->ncells * op->nd * (6 * s + 4) + (double)op->ndofs * 3 * s;
-  const int nc = op->mode == WFX_STIFF_CELL_COLOUR ? op->cplan.ncolours : op->ncolours;
+  const int nc = (op->mode == WFX_STIFF_CELL_COLOUR || (op->cell2 && !op->cell2_brick)) ? op->cplan.ncolours : op->ncolours;
   if (ncolours) *ncolours = nc;
   if (nlaunches) *nlaunches = (op->persistent && op->mode != WFX_STIFF_CELL_COLOUR) ? 1 : nc;
   WFX_API_END
@@ -2097,12 +2638,12 @@ extern "C" int wfx_stiffness_kernel_info(wfx_stiffness* op, int* variant, int* a
 {
   WFX_API_BEGIN
   if (!op) fail("stiffness operator is NULL");
-  if (variant) *variant = op->mode == WFX_STIFF_CELL_COLOUR ? -1 : op->variant;
+  if (variant) *variant = op->mode == WFX_STIFF_CELL_COLOUR ? -1 : (op->cell2 ? (op->cell2_brick ? 4 : 3) : op->variant);
   if (affine) *affine = op->affine ? 1 : 0;
   if (mixed) *mixed = op->mixed ? 1 : 0;
   if (regular_batches) *regular_batches = op->n_regular;
   if (batches) *batches = op->nbatches;
-  if (smem_bytes) *smem_bytes = (int64_t)(op->variant ? op->smem_bytes_reg : op->smem_bytes);
+  if (smem_bytes) *smem_bytes = op->cell2 ? 0 : (int64_t)(op->variant ? op->smem_bytes_reg : op->smem_bytes);
   WFX_API_END
 }
 

@@ -201,7 +201,7 @@ class StiffnessOperator(_Operator):
         v, a, m, nr, nb, sm = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int64()
         capi.call("wfx_stiffness_kernel_info", self.handle, C.byref(v), C.byref(a), C.byref(m), C.byref(nr),
                   C.byref(nb), C.byref(sm))
-        names = {-1: "cell", 0: "brick-generic", 1: "brick-regular", 2: "brick-regular-p4d"}
+        names = {-1: "cell", 0: "brick-generic", 1: "brick-regular", 2: "brick-regular-p4d", 3: "cell-streamed", 4: "brick-streamed"}
         return dict(variant=names.get(v.value, str(v.value)), affine=bool(a.value), mixed=bool(m.value),
                     regular_batches=nr.value, batches=nb.value, smem_bytes=sm.value)
 
