@@ -195,22 +195,25 @@ struct BlockSync
 // conflicts for 64-bit words (16 banks of 8 bytes per half-warp).  For N = 5 the layout was
 // found by search (rows of AT at offsets {0,20,7,26,13} inside a 33-word plane); other
 // degrees use the plain layout.
-// RS = stride between the rows of a plane.  It is odd: roles J / I have every lane walk its own row,
-// so lane l reads word l * RS + m, and an even RS folds the 16 lanes of a half-warp onto a few 64-bit
-// banks (N = 8 unpadded: two banks, every row access an 8-way conflict).
-template <int N>
+// RS = stride between the rows of a plane (WB = bytes per word).  Roles J / I have every lane walk its
+// own row, so lane l reads word l * RS + m: for 64-bit words RS is odd -- an even RS folds the 16 lanes
+// of a half-warp onto a few banks (N = 8 unpadded: two banks, every row access an 8-way conflict;
+// measured P7 fp64 0.644 -> 0.579 ms).  32-bit rows stay unpadded: the compiler reads them with 128-bit
+// loads, and both an odd stride (P7 fp32 0.311 -> 0.323 ms) and a 12-word stride that keeps the
+// alignment (0.329 ms) measured slower.
+template <int N, int WB = 8>
 struct Tiles
 {
 #ifndef WFX_NO_ROW_PAD
-  static constexpr int RS = (N % 2 == 0) ? N + 1 : N;
+  static constexpr int RS = (WB == 8 && N % 2 == 0) ? N + 1 : N;
 #else
   static constexpr int RS = N;
 #endif
   static constexpr int PS_A = N * RS, PS_T = N * RS;
   __host__ __device__ static constexpr int boff(int j) { return j * RS; }
 };
-template <>
-struct Tiles<5>
+template <int WB>
+struct Tiles<5, WB>
 {
   static constexpr int RS = 5;
   static constexpr int PS_A = 25, PS_T = 33;
@@ -219,8 +222,7 @@ struct Tiles<5>
     return j == 0 ? 0 : (j == 1 ? 20 : (j == 2 ? 7 : (j == 3 ? 26 : 13)));
   }
 };
-template <int N> __host__ __device__ constexpr int tile_a_elems() { return N * Tiles<N>::PS_A; }
-template <int N> __host__ __device__ constexpr int slot_elems() { return N * (Tiles<N>::PS_A + Tiles<N>::PS_T); }
+template <int N, int WB> __host__ __device__ constexpr int slot_elems() { return N * (Tiles<N, WB>::PS_A + Tiles<N, WB>::PS_T); }
 template <int N> __host__ __device__ constexpr int ndp_of() { return (N * N * N + 7) & ~7; } // ldm slot stride
 
 // per-thread tile offsets of the three roles (constant for the whole kernel)
@@ -231,15 +233,16 @@ struct RoleOff
   int colK;   // role K: i*N + j (column of G6 and of the local dofmap)
   int iK, jK, kJ, iJ, kI, jI; // the lines this thread owns in the three roles
 };
-template <int N>
+template <int N, int WB>
 __device__ __forceinline__ RoleOff role_offsets(int lane)
 {
+  using TL = Tiles<N, WB>;
   const int hi = lane / N, lo = lane % N;
   RoleOff o;
-  o.kA = hi * Tiles<N>::RS + lo;            // role K: i = hi, j = lo
-  o.kT = Tiles<N>::boff(lo) + hi;
-  o.rA = hi * Tiles<N>::PS_A + lo * Tiles<N>::RS; // role J: k = hi, i = lo, row over j
-  o.rT = hi * Tiles<N>::PS_T + Tiles<N>::boff(lo); // role I: k = hi, j = lo, row over i
+  o.kA = hi * TL::RS + lo;                  // role K: i = hi, j = lo
+  o.kT = TL::boff(lo) + hi;
+  o.rA = hi * TL::PS_A + lo * TL::RS;       // role J: k = hi, i = lo, row over j
+  o.rT = hi * TL::PS_T + TL::boff(lo);      // role I: k = hi, j = lo, row over i
   o.colK = lane;
   o.iK = hi, o.jK = lo, o.kJ = hi, o.iJ = lo, o.kI = hi, o.jI = lo;
   return o;
@@ -247,14 +250,14 @@ __device__ __forceinline__ RoleOff role_offsets(int lane)
 
 // Layout policies: tile geometry + the lane -> line maps of the three roles.
 // LayoutStd: lane = hi*N + lo in all roles, rows stored in index order.
-template <int N>
+template <int N, int WB>
 struct LayoutStd
 {
-  static constexpr int PS_A = Tiles<N>::PS_A, PS_T = Tiles<N>::PS_T;
+  static constexpr int PS_A = Tiles<N, WB>::PS_A, PS_T = Tiles<N, WB>::PS_T;
   static constexpr int AT_OFF = N * PS_A, SLOT_ELEMS = N * (PS_A + PS_T);
   __host__ __device__ static constexpr int eA(int n) { return n; } // offset of element j = n in a row of A
   __host__ __device__ static constexpr int eT(int n) { return n; } // offset of element i = n in a row of AT
-  __device__ static __forceinline__ RoleOff offsets(int lane) { return role_offsets<N>(lane); }
+  __device__ static __forceinline__ RoleOff offsets(int lane) { return role_offsets<N, WB>(lane); }
 };
 
 // LayoutP4D: degree 4, 64-bit words, regular bricks whose lattice strides are Sx = 5, Sy = 2
@@ -570,12 +573,12 @@ stiff_cell_kernel(const int32_t* __restrict__ cells, int ncl, const int32_t* __r
 {
   constexpr int N2 = N * N, ND = N2 * N;
   using V2 = typename Vec2<T>::type;
-  __shared__ __align__(16) T s_w[CPB][slot_elems<N>()];
+  __shared__ __align__(16) T s_w[CPB][slot_elems<N, sizeof(T)>()];
   const int slot = threadIdx.x / SLOT, col = threadIdx.x % SLOT;
   const int ci = blockIdx.x * CPB + slot;
   const bool active = (col < N2) && (ci < ncl);
   const int64_t cell = active ? cells[ci] : 0;
-  const RoleOff ro = role_offsets<N>(active ? col : 0);
+  const RoleOff ro = role_offsets<N, sizeof(T)>(active ? col : 0);
   int32_t dof[N];
   T u[N], yv[N], f2[N];
   V2 g[N][3];
@@ -586,11 +589,11 @@ stiff_cell_kernel(const int32_t* __restrict__ cells, int ncl, const int32_t* __r
     u[k] = active ? x[dof[k]] : T(0);
     yv[k] = 0;
   }
-  if (active) load_G<T, N, N>(G6 + cell * (int64_t)(6 * ND), g_column<LayoutStd<N>, N>(ro, col, g_order), g);
+  if (active) load_G<T, N, N>(G6 + cell * (int64_t)(6 * ND), g_column<LayoutStd<N, sizeof(T)>, N>(ro, col, g_order), g);
   PhaseTimer tm;
   tm.start(false);
-  cell_part1<T, N, LayoutStd<N>, N>(u, g, s_w[slot], ro, Dm, coeff, active, BlockSync(), f2, tm);
-  cell_part2<T, N, LayoutStd<N>>(f2, s_w[slot], ro, Dm, active, BlockSync(), yv, tm);
+  cell_part1<T, N, LayoutStd<N, sizeof(T)>, N>(u, g, s_w[slot], ro, Dm, coeff, active, BlockSync(), f2, tm);
+  cell_part2<T, N, LayoutStd<N, sizeof(T)>>(f2, s_w[slot], ro, Dm, active, BlockSync(), yv, tm);
   if (active)
   {
 #pragma unroll
@@ -657,7 +660,7 @@ stiff_cell2_kernel(const Cell2Args<T> a, const DMat<T, N> Dm, int cell0, int ncl
 {
   constexpr int N2 = N * N, ND = N2 * N, NT = SLOT * CPB;
   using V2 = typename Vec2<T>::type;
-  using L = LayoutStd<N>;
+  using L = LayoutStd<N, sizeof(T)>;
   static_assert(SLOT <= 32 ? (32 % SLOT == 0) : (SLOT % 32 == 0), "a slot is a fraction or a multiple of a warp");
   static_assert(SLOT <= 32 || CPB <= 15, "one named barrier per slot");
   static_assert(!BRICK || NT % 32 == 0, "whole warps");
@@ -733,25 +736,32 @@ stiff_cell2_kernel(const Cell2Args<T> a, const DMat<T, N> Dm, int cell0, int ncl
       WFX_DEV_ASSERT(dofn[k] == BD_HOLE || (int64_t)(dofn[k] & BD_MASK) < a.ndofs);
       u[k] = dofn[k] != BD_HOLE ? __ldg(a.x + (dofn[k] & BD_MASK)) : T(0);
     }
-    if constexpr (SLOT <= 32) cell_part2<T, N, L>(f2, tiles, ro, Dm, active, WarpSync(), yv, tm);
-    else cell_part2<T, N, L>(f2, tiles, ro, Dm, active, SlotBarSync{slot + 1, SLOT}, yv, tm);
-    if (!waited)
-    {
-      pdl_wait(); // earlier colours have finished their writes to y
-      waited = true;
-    }
-    if constexpr (RB)
-      if (it > 0) mbar_wait(&s_rbar, (it - 1) & 1); // every warp has finished round it-1's update of y
-    if (active)
-    {
-      T yo[N], sc[N];
+    // a slot that idles in this round has requested nothing inside the G multiply: load the next cell's
+    // window now (batches of a brick plan leave slots empty in some rounds)
+    if (lane_ok && cn >= 0 && !active) load_G<T, N, GW>(a.G6 + (int64_t)cn * (6 * ND), gcol, g);
+    T yo[N], sc[N];
+    auto request_y = [&]() {
+      if (!waited)
+      {
+        pdl_wait(); // earlier colours have finished their writes to y
+        waited = true;
+      }
+      if constexpr (RB)
+        if (it > 0) mbar_wait(&s_rbar, (it - 1) & 1); // every warp has finished round it-1's update of y
 #pragma unroll
       for (int k = 0; k < N; ++k)
       {
         const uint32_t e = dof[k];
-        yo[k] = (!(e & BD_FIRST) || a.beta) ? __ldcg(a.y + (e & BD_MASK)) : T(0);
-        sc[k] = ((e & BD_LAST) && a.scale) ? ld_once(a.scale + (e & BD_MASK)) : T(1);
+        const bool ok = active; // (idle lanes hold BD_HOLE)
+        yo[k] = (ok && (!(e & BD_FIRST) || a.beta)) ? __ldcg(a.y + (e & BD_MASK)) : T(0);
+        sc[k] = (ok && (e & BD_LAST) && a.scale) ? ld_once(a.scale + (e & BD_MASK)) : T(1);
       }
+    };
+    if constexpr (SLOT <= 32) cell_part2<T, N, L>(f2, tiles, ro, Dm, active, WarpSync(), yv, tm);
+    else cell_part2<T, N, L>(f2, tiles, ro, Dm, active, SlotBarSync{slot + 1, SLOT}, yv, tm);
+    request_y();
+    if (active)
+    {
 #pragma unroll
       for (int k = 0; k < N; ++k) a.y[dof[k] & BD_MASK] = (yo[k] + yv[k]) * sc[k];
     }
@@ -1600,7 +1610,7 @@ template <> struct Cfg<8> { static constexpr int SLOT = 64, W = 1, BX = 2, BY = 
 #define WFX_CELL2_MIN_N64 99
 #endif
 #ifndef WFX_CELL2_MIN_N32
-#define WFX_CELL2_MIN_N32 99
+#define WFX_CELL2_MIN_N32 8 // P7 fp32: 0.259 ms (colour order) / 0.294 (brick order) against 0.311 for the brick kernel
 #endif
 template <int N> struct Cfg2;
 template <> struct Cfg2<3> { static constexpr int CPB = 16, MINB = 2, GW = 3; };
@@ -1642,6 +1652,7 @@ template <> struct Cfg2<8> { static constexpr int CPB = WFX_C2_P7_CPB, MINB = WF
 #ifndef WFX_C3_HI_MINB
 #define WFX_C3_HI_MINB 2
 #endif
+
 template <int N> struct Cfg3;
 template <> struct Cfg3<3> { static constexpr int W = 16, BX = 8, BY = 8, BZ = 8, MINB = 2; };
 template <> struct Cfg3<4> { static constexpr int W = 16, BX = 8, BY = 8, BZ = 4, MINB = 2; };
@@ -1727,16 +1738,16 @@ struct LaunchCfg
 {
   int SLOT, W, BX, BY, BZ, CPB;
 };
-int slot_elems_rt(int N)
+int slot_elems_rt(int N, int esz)
 {
   switch (N)
   {
-  case 3: return slot_elems<3>();
-  case 4: return slot_elems<4>();
-  case 5: return slot_elems<5>();
-  case 6: return slot_elems<6>();
-  case 7: return slot_elems<7>();
-  case 8: return slot_elems<8>();
+  case 3: return esz == 8 ? slot_elems<3, 8>() : slot_elems<3, 4>();
+  case 4: return esz == 8 ? slot_elems<4, 8>() : slot_elems<4, 4>();
+  case 5: return esz == 8 ? slot_elems<5, 8>() : slot_elems<5, 4>();
+  case 6: return esz == 8 ? slot_elems<6, 8>() : slot_elems<6, 4>();
+  case 7: return esz == 8 ? slot_elems<7, 8>() : slot_elems<7, 4>();
+  case 8: return esz == 8 ? slot_elems<8, 8>() : slot_elems<8, 4>();
   }
   return 2 * N * N * N;
 }
@@ -1771,7 +1782,7 @@ struct wfx_stiffness
   // streamed-cell path (shares the colour plan): per-point dofmap with FIRST / LAST flags
   bool cell2 = false;
   bool cell2_brick = false; // cells in the order of a brick plan (one CTA per batch) instead of global colours
-  int cell2_cps = 4; // colour order: cells a slot walks per launch
+  int cell2_cps = 2; // colour order: cells a slot walks per launch
   int axis_perm[3] = {0, 1, 2}; // kernel axis a' is the mesh's tensor axis axis_perm[a'] (see detect_axis_perm)
   DevBuf<uint32_t> d_tdmf;
   DevBuf<unsigned char> d_G6perm; // private copy of G6 in the permuted axis order (empty: identity)
@@ -1917,11 +1928,11 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   using C = Cfg<N>;
   using KernPtr = void (*)(BrickArgs<T>, DMat<T, N>, int);
   const int variant = op->variant;
-  const KernPtr kern_gen = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N>>;
+  const KernPtr kern_gen = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N, sizeof(T)>>;
   KernPtr kern = kern_gen;
   size_t smem = op->smem_bytes;
-  if (variant == 1) kern = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>>, smem = op->smem_bytes_reg;
-  if (variant == 1 && op->affine) kern = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>, true>;
+  if (variant == 1) kern = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N, sizeof(T)>>, smem = op->smem_bytes_reg;
+  if (variant == 1 && op->affine) kern = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N, sizeof(T)>, true>;
   if constexpr (N == 5 && sizeof(T) == 8)
     if (variant == 2) kern = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutP4D>, smem = op->smem_bytes_reg;
   // experiment knob ("L1 is part of the budget"): extra dynamic shared memory per CTA
@@ -1970,8 +1981,8 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   if (op->persistent && part == -1 && variant == 1)
   {
     using PK = void (*)(BrickArgs<T>, PersistArgs, DMat<T, N>);
-    PK pk = op->affine ? (PK)stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N>, true>
-                       : (PK)stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N>, false>;
+    PK pk = op->affine ? (PK)stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N, sizeof(T)>, true>
+                       : (PK)stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N, sizeof(T)>, false>;
     if (op->persist_grid == 0)
     {
       int occ = 0;
@@ -2025,9 +2036,9 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
     {
       // regular batches with the regular-brick kernel, the rest with the generic one; the two
       // launches of a colour touch disjoint dofs and chain like colours do
-      launch(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>, false, true>, op->smem_bytes_reg + smem_pad,
+      launch(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N, sizeof(T)>, false, true>, op->smem_bytes_reg + smem_pad,
              op->reg_off[k], op->reg_off[k + 1] - op->reg_off[k], op->d_reg_ids.p);
-      launch(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N>, false, true>, op->smem_bytes + smem_pad,
+      launch(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N, sizeof(T)>, false, true>, op->smem_bytes + smem_pad,
              op->irr_off[k], op->irr_off[k + 1] - op->irr_off[k], op->d_irr_ids.p);
     }
     else launch(kern, smem, op->colour_off[k], op->colour_off[k + 1] - op->colour_off[k], nullptr);
@@ -2040,19 +2051,19 @@ void configure_brick(wfx_stiffness* op)
 {
   using C = Cfg<N>;
   const int optin = (int)op->ctx->smem_optin;
-  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N>>,
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N, sizeof(T)>>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>>,
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N, sizeof(T)>>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>, true>,
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N, sizeof(T)>, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>, false, true>,
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N, sizeof(T)>, false, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N>, false, true>,
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N, sizeof(T)>, false, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N>, false>,
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N, sizeof(T)>, false>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N>, true>,
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N, sizeof(T)>, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   if constexpr (N == 5 && sizeof(T) == 8)
     WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutP4D>,
@@ -2063,15 +2074,15 @@ void configure_brick(wfx_stiffness* op)
   if (const char* e = std::getenv("WFX_CARVEOUT")) carve = std::atoi(e);
   if (carve > 0)
   {
-    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N>>,
+    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N, sizeof(T)>>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>>,
+    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N, sizeof(T)>>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N>, true>,
+    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N, sizeof(T)>, true>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N>, false>,
+    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N, sizeof(T)>, false>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N>, true>,
+    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N, sizeof(T)>, true>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, carve));
   }
 }
@@ -2273,7 +2284,9 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
       if (ndofs > (int64_t)BD_MASK) fail("stiffness: more than 2^30 local dofs");
       const int nd = op->nd, n = op->N, n2 = n * n;
       // order of the cells: batches of a brick plan (default) or global cell colours
-      op->cell2_brick = true;
+      // (measured, profiles/r2_kernel_experiments.md: global colours are the faster order wherever the
+      // streamed kernel wins at all; partitioned meshes need the batches for their interface part)
+      op->cell2_brick = flags == WFX_STIFF_CELL_STREAM || nshared > 0;
       if (const char* e = std::getenv("WFX_STREAM_ORDER")) op->cell2_brick = std::strcmp(e, "colour") != 0;
       if (nshared > 0 && !op->cell2_brick) fail("stiffness: colour-ordered streamed cells do not take partitioned meshes");
       // key[c]: position of cell c in the execution order (launch, iteration); cells with equal keys
@@ -2380,7 +2393,7 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
       const int ndp = (op->nd + 7) & ~7;
       auto meta_bytes = [&](int rounds) { return (size_t)rounds * lc.W * (ndp * 2 + 4); };
       const int rounds_guess = std::max(8, (lc.BX * lc.BY * lc.BZ + lc.W - 1) / lc.W);
-      const size_t tiles_bytes = (size_t)lc.W * slot_elems_rt(op->N) * esz;
+      const size_t tiles_bytes = (size_t)lc.W * slot_elems_rt(op->N, (int)esz) * esz;
       const size_t work = tiles_bytes + meta_bytes(rounds_guess) + 32;
       const size_t avail = ctx->smem_optin > work + 1024 ? ctx->smem_optin - work - 1024 : 0;
       int nloc_cap = (int)std::min<size_t>(avail / (2 * esz), 65535);
