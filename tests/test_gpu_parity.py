@@ -212,10 +212,12 @@ def test_stiffness_ghost_only_entries_and_errors(wfx, orc, torch):
         op.apply(x, x, beta=0)
 
 
-@pytest.mark.parametrize("P", [2, 4, 6])
+@pytest.mark.parametrize("P", [2, 4, 6, 7])
 def test_stiffness_fp32(wfx, orc, torch, P):
-    mesh = _mesh(wfx, 4 if P < 6 else 2, P)
+    mesh = _mesh(wfx, 4 if P < 6 else (2 if P == 6 else 3), P)
     op = wfx.StiffnessOperator(mesh, P, dtype=np.float32)
+    # WFX_STIFF_AUTO: the streamed-cell kernel where it measured faster (P7 fp32), else a brick kernel
+    assert (op.kernel_info()["variant"] == "cell-streamed") == (P == 7)
     Go, _ = orc.precompute_geometric_data(mesh, P)
     x = np.random.default_rng(1).standard_normal(mesh.ndofs)
     yo = np.zeros(mesh.ndofs)

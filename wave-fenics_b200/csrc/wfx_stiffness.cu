@@ -1550,13 +1550,13 @@ template <> struct Cfg<4> { static constexpr int SLOT = 16, W = 8, BX = 4, BY = 
 #define WFX_P6_MINB 4 // five CTAs per SM cap the kernel at 168 registers and it spills ~100 B; four: 0 B, 0.606 -> 0.524 ms
 #endif
 #ifndef WFX_P7_BZ
-#define WFX_P7_BZ 2
+#define WFX_P7_BZ 1 // 2x2x1 cells: 38 KB per CTA, four CTAs per SM at 227 registers (no spills): fp64 0.579 -> 0.540 ms
 #endif
 #ifndef WFX_P6_BZ
 #define WFX_P6_BZ 2
 #endif
 #ifndef WFX_P7_MINB
-#define WFX_P7_MINB 3
+#define WFX_P7_MINB 4
 #endif
 template <> struct Cfg<5> { static constexpr int SLOT = 32, W = WFX_P4_W, BX = WFX_P4_BE, BY = WFX_P4_BE, BZ = WFX_P4_BZ, CPB = 8, MINB = WFX_P4_MINB, CARVEOUT = WFX_P4_CARVE, CARVEOUT32 = 0, GW = WFX_P4_GW; };
 #ifndef WFX_P5_W
@@ -1572,8 +1572,21 @@ template <> struct Cfg<5> { static constexpr int SLOT = 32, W = WFX_P4_W, BX = W
 #define WFX_P5_CARVE 58
 #endif
 template <> struct Cfg<6> { static constexpr int SLOT = 64, W = WFX_P5_W, BX = WFX_P5_BX, BY = 2, BZ = 2, CPB = 4, MINB = WFX_P5_MINB, CARVEOUT = WFX_P5_CARVE, CARVEOUT32 = 0, GW = WFX_P5_GW; };
-template <> struct Cfg<7> { static constexpr int SLOT = 64, W = 1, BX = 2, BY = 2, BZ = WFX_P6_BZ, CPB = 4, MINB = WFX_P6_MINB, CARVEOUT = 72, CARVEOUT32 = 58, GW = WFX_P6_GW; };
-template <> struct Cfg<8> { static constexpr int SLOT = 64, W = 1, BX = 2, BY = 2, BZ = WFX_P7_BZ, CPB = 2, MINB = WFX_P7_MINB, CARVEOUT = 0, CARVEOUT32 = 0, GW = WFX_P7_GW; };
+#ifndef WFX_P6_W
+#define WFX_P6_W 1
+#define WFX_P6_BX 2
+#define WFX_P6_BY 2
+#endif
+#ifndef WFX_P7_W
+#define WFX_P7_W 1
+#define WFX_P7_BX 2
+#define WFX_P7_BY 2
+#endif
+#ifndef WFX_P6_CARVE
+#define WFX_P6_CARVE 72
+#endif
+template <> struct Cfg<7> { static constexpr int SLOT = 64, W = WFX_P6_W, BX = WFX_P6_BX, BY = WFX_P6_BY, BZ = WFX_P6_BZ, CPB = 4, MINB = WFX_P6_MINB, CARVEOUT = WFX_P6_CARVE, CARVEOUT32 = 58, GW = WFX_P6_GW; };
+template <> struct Cfg<8> { static constexpr int SLOT = 64, W = WFX_P7_W, BX = WFX_P7_BX, BY = WFX_P7_BY, BZ = WFX_P7_BZ, CPB = 2, MINB = WFX_P7_MINB, CARVEOUT = 0, CARVEOUT32 = 0, GW = WFX_P7_GW; };
 
 // per-degree configuration of the streamed-cell kernel (stiff_cell2_kernel): cells per CTA, min CTAs
 // per SM, planes of G in the register window (fp64; fp32 holds a whole cell).  The slot width is
