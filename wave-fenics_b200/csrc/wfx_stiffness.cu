@@ -891,15 +891,8 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   // into registers first and consumed afterwards -- two round trips instead of six.
   V2 g[GW][3];
   uint32_t e[U];
-#ifdef WFX_BD_SHARED
-  // experiment (timing only, wrong flags on boundary bricks): one shared relative dof list
-  const uint32_t bd_shift = (__ldg(a.bdofs + d0) & BD_MASK) - (__ldg(a.bdofs) & BD_MASK);
-#define WFX_BD(idx) (ld_once(a.bdofs + (idx) - d0) + bd_shift)
-#else
-#define WFX_BD(idx) ld_once(a.bdofs + (idx))
-#endif
 #pragma unroll
-  for (int q = 0; q < U; ++q) e[q] = tid + q * NT < nloc ? WFX_BD(d0 + tid + q * NT) : BD_HOLE;
+  for (int q = 0; q < U; ++q) e[q] = tid + q * NT < nloc ? ld_once(a.bdofs + d0 + tid + q * NT) : BD_HOLE;
   const int nslots = nr * W;
   const int sc_v = tid < nslots ? __ldg(a.slot_cell + (int64_t)r0 * W + tid) : -1;
   uint16_t sb_v = 0;
@@ -954,7 +947,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
   for (int base = tid + NT * U; base < nloc; base += NT * U)
   {
 #pragma unroll
-    for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? WFX_BD(d0 + base + q * NT) : BD_HOLE;
+    for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? ld_once(a.bdofs + d0 + base + q * NT) : BD_HOLE;
 #pragma unroll
     for (int q = 0; q < U; ++q)
     {
@@ -1061,13 +1054,11 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
           if (c2 >= 0) l2_prefetch_bulk(a.G6 + (int64_t)c2 * (6 * ND), (uint32_t)(6 * ND * sizeof(T)));
         }
       // the write-back walks the batch's dof list again: keep it in L2 (it was read ~30 us ago)
-#ifndef WFX_BD_SHARED
       if (r == nr - 1 && tid == SLOT * (W > 1 ? 1 : 0))
       {
         const int64_t dn = d0 & ~(int64_t)3;
         l2_prefetch_bulk(a.bdofs + dn, (uint32_t)(((d0 + nloc + 3) & ~(int64_t)3) - dn) * 4u);
       }
-#endif
       // In the last round, warm L2 for the CTA that will take this one's place on the SM
       // (blocks are dispatched in index order, a.pf_stride of them are resident): the first
       // cells' G, the batch's dof list and its local dofmap -- what that CTA waits for first.
@@ -1087,9 +1078,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
           const int64_t dn1 = a.uni_nloc ? dn0 + a.uni_nloc : __ldg(a.dof_off + bn + 1);
           const int64_t dn = dn0 & ~(int64_t)3;
           const uint32_t nbytes = (uint32_t)(((dn1 + 3) & ~(int64_t)3) - dn) * 4u;
-#ifndef WFX_BD_SHARED
           if (nbytes) l2_prefetch_bulk(a.bdofs + dn, nbytes);
-#endif
           if constexpr (!REG)
           {
             const int nrn = a.uni_nr ? a.uni_nr : __ldg(a.round_off + bn + 1) - r0n;
@@ -1126,7 +1115,7 @@ stiff_brick_kernel(const BrickArgs<T> a, const DMat<T, N> Dm, int batch0)
     uint32_t e[U];
     T v[U], sc[U];
 #pragma unroll
-    for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? WFX_BD(d0 + base + q * NT) : BD_HOLE;
+    for (int q = 0; q < U; ++q) e[q] = base + q * NT < nloc ? ld_once(a.bdofs + d0 + base + q * NT) : BD_HOLE;
     if (base == tid)
     {
       pdl_wait(); // earlier colours have finished their writes to y
