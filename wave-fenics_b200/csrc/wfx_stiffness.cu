@@ -1571,7 +1571,16 @@ template <> struct Cfg<5> { static constexpr int SLOT = 32, W = WFX_P4_W, BX = W
 #ifndef WFX_P5_CARVE
 #define WFX_P5_CARVE 58
 #endif
-template <> struct Cfg<6> { static constexpr int SLOT = 64, W = WFX_P5_W, BX = WFX_P5_BX, BY = 2, BZ = 2, CPB = 4, MINB = WFX_P5_MINB, CARVEOUT = WFX_P5_CARVE, CARVEOUT32 = 0, GW = WFX_P5_GW; };
+#ifndef WFX_P5_SLOT
+#define WFX_P5_SLOT 64
+#endif
+#ifndef WFX_P5_BY
+#define WFX_P5_BY 2
+#endif
+#ifndef WFX_P5_BZ
+#define WFX_P5_BZ 2
+#endif
+template <> struct Cfg<6> { static constexpr int SLOT = WFX_P5_SLOT, W = WFX_P5_W, BX = WFX_P5_BX, BY = WFX_P5_BY, BZ = WFX_P5_BZ, CPB = 4, MINB = WFX_P5_MINB, CARVEOUT = WFX_P5_CARVE, CARVEOUT32 = 0, GW = WFX_P5_GW; };
 #ifndef WFX_P6_W
 #define WFX_P6_W 1
 #define WFX_P6_BX 2
@@ -1865,12 +1874,18 @@ void launch_simple(wfx_stiffness* op, const T* x, T* y, cudaStream_t st)
   WFX_CUDA(cudaGetLastError());
 }
 
+template <int N>
+struct Cell2Slot
+{
+  static constexpr int SLOT = Cfg<N>::SLOT <= 32 ? Cfg<N>::SLOT : 64;
+};
+
 template <typename T, int N>
 void launch_cell2(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta, int part, cudaStream_t st)
 {
-  using C = Cfg<N>;
   using C2 = Cfg2<N>;
   using C3 = Cfg3<N>;
+  using C = Cell2Slot<N>; // whole warps per slot
   constexpr int GW = sizeof(T) == 4 ? N : C2::GW;
   DMat<T, N> Dm;
   for (int q = 0; q < N * N; ++q) Dm.d[q] = (T)op->Dhost[q];
