@@ -199,6 +199,53 @@ def test_brick_plan_invariants_on_random_connectivity(wfx):
     run()
 
 
+@pytest.mark.parametrize("P,shape,brick,W", [(2, (5, 4, 3), (8, 8, 8), 16), (3, (3, 5, 2), (8, 8, 4), 16),
+                                             (4, (5, 6, 9), (4, 4, 4), 8), (5, (3, 2, 4), (4, 4, 2), 4)])
+def test_stream_plan_invariants_on_meshes(wfx, P, shape, brick, W):
+    """The streamed-cell kernel's plan (FIRST / LAST flags in the per-point dofmap, relabelled axes, both cell
+    orders) on ragged structured meshes: wfx_debug_stream_plan_check replays the execution order and fails on
+    any violated invariant.  Lexicographic numbering puts the contiguous (z) axis on the fast lane index;
+    renumbered dofs keep the mesh's axes."""
+    capi = wfx.capi
+    mesh = wfx.create_box_hex(shape, P, (1.0, 0.7, 1.3), perturb=0.1)
+    cen = mesh.x[mesh.xdofs].mean(axis=1)
+    for order in (True, False):
+        s = capi.debug_stream_plan_check(P, mesh.dofmap, mesh.ndofs, cen, order, brick, W)
+        assert s["axis_perm"] == [1, 2, 0] and s["untouched"] == 0
+        assert s["colours"] == 8 or order  # cell colours: the 8 parity classes; batch colours: up to 8
+        s = capi.debug_stream_plan_check(P, mesh.dofmap, mesh.ndofs + 3, cen, order, brick, W, relabel_axes=False)
+        assert s["axis_perm"] == [0, 1, 2] and s["untouched"] == 3
+    ren = wfx.create_box_hex(shape, P, (1.0, 0.7, 1.3), perturb=0.1, renumber=5)
+    assert capi.debug_stream_plan_check(P, ren.dofmap, ren.ndofs, cen, True, brick, W)["axis_perm"] == [0, 1, 2]
+    # rank-shared dofs (a lattice plane): interface batches first, never LAST; brick order only
+    M = [P * n + 1 for n in shape]
+    plane = (np.arange(M[1] * M[2]) + (M[0] // 2) * M[1] * M[2]).astype(np.int32)
+    s = capi.debug_stream_plan_check(P, mesh.dofmap, mesh.ndofs, cen, True, brick, W, shared=plane)
+    assert s["part_split"] > 0
+    with pytest.raises(wfx.WfxError, match="partitioned"):
+        capi.debug_stream_plan_check(P, mesh.dofmap, mesh.ndofs, cen, False, brick, W, shared=plane)
+
+
+def test_stream_plan_invariants_on_random_connectivity(wfx):
+    """Property test: arbitrary cell -> dof connectivity, both cell orders, with and without shared dofs."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(0, 2 ** 31 - 1), st.sampled_from([2, 3]), st.integers(1, 12), st.sampled_from([1, 2, 4, 8]),
+           st.sampled_from([1, 2, 4]), st.booleans(), st.booleans(), st.integers(0, 3))
+    def run(seed, P, ncells, W, be, brick_order, with_shared, extra):
+        rng = np.random.default_rng(seed)
+        nd = (P + 1) ** 3
+        ndofs = int(rng.integers(nd, nd * ncells + 1)) + extra
+        dofmap = np.stack([rng.choice(ndofs - extra, size=nd, replace=False) for _ in range(ncells)]).astype(np.int32)
+        cen = rng.uniform(0, 1, size=(ncells, 3)).astype(np.float32)
+        shared = rng.choice(ndofs, size=max(1, ndofs // 7), replace=False) if (with_shared and brick_order) else None
+        s = wfx.capi.debug_stream_plan_check(P, dofmap, ndofs, cen, brick_order, (be, be, be), W, shared=shared)
+        assert s["untouched"] == ndofs - len(np.unique(dofmap))
+
+    run()
+
+
 def test_structured_coordinates_from_connectivity(wfx):
     """The planner's integer cell coordinates come from the mesh connectivity, not the geometry:
     exact for any cell order, independent of shear / grading; rejected for meshes that are not one

@@ -117,6 +117,8 @@ _SIG = {
     "wfx_wave_destroy": [_vp],
     "wfx_debug_structured_coords": [C.c_int64, C.c_int64, _c_i32p, _c_i32p, C.POINTER(C.c_int)],
     # debug helper (not in wavefx.h): host-only plan construction + verification
+    "wfx_debug_stream_plan_check": [C.c_int, C.c_int64, C.c_int64, _c_i32p, C.POINTER(C.c_float), C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_int), _c_i64p],
     "wfx_debug_plan_stats": [C.c_int, C.c_int64, C.c_int64, _c_i32p, C.POINTER(C.c_float), C.c_int,
                              C.c_int, C.c_int, _c_i64p],
 }
@@ -223,6 +225,31 @@ def debug_structured_coords(xdofs, npts):
     call("wfx_debug_structured_coords", xdofs.shape[0], int(npts), i32p(xdofs.reshape(-1)), i32p(ijk.reshape(-1)),
          C.byref(ok))
     return bool(ok.value), ijk
+
+
+def debug_stream_plan_check(P, dofmap, ndofs, centroid=None, brick_order=True, brick=(4, 4, 4), W=8, shared=None,
+                            relabel_axes=True):
+    """Builds the streamed-cell kernel's plan on the host and verifies every invariant the kernel relies on
+    (verify_stream_plan); raises WfxError on a violation."""
+    dofmap = np.ascontiguousarray(dofmap, dtype=np.int32)
+    nd = (P + 1) ** 3
+    ncells = dofmap.size // nd
+    stats = np.zeros(8, dtype=np.int64)
+    axes = np.zeros(3, dtype=np.int32)
+    cptr = None
+    if centroid is not None:
+        centroid = np.ascontiguousarray(centroid, dtype=np.float32)
+        cptr = centroid.ctypes.data_as(C.POINTER(C.c_float))
+    sptr = None
+    if shared is not None:
+        flags = np.zeros(ndofs, dtype=np.uint8)
+        flags[np.asarray(shared, dtype=np.int64)] = 1
+        sptr = flags.ctypes.data_as(C.POINTER(C.c_uint8))
+    call("wfx_debug_stream_plan_check", P, ncells, ndofs, i32p(dofmap.reshape(-1)), cptr, int(bool(brick_order)),
+         int(brick[0]), int(brick[1]), int(brick[2]), W, sptr, int(bool(relabel_axes)),
+         axes.ctypes.data_as(C.POINTER(C.c_int)), stats.ctypes.data_as(_c_i64p))
+    keys = ["colours", "batches", "part_split", "uni_nr", "untouched"]
+    return dict(zip(keys, stats.tolist()), axis_perm=axes.tolist())
 
 
 def debug_plan_stats(P, dofmap, ndofs, centroid=None, brick_edge=4, W=8, nloc_cap=65535):

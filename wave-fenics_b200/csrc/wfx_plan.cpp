@@ -857,6 +857,242 @@ extern "C" int wfx_debug_structured_coords(int64_t ncells, int64_t npts, const i
   WFX_API_END
 }
 
+namespace wfx
+{
+void detect_axis_perm(int n, int64_t ncells, const int32_t* tdm, int (&s)[3])
+{
+  const int n2 = n * n, nd = n2 * n;
+  int64_t votes[3] = {0, 0, 0};
+  const int64_t ns = std::min<int64_t>(ncells, 256), step = std::max<int64_t>(1, ncells / std::max<int64_t>(ns, 1));
+  int64_t seen = 0;
+  for (int64_t c = 0; c < ncells; c += step, ++seen)
+  {
+    // tensor point (i,j,k) is entry k*n2 + i*n + j; 1-D index 0 is lattice position 0, index 2 position 1
+    const int32_t* d = tdm + c * nd;
+    const int32_t o = d[0];
+    if (std::abs(d[2 * n + 0] - o) == 1) ++votes[0]; // (2,0,0)
+    if (std::abs(d[2] - o) == 1) ++votes[1];         // (0,2,0)
+    if (std::abs(d[2 * n2] - o) == 1) ++votes[2];    // (0,0,2)
+  }
+  s[0] = 0, s[1] = 1, s[2] = 2;
+  if (2 * votes[2] > seen) s[0] = 1, s[1] = 2, s[2] = 0;
+  else if (2 * votes[0] > seen) s[0] = 2, s[1] = 0, s[2] = 1;
+}
+
+void build_stream_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm, const float* centroid,
+                       const int32_t* cell_ijk, bool brick_order, BrickShape brick, int W,
+                       const uint8_t* dof_shared, bool split_parts, bool relabel_axes, StreamPlan& sp)
+{
+  const int n = P + 1, n2 = n * n, nd = n2 * n;
+  if (n < 3) fail("stream plan: degree %d not supported", P);
+  if (ndofs > (int64_t)BD_MASK) fail("stream plan: more than 2^30 local dofs");
+  if (dof_shared && !brick_order) fail("stream plan: colour-ordered cells do not take partitioned meshes");
+  sp = StreamPlan();
+  sp.brick_order = brick_order;
+  sp.P = P;
+  sp.nd = nd;
+  sp.ncells = ncells;
+  sp.ndofs = ndofs;
+  // key[c]: position of cell c in the execution order (launch, iteration)
+  std::vector<uint32_t> key((size_t)ncells, 0);
+  if (brick_order)
+  {
+    BrickPlan bp;
+    build_brick_plan(P, ncells, ndofs, tdm, centroid, brick, W, 65535, bp, dof_shared, 8, false, cell_ijk, split_parts);
+    sp.W = bp.W;
+    sp.ncolours = bp.ncolours;
+    sp.part_split = bp.part_split;
+    sp.nbatches = bp.nbatches;
+    sp.rounds_max = bp.rounds_max;
+    sp.colour_off = bp.colour_off;
+    bool ur = bp.nbatches > 0;
+    for (int b = 0; b < bp.nbatches; ++b) ur = ur && bp.round_off[b + 1] - bp.round_off[b] == bp.round_off[1];
+    sp.uni_nr = ur ? bp.round_off[1] : 0;
+    if (bp.ncolours >= 65536 || bp.rounds_max >= 65536) fail("stream plan: order key overflow");
+    for (int k = 0; k < bp.ncolours; ++k)
+      for (int b = bp.colour_off[k]; b < bp.colour_off[k + 1]; ++b)
+        for (int r = bp.round_off[b]; r < bp.round_off[b + 1]; ++r)
+          for (int w = 0; w < bp.W; ++w)
+          {
+            const int32_t c = bp.slot_cell[(size_t)r * bp.W + w];
+            if (c >= 0) key[c] = (uint32_t)k * 65536u + (uint32_t)(r - bp.round_off[b]);
+          }
+    sp.round_off = std::move(bp.round_off);
+    sp.slot_cell = std::move(bp.slot_cell);
+  }
+  else
+  {
+    CellColourPlan cp;
+    build_cell_colour_plan(nd, ncells, ndofs, tdm, cp);
+    sp.ncolours = cp.ncolours;
+    sp.colour_off = cp.colour_off;
+    for (int k = 0; k < cp.ncolours; ++k)
+      for (int32_t p = cp.colour_off[k]; p < cp.colour_off[k + 1]; ++p) key[cp.cells[p]] = (uint32_t)k;
+    sp.cells = std::move(cp.cells);
+  }
+  std::vector<uint32_t> kmin((size_t)ndofs, 0xffffffffu), kmax((size_t)ndofs, 0);
+  for (int64_t c = 0; c < ncells; ++c)
+    for (int t = 0; t < nd; ++t)
+    {
+      const int32_t d = tdm[c * nd + t];
+      kmin[d] = std::min(kmin[d], key[c]);
+      kmax[d] = std::max(kmax[d], key[c]);
+    }
+  if (relabel_axes && ncells > 0) detect_axis_perm(n, ncells, tdm, sp.axis_perm);
+  const int s0 = sp.axis_perm[0], s1 = sp.axis_perm[1], s2 = sp.axis_perm[2];
+  sp.tdmf.resize((size_t)ncells * nd);
+  parallel_for(ncells, [&](int64_t cb, int64_t ce) {
+    for (int64_t c = cb; c < ce; ++c)
+      for (int kp = 0; kp < n; ++kp)
+        for (int ip = 0; ip < n; ++ip)
+          for (int jp = 0; jp < n; ++jp)
+          {
+            int sidx[3];
+            sidx[s0] = ip, sidx[s1] = jp, sidx[s2] = kp; // the point's indices on the mesh's own axes
+            const int32_t d = tdm[c * nd + sidx[2] * n2 + sidx[0] * n + sidx[1]];
+            uint32_t e = (uint32_t)d;
+            if (key[c] == kmin[d]) e |= BD_FIRST;
+            if (key[c] == kmax[d] && !(dof_shared && dof_shared[d])) e |= BD_LAST;
+            sp.tdmf[c * nd + kp * n2 + ip * n + jp] = e;
+          }
+  });
+  for (int64_t d = 0; d < ndofs; ++d)
+    if (kmin[d] == 0xffffffffu) sp.untouched.push_back((int32_t)d);
+}
+
+void verify_stream_plan(const StreamPlan& sp, const int32_t* tdm, const uint8_t* dof_shared)
+{
+  const int nd = sp.nd, n = sp.P + 1, n2 = n * n;
+  if ((int64_t)sp.tdmf.size() != sp.ncells * nd) fail("stream plan: wrong dofmap size");
+  {
+    int seen[3] = {0, 0, 0};
+    for (int a = 0; a < 3; ++a)
+    {
+      if (sp.axis_perm[a] < 0 || sp.axis_perm[a] > 2) fail("stream plan: bad axis relabelling");
+      seen[sp.axis_perm[a]]++;
+    }
+    if (seen[0] != 1 || seen[1] != 1 || seen[2] != 1) fail("stream plan: axis relabelling is not a permutation");
+  }
+  // replay the execution order: step = (launch, iteration); stamp[d] = last step that touched dof d
+  std::vector<int64_t> stamp((size_t)sp.ndofs, -1);
+  std::vector<uint8_t> done((size_t)sp.ncells, 0), has_last((size_t)sp.ndofs, 0);
+  std::vector<int32_t> last_cell((size_t)sp.ndofs, -1), last_pt((size_t)sp.ndofs, -1);
+  int64_t step = 0, ndone = 0;
+  auto visit = [&](int32_t c) {
+    if (c < 0 || c >= sp.ncells || done[c]) fail("stream plan: cell listed twice or out of range");
+    done[c] = 1;
+    ++ndone;
+    const int s0 = sp.axis_perm[0], s1 = sp.axis_perm[1], s2 = sp.axis_perm[2];
+    for (int kp = 0; kp < n; ++kp)
+      for (int ip = 0; ip < n; ++ip)
+        for (int jp = 0; jp < n; ++jp)
+        {
+          int sidx[3];
+          sidx[s0] = ip, sidx[s1] = jp, sidx[s2] = kp;
+          const int t = kp * n2 + ip * n + jp;
+          const uint32_t e = sp.tdmf[(int64_t)c * nd + t];
+          const int32_t d = (int32_t)(e & BD_MASK);
+          if (d != tdm[(int64_t)c * nd + sidx[2] * n2 + sidx[0] * n + sidx[1]]) fail("stream plan: dofmap entry does not match the mesh");
+          if (stamp[d] == step) fail("stream plan: two cells of one step share dof %d", d);
+          if (((e & BD_FIRST) != 0) != (stamp[d] < 0)) fail("stream plan: FIRST flag wrong at dof %d", d);
+          if (has_last[d]) fail("stream plan: dof %d touched after its LAST point", d);
+          if (e & BD_LAST)
+          {
+            if (dof_shared && dof_shared[d]) fail("stream plan: LAST set on a rank-shared dof");
+            has_last[d] = 1;
+          }
+          stamp[d] = step;
+        }
+  };
+  if (sp.brick_order)
+  {
+    if ((int)sp.colour_off.size() != sp.ncolours + 1) fail("stream plan: bad colour offsets");
+    for (int k = 0; k < sp.ncolours; ++k)
+    {
+      for (int b = sp.colour_off[k]; b < sp.colour_off[k + 1]; ++b)
+        for (int r = sp.round_off[b]; r < sp.round_off[b + 1]; ++r)
+        {
+          for (int w = 0; w < sp.W; ++w)
+          {
+            const int32_t c = sp.slot_cell[(size_t)r * sp.W + w];
+            if (c >= 0) visit(c);
+          }
+          ++step;
+        }
+    }
+    // batches of one launch run concurrently and their rounds interleave arbitrarily: a dof must not be
+    // shared between two batches of a launch at all
+    std::vector<int32_t> batch_of((size_t)sp.ndofs, -1), colour_of((size_t)sp.ndofs, -1);
+    for (int k = 0; k < sp.ncolours; ++k)
+      for (int b = sp.colour_off[k]; b < sp.colour_off[k + 1]; ++b)
+        for (int r = sp.round_off[b]; r < sp.round_off[b + 1]; ++r)
+          for (int w = 0; w < sp.W; ++w)
+          {
+            const int32_t c = sp.slot_cell[(size_t)r * sp.W + w];
+            if (c < 0) continue;
+            for (int t = 0; t < nd; ++t)
+            {
+              const int32_t d = tdm[(int64_t)c * nd + t];
+              if (colour_of[d] == k && batch_of[d] != b) fail("stream plan: two batches of launch %d share dof %d", k, d);
+              colour_of[d] = k, batch_of[d] = b;
+            }
+          }
+  }
+  else
+  {
+    for (int k = 0; k < sp.ncolours; ++k)
+    {
+      for (int32_t p = sp.colour_off[k]; p < sp.colour_off[k + 1]; ++p) visit(sp.cells[p]);
+      ++step;
+    }
+  }
+  if (ndone != sp.ncells) fail("stream plan: %lld of %lld cells scheduled", (long long)ndone, (long long)sp.ncells);
+  for (int64_t d = 0; d < sp.ndofs; ++d)
+    if (stamp[d] >= 0 && !has_last[d] && !(dof_shared && dof_shared[d])) fail("stream plan: dof %lld has no LAST point", (long long)d);
+  for (int32_t d : sp.untouched)
+    if (stamp[d] >= 0) fail("stream plan: dof %d listed as untouched", d);
+}
+} // namespace wfx
+
+// CPU-callable check of the streamed-cell plan (tests): builds it for a DOLFINx-ordered dofmap and runs
+// verify_stream_plan.  out: axis_perm[3]; stats: ncolours, nbatches, part_split, uni_nr, untouched.
+extern "C" int wfx_debug_stream_plan_check(int P, int64_t ncells, int64_t ndofs, const int32_t* dofmap_host,
+                                           const float* centroid_host, int brick_order, int bx, int by, int bz,
+                                           int W, const uint8_t* dof_shared, int relabel_axes, int* axis_perm,
+                                           int64_t* stats)
+{
+  WFX_API_BEGIN
+  using namespace wfx;
+  const int n = P + 1, n2 = n * n, nd = n2 * n;
+  std::vector<int32_t> perm(nd);
+  tensor_perm(P, perm.data());
+  std::vector<int32_t> tdm((size_t)ncells * nd);
+  for (int64_t c = 0; c < ncells; ++c)
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j)
+        for (int k = 0; k < n; ++k)
+        {
+          const int32_t d = dofmap_host[c * nd + perm[(i * n + j) * n + k]];
+          if (d < 0 || d >= ndofs) fail("dofmap entry out of range");
+          tdm[c * nd + k * n2 + i * n + j] = d;
+        }
+  StreamPlan sp;
+  build_stream_plan(P, ncells, ndofs, tdm.data(), centroid_host, nullptr, brick_order != 0, BrickShape(bx, by, bz), W,
+                    dof_shared, true, relabel_axes != 0, sp);
+  verify_stream_plan(sp, tdm.data(), dof_shared);
+  if (axis_perm)
+    for (int a = 0; a < 3; ++a) axis_perm[a] = sp.axis_perm[a];
+  if (stats)
+  {
+    stats[0] = sp.ncolours;
+    stats[1] = sp.nbatches;
+    stats[2] = sp.part_split;
+    stats[3] = sp.uni_nr;
+    stats[4] = (int64_t)sp.untouched.size();
+  }
+  WFX_API_END
+}
+
 extern "C" int wfx_debug_plan_stats(int P, int64_t ncells, int64_t ndofs,
                                     const int32_t* dofmap_host, const float* centroid_host,
                                     int brick_edge, int W, int nloc_cap, int64_t* stats)

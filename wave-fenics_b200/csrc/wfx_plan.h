@@ -102,6 +102,40 @@ void build_brick_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm,
                       BrickPlan& plan, const uint8_t* dof_shared = nullptr, int word_bytes = 8,
                       bool allow_tuned = true, const int32_t* cell_ijk = nullptr, bool split_parts = true);
 
+// Execution plan of the streamed-cell kernel (stiff_cell2_kernel): the cells in launch / iteration order
+// and the per-point dofmap with FIRST / LAST flags.
+//  brick order : launches = execution colours of a brick plan, one CTA per batch, iteration = round;
+//  colour order: launches = cell colours, a slot walks consecutive cells of its colour.
+// Cells of one (launch, iteration) share no dof -- in brick order within a batch, batches of one launch
+// being disjoint anyway.  FIRST marks the point whose cell comes first in that order at its dof, LAST the
+// last one (never set on dofs that also live on another rank).
+struct StreamPlan
+{
+  bool brick_order = true;
+  int P = 0, nd = 0, W = 0;
+  int64_t ncells = 0, ndofs = 0;
+  int ncolours = 0, part_split = 0, nbatches = 0, rounds_max = 0;
+  int uni_nr = 0;                  // > 0: every batch has this many rounds
+  std::vector<int32_t> colour_off; // [ncolours+1] into batches (brick order) or cells (colour order)
+  std::vector<int32_t> round_off;  // brick order: [nbatches+1]
+  std::vector<int32_t> slot_cell;  // brick order: [nrounds_total*W] cell id or -1
+  std::vector<int32_t> cells;      // colour order: cell ids sorted by colour
+  int axis_perm[3] = {0, 1, 2};    // kernel axis a' is the mesh's tensor axis axis_perm[a']
+  std::vector<uint32_t> tdmf;      // [ncells][nd], point order k'*n^2 + i'*n + j' of the kernel axes: dof | flags
+  std::vector<int32_t> untouched;  // vector entries no cell references
+};
+
+// Which tensor axis of the cells runs along consecutive dof numbers (lexicographic numberings of
+// structured meshes: the fastest grid axis)?  The streamed-cell kernel wants that axis on its fast lane
+// index (j'), so that a gather / update instruction touches few sectors: s[1] = that axis, or the
+// identity when no axis is contiguous (unstructured or renumbered dofs).
+void detect_axis_perm(int n, int64_t ncells, const int32_t* tdm, int (&s)[3]);
+
+void build_stream_plan(int P, int64_t ncells, int64_t ndofs, const int32_t* tdm, const float* centroid,
+                       const int32_t* cell_ijk, bool brick_order, BrickShape brick, int W,
+                       const uint8_t* dof_shared, bool split_parts, bool relabel_axes, StreamPlan& plan);
+void verify_stream_plan(const StreamPlan& plan, const int32_t* tdm, const uint8_t* dof_shared = nullptr);
+
 // Checks every invariant the kernels rely on; throws wfx::Error on violation.
 void verify_brick_plan(const BrickPlan& plan, const int32_t* tdm, const uint8_t* dof_shared = nullptr);
 void verify_cell_colour_plan(const CellColourPlan& plan, int nd, int64_t ncells, int64_t ndofs,

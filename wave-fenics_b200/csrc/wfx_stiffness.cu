@@ -1731,31 +1731,6 @@ __global__ void permute_g_axes_kernel(int n, int64_t ncells, int s0, int s1, int
   dst[2 * n2] = q;
 }
 
-// Which tensor axis of the cells runs along consecutive dof numbers (lexicographic numberings of
-// structured meshes: the fastest grid axis)?  The streamed-cell kernel wants that axis on the fast lane
-// index (j'), so that a gather / update instruction touches few sectors: returns s with s[1] = that
-// axis, or the identity when no axis is contiguous (unstructured or renumbered dofs).
-void detect_axis_perm(int n, int64_t ncells, const int32_t* tdm, int (&s)[3])
-{
-  const int n2 = n * n, nd = n2 * n;
-  int64_t votes[3] = {0, 0, 0};
-  const int64_t ns = std::min<int64_t>(ncells, 256), step = std::max<int64_t>(1, ncells / ns);
-  int64_t seen = 0;
-  for (int64_t c = 0; c < ncells; c += step, ++seen)
-  {
-    // tensor point (i,j,k) is entry k*n2 + i*n + j; 1-D index 0 is lattice position 0, index 2 position 1
-    const int32_t* d = tdm + c * nd;
-    const int32_t o = d[0];
-    if (std::abs(d[2 * n + 0] - o) == 1) ++votes[0];  // (2,0,0)
-    if (std::abs(d[2] - o) == 1) ++votes[1];          // (0,2,0)
-    if (std::abs(d[2 * n2] - o) == 1) ++votes[2];     // (0,0,2)
-  }
-  s[0] = 0, s[1] = 1, s[2] = 2;
-  if (n < 3) return;
-  if (2 * votes[2] > seen) s[0] = 1, s[1] = 2, s[2] = 0;
-  else if (2 * votes[0] > seen) s[0] = 2, s[1] = 0, s[2] = 1;
-}
-
 struct LaunchCfg
 {
   int SLOT, W, BX, BY, BZ, CPB;
@@ -2317,85 +2292,39 @@ extern "C" int wfx_stiffness_create_partitioned(wfx_ctx* ctx, wfx_geom* geom, in
       op->cell2_brick = flags == WFX_STIFF_CELL_STREAM || nshared > 0;
       if (const char* e = std::getenv("WFX_STREAM_ORDER")) op->cell2_brick = std::strcmp(e, "colour") != 0;
       if (nshared > 0 && !op->cell2_brick) fail("stiffness: colour-ordered streamed cells do not take partitioned meshes");
-      // key[c]: position of cell c in the execution order (launch, iteration); cells with equal keys
-      // share no dof.  FIRST / LAST of a point: its cell has the lowest / highest key at that dof.
-      std::vector<uint32_t> key((size_t)op->ncells, 0);
+      const Cfg3Rt c3 = cfg3_rt(op->N);
+      bool relabel = geom->g_colpos.empty(); // (a G with reordered columns keeps the mesh's axes)
+      if (const char* e = std::getenv("WFX_AXIS_PERM")) relabel = relabel && std::atoi(e) != 0;
+      StreamPlan sp;
+      build_stream_plan(op->P, op->ncells, ndofs, tdm.data(), geom->centroid.empty() ? nullptr : geom->centroid.data(),
+                        geom->cell_ijk.empty() ? nullptr : geom->cell_ijk.data(), op->cell2_brick,
+                        BrickShape(c3.BX, c3.BY, c3.BZ), c3.W, shared.empty() ? nullptr : shared.data(), split_parts,
+                        relabel, sp);
+      timer.lap("stream plan");
+      if (std::getenv("WFX_VERIFY_PLAN")) verify_stream_plan(sp, tdm.data(), shared.empty() ? nullptr : shared.data());
       if (op->cell2_brick)
       {
-        const Cfg3Rt c3 = cfg3_rt(op->N);
-        BrickPlan bp;
-        build_brick_plan(op->P, op->ncells, ndofs, tdm.data(),
-                         geom->centroid.empty() ? nullptr : geom->centroid.data(), BrickShape(c3.BX, c3.BY, c3.BZ),
-                         c3.W, 65535, bp, shared.empty() ? nullptr : shared.data(), op->dtype == WFX_F64 ? 8 : 4,
-                         false, geom->cell_ijk.empty() ? nullptr : geom->cell_ijk.data(), split_parts);
-        timer.lap("brick plan");
-        op->ncolours = bp.ncolours;
-        op->part_split = bp.part_split;
-        op->colour_off = bp.colour_off;
-        op->W = bp.W;
-        op->nbatches = bp.nbatches;
-        op->rounds_max = bp.rounds_max;
-        bool ur = bp.nbatches > 0;
-        for (int b = 0; b < bp.nbatches; ++b) ur = ur && bp.round_off[b + 1] - bp.round_off[b] == bp.round_off[1];
-        op->uni_nr = ur ? bp.round_off[1] : 0;
-        for (int k = 0; k < bp.ncolours; ++k)
-          for (int b = bp.colour_off[k]; b < bp.colour_off[k + 1]; ++b)
-            for (int r = bp.round_off[b]; r < bp.round_off[b + 1]; ++r)
-              for (int w = 0; w < bp.W; ++w)
-              {
-                const int32_t c = bp.slot_cell[(size_t)r * bp.W + w];
-                if (c >= 0) key[c] = (uint32_t)k * 65536u + (uint32_t)(r - bp.round_off[b]);
-              }
-        op->d_round_off.upload(bp.round_off);
-        op->d_slot_cell.upload(bp.slot_cell);
+        op->ncolours = sp.ncolours;
+        op->part_split = sp.part_split;
+        op->colour_off = sp.colour_off;
+        op->W = sp.W;
+        op->nbatches = sp.nbatches;
+        op->rounds_max = sp.rounds_max;
+        op->uni_nr = sp.uni_nr;
+        op->d_round_off.upload(sp.round_off);
+        op->d_slot_cell.upload(sp.slot_cell);
       }
       else
       {
-        build_cell_colour_plan(nd, op->ncells, ndofs, tdm.data(), op->cplan);
-        timer.lap("cell colour plan");
-        for (int k = 0; k < op->cplan.ncolours; ++k)
-          for (int32_t p = op->cplan.colour_off[k]; p < op->cplan.colour_off[k + 1]; ++p)
-            key[op->cplan.cells[p]] = (uint32_t)k;
-        op->d_cells.upload(op->cplan.cells);
+        op->cplan.ncolours = sp.ncolours;
+        op->cplan.colour_off = sp.colour_off;
+        op->d_cells.upload(sp.cells);
         if (const char* e = std::getenv("WFX_CELL2_CPS")) op->cell2_cps = std::max(1, std::atoi(e));
       }
-      std::vector<uint32_t> kmin((size_t)ndofs, 0xffffffffu), kmax((size_t)ndofs, 0);
-      for (int64_t c = 0; c < op->ncells; ++c)
-        for (int t = 0; t < nd; ++t)
-        {
-          const int32_t d = tdm[c * nd + t];
-          kmin[d] = std::min(kmin[d], key[c]);
-          kmax[d] = std::max(kmax[d], key[c]);
-        }
-      // axis order of the kernel: the contiguous axis of the dof numbering on the fast lane index
-      detect_axis_perm(n, op->ncells, tdm.data(), op->axis_perm);
-      if (const char* e = std::getenv("WFX_AXIS_PERM"))
-        if (std::atoi(e) == 0) op->axis_perm[0] = 0, op->axis_perm[1] = 1, op->axis_perm[2] = 2;
-      if (!geom->g_colpos.empty()) op->axis_perm[0] = 0, op->axis_perm[1] = 1, op->axis_perm[2] = 2;
+      for (int q = 0; q < 3; ++q) op->axis_perm[q] = sp.axis_perm[q];
       const int s0 = op->axis_perm[0], s1 = op->axis_perm[1], s2 = op->axis_perm[2];
-      // per-point dofmap in the kernel's (primed) point order k'*n2 + i'*n + j' with the flags; dofs
-      // that also live on another rank are never LAST (their scaling waits for the ghost reduction)
-      std::vector<uint32_t> tdmf((size_t)op->ncells * nd);
-      parallel_for(op->ncells, [&](int64_t cb, int64_t ce) {
-        for (int64_t c = cb; c < ce; ++c)
-          for (int kp = 0; kp < n; ++kp)
-            for (int ip = 0; ip < n; ++ip)
-              for (int jp = 0; jp < n; ++jp)
-              {
-                int sidx[3];
-                sidx[s0] = ip, sidx[s1] = jp, sidx[s2] = kp;
-                const int32_t d = tdm[c * nd + sidx[2] * n2 + sidx[0] * n + sidx[1]];
-                uint32_t e = (uint32_t)d;
-                if (key[c] == kmin[d]) e |= BD_FIRST;
-                if (key[c] == kmax[d] && (shared.empty() || !shared[d])) e |= BD_LAST;
-                tdmf[c * nd + kp * n2 + ip * n + jp] = e;
-              }
-      });
-      std::vector<int32_t> untouched;
-      for (int64_t d = 0; d < ndofs; ++d)
-        if (kmin[d] == 0xffffffffu) untouched.push_back((int32_t)d);
-      op->d_tdmf.upload(tdmf);
-      if (!untouched.empty()) op->d_untouched.upload(untouched);
+      op->d_tdmf.upload(sp.tdmf);
+      if (!sp.untouched.empty()) op->d_untouched.upload(sp.untouched);
       if (s0 != 0 || s1 != 1)
       {
         const size_t esz = op->dtype == WFX_F64 ? 8 : 4;
