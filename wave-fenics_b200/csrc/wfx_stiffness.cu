@@ -1531,6 +1531,9 @@ template <> struct Cfg<4> { static constexpr int SLOT = 16, W = 8, BX = 4, BY = 
 #ifndef WFX_P4_BZ
 #define WFX_P4_BZ WFX_P4_BE
 #endif
+#ifndef WFX_P4_MINB32
+#define WFX_P4_MINB32 WFX_P4_MINB
+#endif
 #ifndef WFX_P4_CARVE
 #define WFX_P4_CARVE 0
 #endif
@@ -1729,6 +1732,15 @@ __global__ void permute_g_axes_kernel(int n, int64_t ncells, int s0, int s1, int
   dst[n2] = q;
   q.x = G[s1][s2], q.y = G[s2][s2];
   dst[2 * n2] = q;
+}
+
+// min CTAs per SM of the brick kernels per scalar type (fp32 batches are half the size and the kernel
+// needs fewer registers, so more CTAs can be resident)
+template <typename T, int N>
+constexpr int minb_of()
+{
+  if constexpr (sizeof(T) == 4 && N == 5) return WFX_P4_MINB32;
+  else return Cfg<N>::MINB;
 }
 
 struct LaunchCfg
@@ -1931,13 +1943,13 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   using C = Cfg<N>;
   using KernPtr = void (*)(BrickArgs<T>, DMat<T, N>, int);
   const int variant = op->variant;
-  const KernPtr kern_gen = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N, sizeof(T)>>;
+  const KernPtr kern_gen = stiff_brick_kernel<T, N, C::SLOT, C::W, minb_of<T, N>(), false, LayoutStd<N, sizeof(T)>>;
   KernPtr kern = kern_gen;
   size_t smem = op->smem_bytes;
-  if (variant == 1) kern = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N, sizeof(T)>>, smem = op->smem_bytes_reg;
-  if (variant == 1 && op->affine) kern = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N, sizeof(T)>, true>;
+  if (variant == 1) kern = stiff_brick_kernel<T, N, C::SLOT, C::W, minb_of<T, N>(), true, LayoutStd<N, sizeof(T)>>, smem = op->smem_bytes_reg;
+  if (variant == 1 && op->affine) kern = stiff_brick_kernel<T, N, C::SLOT, C::W, minb_of<T, N>(), true, LayoutStd<N, sizeof(T)>, true>;
   if constexpr (N == 5 && sizeof(T) == 8)
-    if (variant == 2) kern = stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutP4D>, smem = op->smem_bytes_reg;
+    if (variant == 2) kern = stiff_brick_kernel<T, N, C::SLOT, C::W, minb_of<T, N>(), true, LayoutP4D>, smem = op->smem_bytes_reg;
   // experiment knob ("L1 is part of the budget"): extra dynamic shared memory per CTA
   static const size_t smem_pad = std::getenv("WFX_SMEM_PAD") ? (size_t)std::atoi(std::getenv("WFX_SMEM_PAD")) : 0;
   smem += smem_pad;
@@ -1959,7 +1971,7 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   a.beta = beta;
   a.nloc_pad = op->nloc_pad;
   a.rounds_max = op->rounds_max;
-  a.pf_stride = C::MINB * op->ctx->num_sms;
+  a.pf_stride = minb_of<T, N>() * op->ctx->num_sms;
   a.slot_base = op->d_slot_base.p;
   a.Sx = op->Sx;
   a.Sy = op->Sy;
@@ -1984,8 +1996,8 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   if (op->persistent && part == -1 && variant == 1)
   {
     using PK = void (*)(BrickArgs<T>, PersistArgs, DMat<T, N>);
-    PK pk = op->affine ? (PK)stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N, sizeof(T)>, true>
-                       : (PK)stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N, sizeof(T)>, false>;
+    PK pk = op->affine ? (PK)stiff_brick_persist<T, N, C::SLOT, C::W, minb_of<T, N>(), LayoutStd<N, sizeof(T)>, true>
+                       : (PK)stiff_brick_persist<T, N, C::SLOT, C::W, minb_of<T, N>(), LayoutStd<N, sizeof(T)>, false>;
     if (op->persist_grid == 0)
     {
       int occ = 0;
@@ -2039,9 +2051,9 @@ void launch_brick(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
     {
       // regular batches with the regular-brick kernel, the rest with the generic one; the two
       // launches of a colour touch disjoint dofs and chain like colours do
-      launch(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N, sizeof(T)>, false, true>, op->smem_bytes_reg + smem_pad,
+      launch(stiff_brick_kernel<T, N, C::SLOT, C::W, minb_of<T, N>(), true, LayoutStd<N, sizeof(T)>, false, true>, op->smem_bytes_reg + smem_pad,
              op->reg_off[k], op->reg_off[k + 1] - op->reg_off[k], op->d_reg_ids.p);
-      launch(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N, sizeof(T)>, false, true>, op->smem_bytes + smem_pad,
+      launch(stiff_brick_kernel<T, N, C::SLOT, C::W, minb_of<T, N>(), false, LayoutStd<N, sizeof(T)>, false, true>, op->smem_bytes + smem_pad,
              op->irr_off[k], op->irr_off[k + 1] - op->irr_off[k], op->d_irr_ids.p);
     }
     else launch(kern, smem, op->colour_off[k], op->colour_off[k + 1] - op->colour_off[k], nullptr);
@@ -2054,22 +2066,22 @@ void configure_brick(wfx_stiffness* op)
 {
   using C = Cfg<N>;
   const int optin = (int)op->ctx->smem_optin;
-  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N, sizeof(T)>>,
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, minb_of<T, N>(), false, LayoutStd<N, sizeof(T)>>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N, sizeof(T)>>,
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, minb_of<T, N>(), true, LayoutStd<N, sizeof(T)>>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N, sizeof(T)>, true>,
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, minb_of<T, N>(), true, LayoutStd<N, sizeof(T)>, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N, sizeof(T)>, false, true>,
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, minb_of<T, N>(), true, LayoutStd<N, sizeof(T)>, false, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N, sizeof(T)>, false, true>,
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, minb_of<T, N>(), false, LayoutStd<N, sizeof(T)>, false, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N, sizeof(T)>, false>,
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persist<T, N, C::SLOT, C::W, minb_of<T, N>(), LayoutStd<N, sizeof(T)>, false>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N, sizeof(T)>, true>,
+  WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persist<T, N, C::SLOT, C::W, minb_of<T, N>(), LayoutStd<N, sizeof(T)>, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   if constexpr (N == 5 && sizeof(T) == 8)
-    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutP4D>,
+    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, minb_of<T, N>(), true, LayoutP4D>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   // Shared-memory carve-out (percent of the SM's 228 KB): L1 is what is left, and L1 is the landing
   // buffer of the loads in flight.  Default: the driver's choice (max occupancy).
@@ -2077,15 +2089,15 @@ void configure_brick(wfx_stiffness* op)
   if (const char* e = std::getenv("WFX_CARVEOUT")) carve = std::atoi(e);
   if (carve > 0)
   {
-    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, false, LayoutStd<N, sizeof(T)>>,
+    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, minb_of<T, N>(), false, LayoutStd<N, sizeof(T)>>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N, sizeof(T)>>,
+    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, minb_of<T, N>(), true, LayoutStd<N, sizeof(T)>>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, C::MINB, true, LayoutStd<N, sizeof(T)>, true>,
+    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_kernel<T, N, C::SLOT, C::W, minb_of<T, N>(), true, LayoutStd<N, sizeof(T)>, true>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N, sizeof(T)>, false>,
+    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persist<T, N, C::SLOT, C::W, minb_of<T, N>(), LayoutStd<N, sizeof(T)>, false>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persist<T, N, C::SLOT, C::W, C::MINB, LayoutStd<N, sizeof(T)>, true>,
+    WFX_CUDA(cudaFuncSetAttribute(stiff_brick_persist<T, N, C::SLOT, C::W, minb_of<T, N>(), LayoutStd<N, sizeof(T)>, true>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, carve));
   }
 }
