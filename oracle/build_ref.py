@@ -1,7 +1,8 @@
 """Builds oracle/_ref/libwfref_cuda.so from the REFERENCE's own CUDA sources (read in place under
 /root/reference, never copied) plus the forwarding shim oracle/ref_cuda_shim.cu.
 
-TEST INFRASTRUCTURE ONLY.  What compiles of the reference without its un-vendored dependencies
+TEST INFRASTRUCTURE ONLY.  build_cpu() does the same for the two cell kernels of the CPU operators
+(skernel, mkernel of common/operators.hpp), see oracle/ref_cpu_shim.cpp.  What compiles of the reference without its un-vendored dependencies
 (DOLFINx, Basix, xtensor, FFCx, MPI) are the device primitives of the hackathon GPU operators:
 common/cuda/scatter.cu (gather, atomicAdd scatter) and common/cuda/transform.cu (pointwise detJ
 multiply).  Everything else on the hot path includes <dolfinx.h> / <basix/...> / <xtensor/...> and is
@@ -37,5 +38,83 @@ def build(force=False):
     return LIB
 
 
+LIB_CPU = os.path.join(OUT, "libwfref_cpu.so")
+
+
+def _braces(lines, i):
+    """Index of the line that closes the first brace opened on or after line i."""
+    depth, seen, j = 0, False, i
+    while True:
+        for ch in lines[j]:
+            if ch == "{":
+                depth += 1
+                seen = True
+            elif ch == "}":
+                depth -= 1
+        if seen and depth == 0:
+            return j
+        j += 1
+
+
+def _cut(text, marker, after=None, with_template=True):
+    """The text of the definition whose first line contains `marker` (the first one after a line
+    containing `after`, if given): from its `template <...>` line, when it has one, to its closing brace."""
+    lines = text.split("\n")
+    lo = 0
+    if after is not None:
+        lo = next(i for i, l in enumerate(lines) if after in l)
+    hits = [i for i in range(lo, len(lines)) if marker in lines[i]]
+    if not hits:
+        raise RuntimeError("reference header: no definition of %r" % marker)
+    i = hits[0]
+    start = i - 1 if (with_template and "template" in lines[i - 1]) else i
+    return "\n".join(lines[start:_braces(lines, i) + 1]) + "\n"
+
+
+def build_cpu(force=False):
+    """oracle/_ref/libwfref_cpu.so: the reference's own CPU code of the hot path that needs none of its
+    dependencies' arithmetic -- skernel / mkernel, the two operators' call loops (common/operators.hpp),
+    kernels::copy / axpy and LinearGLLOpt::init / f0 / f1 / rk4 (common/LinearGLL.hpp) -- cut out of the
+    headers where they lie and compiled against the stand-ins of oracle/ref_cpu_shim.cpp with the parity
+    flags of the oracle (-O2 -ffp-contract=off).  Returns the library path, or None when the reference
+    sources are not present and no prebuilt library exists."""
+    hdr = os.path.join(REF, "common", "operators.hpp")
+    whdr = os.path.join(REF, "common", "LinearGLL.hpp")
+    shim = os.path.join(HERE, "ref_cpu_shim.cpp")
+    if not (os.path.exists(hdr) and os.path.exists(whdr)):
+        return LIB_CPU if os.path.exists(LIB_CPU) else None
+    if not force and os.path.exists(LIB_CPU) and os.path.getmtime(LIB_CPU) >= max(
+            os.path.getmtime(hdr), os.path.getmtime(whdr), os.path.getmtime(shim), os.path.getmtime(__file__)):
+        return LIB_CPU
+    os.makedirs(OUT, exist_ok=True)
+    ops, wave = open(hdr).read(), open(whdr).read()
+    pieces = {
+        "ref_cell_kernels.inc": _cut(ops, "inline void mkernel(") + _cut(ops, "inline void skernel("),
+        "ref_mass_call.inc": _cut(ops, "void operator()(", after="class MassOperatorCPU"),
+        "ref_stiffness_call.inc": _cut(ops, "void operator()(", after="class StiffnessOperator"),
+        "ref_wave_kernels.inc": _cut(wave, "namespace kernels", with_template=False),
+        "ref_wave_methods.inc": "".join(_cut(wave, sig, after="class LinearGLLOpt", with_template=False)
+                                        for sig in ("void init()", "void f0(", "void f1(", "void rk4(")),
+    }
+    written = []
+    try:
+        for name, text in pieces.items():
+            path = os.path.join(OUT, name)
+            with open(path, "w") as fh:
+                fh.write(text)
+            written.append(path)
+        cmd = ["g++", "-O2", "-std=c++17", "-march=x86-64-v3", "-ffp-contract=off", "-shared", "-fPIC", "-I", OUT, shim,
+               "-o", LIB_CPU]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("building oracle/_ref/libwfref_cpu.so failed")
+    finally:
+        for path in written:
+            os.remove(path)  # reference text never stays in the tree, not even in the ignored directory
+    return LIB_CPU
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
+    print(build_cpu(force="--force" in sys.argv))

@@ -106,6 +106,81 @@ def ref_cuda():
     return L
 
 
+def ref_cpu():
+    """ctypes handle of oracle/_ref/libwfref_cpu.so -- the REFERENCE's own cell kernels skernel and mkernel
+    (common/operators.hpp:113-133, 36-40), cut out of the header where it lies under /root/reference and
+    compiled by oracle/build_ref.py -- or None when it has not been built.
+      wfref_skernel(A[nd] (+=), w[nd], G[nq][3][3], dphi[3][nq][nd], nq, nd)
+      wfref_mkernel(A[nq] (=), w[nq], detJ[nq], nq, nd)"""
+    from . import build_ref
+    path = build_ref.build_cpu()
+    if not path or not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.wfref_skernel.argtypes = [_f64p, _f64p, _f64p, _f64p, C.c_int, C.c_int]
+    L.wfref_skernel.restype = None
+    L.wfref_mkernel.argtypes = [_f64p, _f64p, _f64p, C.c_int, C.c_int]
+    L.wfref_mkernel.restype = None
+    L.wfref_stiffness_apply.argtypes = [C.c_int, C.c_int, C.c_int, _i32p, _f64p, _f64p, _f64p, _f64p]
+    L.wfref_stiffness_apply.restype = None
+    L.wfref_mass_apply.argtypes = [C.c_int, C.c_int, C.c_int, _i32p, _f64p, _i32p, _f64p, _f64p]
+    L.wfref_mass_apply.restype = None
+    d = C.c_double
+    L.wfref_rk4.argtypes = [C.c_int, C.c_int, C.c_int, _i32p, _f64p, _f64p, _f64p, _f64p, _f64p, d, d, d, d, d, d,
+                            _f64p, _f64p]
+    L.wfref_rk4.restype = None
+    L.wfref_f1.argtypes = [C.c_int, C.c_int, C.c_int, _i32p, _f64p, _f64p, _f64p, _f64p, _f64p, d, d, d, d,
+                           _f64p, _f64p, _f64p]
+    L.wfref_f1.restype = None
+    return L
+
+
+def reference_stiffness_apply(mesh, P, G, x, y):
+    """y += A x through the REFERENCE's own StiffnessOperator::operator() and skernel
+    (common/operators.hpp:182-200, 113-133), compiled into oracle/_ref/libwfref_cpu.so."""
+    nd = (P + 1) ** 3
+    dphi = np.ascontiguousarray(tabulate_dphi(P))
+    dm = np.ascontiguousarray(mesh.dofmap, dtype=np.int32)
+    G = np.ascontiguousarray(G, dtype=np.float64)
+    ref_cpu().wfref_stiffness_apply(mesh.ncells, mesh.ndofs, nd, _i(dm.reshape(-1)), _f(G.reshape(-1)),
+                                    _f(dphi.reshape(-1)), _f(x), _f(y))
+
+
+def reference_mass_apply(mesh, P, detJ, x, y):
+    """y += M x through the REFERENCE's own MassOperatorCPU::operator() and mkernel
+    (common/operators.hpp:85-108, 36-40)."""
+    nd = (P + 1) ** 3
+    dm = np.ascontiguousarray(mesh.dofmap, dtype=np.int32)
+    detJ = np.ascontiguousarray(detJ, dtype=np.float64)
+    pm = np.ascontiguousarray(perm(P), dtype=np.int32)
+    ref_cpu().wfref_mass_apply(mesh.ncells, mesh.ndofs, nd, _i(dm.reshape(-1)), _f(detJ.reshape(-1)), _i(pm),
+                               _f(x), _f(y))
+
+
+def reference_rk4(mesh, P, G, m, m1, m2, c0, f0, p0, t0, tf, dt, u, v):
+    """The REFERENCE's own LinearGLLOpt::rk4 / f0 / f1 / kernels::copy / axpy (common/LinearGLL.hpp:15-35,
+    130-287) around its own stiffness operator; u, v updated in place.  The boundary form (FFCx kernel in
+    the reference) is the diagonal GLL facet form with the facet masses m1, m2."""
+    nd = (P + 1) ** 3
+    dphi = np.ascontiguousarray(tabulate_dphi(P))
+    dm = np.ascontiguousarray(mesh.dofmap, dtype=np.int32)
+    G = np.ascontiguousarray(G, dtype=np.float64)
+    ref_cpu().wfref_rk4(mesh.ncells, mesh.ndofs, nd, _i(dm.reshape(-1)), _f(G.reshape(-1)), _f(dphi.reshape(-1)),
+                        _f(m), _f(m1), _f(m2), c0, f0, p0, t0, tf, dt, _f(u), _f(v))
+
+
+def reference_f1(mesh, P, G, m, m1, m2, c0, f0, p0, t, u, v):
+    """dv/dt = f1(t, u, v) through the REFERENCE's own LinearGLLOpt::f1 (common/LinearGLL.hpp:151-192)."""
+    nd = (P + 1) ** 3
+    dphi = np.ascontiguousarray(tabulate_dphi(P))
+    dm = np.ascontiguousarray(mesh.dofmap, dtype=np.int32)
+    G = np.ascontiguousarray(G, dtype=np.float64)
+    out = np.empty(mesh.ndofs)
+    ref_cpu().wfref_f1(mesh.ncells, mesh.ndofs, nd, _i(dm.reshape(-1)), _f(G.reshape(-1)), _f(dphi.reshape(-1)),
+                       _f(m), _f(m1), _f(m2), c0, f0, p0, t, _f(u), _f(v), _f(out))
+    return out
+
+
 def _f(a):
     assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(_f64p)

@@ -6,14 +6,23 @@
  * cpu_baseline / --impl reference legs of bench.py, always as the checker or the
  * timed CPU baseline, never as the product path.
  *
- * PARITY UNPINNED: the reference (/root/reference) has no tests, golden vectors
- * or fixtures for this path, and it cannot be built here (DOLFINx, Basix,
- * xtensor, FFCx, MPI are absent and un-vendored).  The Basix/DOLFINx pieces the
- * reference calls (GLL quadrature, gll_warped Lagrange tabulation, tensor-product
- * permutation, cmap tabulation, math::det / math::inv, FFCx facet kernel) are
- * restated from their published algorithms; each such function says [recalled].
- * The pins that replace golden vectors are the analytic known answers in
- * tests/test_oracle_kat.py.
+ * PARITY, what is pinned and what is not.  The reference (/root/reference) has no
+ * tests, golden vectors or fixtures for this path, and its headers cannot be built
+ * as a whole (DOLFINx, Basix, xtensor, FFCx, MPI are absent and un-vendored).
+ *  PINNED to the reference's own code: the cell kernels skernel / mkernel, the call
+ *   loops of StiffnessOperator / MassOperatorCPU, kernels::copy / axpy and
+ *   LinearGLLOpt::init / f0 / f1 / rk4 are cut out of the reference headers at build
+ *   time and compiled against container stand-ins (oracle/build_ref.py,
+ *   oracle/ref_cpu_shim.cpp -> oracle/_ref/libwfref_cpu.so); the restatements below
+ *   reproduce them BIT FOR BIT -- operators, right-hand side, whole RK4 trajectories
+ *   (tests/test_reference_pins.py).  Likewise gather / scatter / transform1 against
+ *   the reference's CUDA kernels (oracle/_ref/libwfref_cuda.so).
+ *  UNPINNED (third-party arithmetic the reference calls, absent here): the Basix /
+ *   DOLFINx pieces -- GLL quadrature, gll_warped Lagrange tabulation, tensor-product
+ *   permutation, cmap tabulation, math::det / math::inv inside
+ *   precompute_geometric_data, the FFCx facet kernel -- are restated from their
+ *   published algorithms; each such function says [recalled].  Their pins are the
+ *   analytic known answers in tests/test_oracle_kat.py.
  *
  * Every function cites the reference file:line it follows (relative to
  * /root/reference).

@@ -882,3 +882,55 @@ def test_primitives_against_the_reference_cuda_kernels(wfx, orc, torch, dtype):
     mass(x, y)
     torch.cuda.synchronize()
     assert float((y - y_ref).norm() / y_ref.norm()) < (1e-14 if dtype == np.float64 else 2e-6)
+
+
+# ---- the reference's own CPU code (oracle/_ref/libwfref_cpu.so, cut out of /root/reference's headers) -----
+@pytest.mark.gpu
+@pytest.mark.parametrize("P,shape,perturb", [(4, (4, 3, 2), 0.15), (2, (5, 4, 3), 0.15), (5, (2, 2, 2), 0.1)])
+def test_cuda_operators_against_the_reference_cpu_code(wfx, orc, torch, P, shape, perturb):
+    """The CUDA stiffness and mass operators against the REFERENCE's own StiffnessOperator::operator() /
+    skernel and MassOperatorCPU::operator() / mkernel (common/operators.hpp), compiled from the reference
+    sources (tests/test_reference_pins.py has the bit-for-bit pin of the oracle to the same code)."""
+    if orc.ref_cpu() is None:
+        pytest.skip("oracle/_ref/libwfref_cpu.so was not built (needs /root/reference at build time)")
+    mesh = wfx.create_box_hex(shape, P, (L, 0.7 * L, 1.3 * L), perturb=perturb)
+    geo = wfx.Geometry(mesh, P)
+    Go, detJ = orc.precompute_geometric_data(mesh, P)
+    rng = np.random.default_rng(21)
+    x, y0 = rng.standard_normal(mesh.ndofs), rng.standard_normal(mesh.ndofs)
+    yr = y0.copy()
+    orc.reference_stiffness_apply(mesh, P, Go, x, yr)
+    for mode in (wfx.capi.STIFF_AUTO, wfx.capi.STIFF_CELL_STREAM, wfx.capi.STIFF_CELL_COLOUR):
+        op = wfx.StiffnessOperator(mesh, P, geometry=geo, mode=mode)
+        yd = dev(torch, y0)
+        op(dev(torch, x), yd)                              # y += A x like the reference
+        assert rel_l2(yd.cpu().numpy() - y0, yr - y0) < TOL64
+    mr = np.zeros(mesh.ndofs)
+    orc.reference_mass_apply(mesh, P, detJ, np.ones(mesh.ndofs), mr)
+    assert np.array_equal(wfx.MassOperator(mesh, P, geometry=geo).diagonal(), mr)   # lumped mass: bit-exact
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,perturb,nsteps,frac", [((4, 3, 2), 0.15, 40, 0.0), ((3, 3, 3), 0.0, 25, 0.4)])
+def test_cuda_rk4_against_the_reference_time_stepper(wfx, orc, torch, capfd, shape, perturb, nsteps, frac):
+    """The CUDA time stepper against the REFERENCE's own LinearGLLOpt::rk4 / f0 / f1 / kernels::axpy / copy
+    (common/LinearGLL.hpp) over whole trajectories, including a shorter last step."""
+    if orc.ref_cpu() is None:
+        pytest.skip("oracle/_ref/libwfref_cpu.so was not built (needs /root/reference at build time)")
+    P, c0, f0, p0 = 4, 1500.0, 0.5e6, 6e4
+    mesh = wfx.create_box_hex(shape, P, (L * shape[0] / 8, L * shape[1] / 8, L * shape[2] / 8), perturb=perturb)
+    Go, detJ = orc.precompute_geometric_data(mesh, P)
+    m = np.zeros(mesh.ndofs)
+    orc.reference_mass_apply(mesh, P, detJ, np.ones(mesh.ndofs), m)
+    m1, m2 = orc.boundary_facet_mass(mesh, P)
+    dt = wfx.cfl_timestep(mesh.h_min, c0, P, f0)
+    tf = (nsteps + frac) * dt
+    ur, vr = np.zeros(mesh.ndofs), np.zeros(mesh.ndofs)
+    orc.reference_rk4(mesh, P, Go, m, m1, m2, c0, f0, p0, 0.0, tf, dt, ur, vr)
+    capfd.readouterr()
+    eqn = wfx.LinearGLLOpt(mesh, None, P, c0, f0, p0)
+    eqn.init()
+    s, t = eqn.rk4(0.0, tf, dt)
+    u, v = eqn.get_state()
+    assert s == nsteps + (1 if frac else 0) and np.abs(ur).max() > 0
+    assert rel_l2(u, ur) < TOL64 and rel_l2(v, vr) < TOL64

@@ -1,0 +1,124 @@
+"""The oracle pinned to REFERENCE CODE where the reference compiles.  Cut out of the headers where they lie
+under /root/reference and compiled into oracle/_ref/libwfref_cpu.so (oracle/build_ref.py) against the small
+container stand-ins of oracle/ref_cpu_shim.cpp: the cell kernels `skernel` / `mkernel`, the call loops
+StiffnessOperator::operator() / MassOperatorCPU::operator() (common/operators.hpp), kernels::copy / axpy and
+LinearGLLOpt::init / f0 / f1 / rk4 (common/LinearGLL.hpp).  The oracle's restatements must reproduce them BIT
+FOR BIT (same flags: -O2 -ffp-contract=off) -- operators, right-hand side and whole RK4 trajectories.  What
+stays restated (third-party arithmetic, absent here): Basix tables, DOLFINx geometry, the FFCx facet kernel.
+The GPU box uses the prebuilt library (it travels with the snapshot)."""
+import numpy as np
+import pytest
+
+from oracle import refmesh
+
+CASES = [(2, (3, 2, 2), 0.15), (3, (2, 2, 3), 0.15), (4, (2, 2, 2), 0.15), (4, (3, 1, 2), 0.0), (5, (1, 2, 1), 0.2)]
+
+
+@pytest.fixture(scope="module")
+def ref(orc):
+    L = orc.ref_cpu()
+    if L is None:
+        pytest.skip("oracle/_ref/libwfref_cpu.so was not built (needs /root/reference at build time)")
+    return L
+
+
+@pytest.mark.parametrize("P,shape,perturb", CASES)
+def test_oracle_stiffness_is_the_reference_skernel(orc, ref, P, shape, perturb):
+    mesh = refmesh.box(shape, P, (0.1, 0.07, 0.13), perturb=perturb)
+    G, _ = orc.precompute_geometric_data(mesh, P)
+    rng = np.random.default_rng(P)
+    x, y0 = rng.standard_normal(mesh.ndofs), rng.standard_normal(mesh.ndofs)
+    yo, yr = y0.copy(), y0.copy()
+    orc.stiffness_apply(mesh, P, G, x, yo, dense=True)       # the oracle's restatement
+    orc.reference_stiffness_apply(mesh, P, G, x, yr)         # the reference's own skernel
+    assert np.abs(yr - y0).max() > 0
+    assert np.array_equal(yo, yr)
+    # the sum-factorised form of the oracle (what the large GPU comparisons use) agrees to rounding
+    ys = y0.copy()
+    orc.stiffness_apply(mesh, P, G, x, ys, dense=False)
+    assert np.linalg.norm(ys - yr) <= 1e-13 * np.linalg.norm(yr - y0)
+
+
+@pytest.mark.parametrize("P,shape,perturb", CASES)
+def test_oracle_mass_is_the_reference_mkernel(orc, ref, P, shape, perturb):
+    mesh = refmesh.box(shape, P, (0.1, 0.07, 0.13), perturb=perturb)
+    _, detJ = orc.precompute_geometric_data(mesh, P)
+    rng = np.random.default_rng(10 + P)
+    x, y0 = rng.standard_normal(mesh.ndofs), rng.standard_normal(mesh.ndofs)
+    yo, yr = y0.copy(), y0.copy()
+    orc.mass_apply(mesh, P, detJ, x, yo)
+    orc.reference_mass_apply(mesh, P, detJ, x, yr)
+    assert np.array_equal(yo, yr)
+
+
+def test_reference_skernel_ignores_params_and_accumulates(orc, ref):
+    """Quirks the restatement keeps: c0 = 1500 hard-coded, A is accumulated into."""
+    P, nd = 2, 27
+    dphi = np.ascontiguousarray(orc.tabulate_dphi(P))
+    rng = np.random.default_rng(0)
+    w, G = rng.standard_normal(nd), rng.standard_normal((nd, 3, 3))
+    A = np.ones(nd)
+    ref.wfref_skernel(orc._f(A), orc._f(w), orc._f(G.reshape(-1)), orc._f(dphi.reshape(-1)), nd, nd)
+    B = np.zeros(nd)
+    ref.wfref_skernel(orc._f(B), orc._f(w), orc._f(G.reshape(-1)), orc._f(dphi.reshape(-1)), nd, nd)
+    assert np.allclose(A - 1.0, B, rtol=0, atol=1e-9 * np.abs(B).max())
+    # -c0^2 with c0 = 1500: against the formula evaluated in numpy
+    wq = np.einsum("aqi,i->qa", dphi, w)
+    f = -1500.0 ** 2 * np.einsum("qab,qb->qa", G, wq)
+    want = np.einsum("qa,aqi->i", f, dphi)
+    assert np.linalg.norm(B - want) <= 1e-13 * np.linalg.norm(want)
+
+
+def _wave_setup(wfx, orc, P, shape, perturb):
+    Lx = 0.1
+    mesh = wfx.create_box_hex(shape, P, (Lx * shape[0] / 8, Lx * shape[1] / 8, Lx * shape[2] / 8), perturb=perturb)
+    G, detJ = orc.precompute_geometric_data(mesh, P)
+    m = np.zeros(mesh.ndofs)
+    orc.reference_mass_apply(mesh, P, detJ, np.ones(mesh.ndofs), m)      # m = M 1 (LinearGLL.hpp:102-110)
+    mo = np.zeros(mesh.ndofs)
+    orc.mass_apply(mesh, P, detJ, np.ones(mesh.ndofs), mo)
+    assert np.array_equal(m, mo)
+    m1, m2 = orc.boundary_facet_mass(mesh, P)
+    return mesh, G, m, m1, m2
+
+
+@pytest.mark.parametrize("P,shape,perturb", [(2, (4, 3, 2), 0.15), (4, (2, 2, 2), 0.15), (3, (3, 2, 2), 0.0)])
+def test_oracle_f1_is_the_reference_f1(wfx, orc, ref, P, shape, perturb):
+    c0, f0, p0 = 1500.0, 0.5e6, 6e4
+    mesh, G, m, m1, m2 = _wave_setup(wfx, orc, P, shape, perturb)
+    rng = np.random.default_rng(3)
+    u, v = rng.standard_normal(mesh.ndofs), rng.standard_normal(mesh.ndofs)
+    for t in (0.0, 0.3e-6, 7.9e-6, 2.0e-5):              # inside, at the end of and after the Hann ramp
+        got = orc.reference_f1(mesh, P, G, m, m1, m2, c0, f0, p0, t, u, v)
+        # one Euler-free way to reach the oracle's f1: a single RK4 stage is not exposed, so compose it from
+        # the oracle's operator (bit-identical to the reference's, above) and the formulas of :155-191
+        w0, T, alpha = 2.0 * np.pi * f0, 1.0 / f0, 4.0
+        window = 0.5 * (1.0 - np.cos(f0 * np.pi * t / alpha)) if t < T * alpha else 1.0
+        g = window * p0 * w0 / c0 * np.cos(w0 * t)
+        b = np.zeros(mesh.ndofs)
+        orc.stiffness_apply(mesh, P, G, u, b, dense=True)
+        want = (b + (c0 * c0 * g * m1 - c0 * v * m2)) / m
+        assert np.linalg.norm(got - want) <= 1e-15 * np.linalg.norm(want)
+
+
+@pytest.mark.parametrize("P,shape,perturb,nsteps,frac", [(2, (4, 3, 2), 0.15, 12, 0.0), (4, (2, 2, 2), 0.15, 6, 0.0),
+                                                         (3, (3, 2, 2), 0.0, 9, 0.37), (4, (3, 2, 1), 0.1, 60, 0.5)])
+def test_oracle_rk4_is_the_reference_rk4(wfx, orc, ref, capfd, P, shape, perturb, nsteps, frac):
+    """Whole trajectories: the reference's rk4 loop (tableau, stage algebra, axpy on owned entries, dt clipped
+    at the final time, final copies), its f0 / f1 and its stiffness operator, against the oracle's restatement
+    -- bit for bit, from rest through the source ramp and from a random state."""
+    c0, f0, p0 = 1500.0, 0.5e6, 6e4
+    mesh, G, m, m1, m2 = _wave_setup(wfx, orc, P, shape, perturb)
+    dt = wfx.cfl_timestep(mesh.h_min, c0, P, f0)
+    tf = (nsteps + frac) * dt                            # frac > 0: a last, shorter step (:241)
+    rng = np.random.default_rng(5)
+    for u0, v0 in ((np.zeros(mesh.ndofs), np.zeros(mesh.ndofs)),
+                   (rng.standard_normal(mesh.ndofs), 1e3 * rng.standard_normal(mesh.ndofs))):
+        uo, vo = u0.copy(), v0.copy()
+        steps, t_end = orc.rk4(mesh, P, G, m, m1, m2, c0, f0, p0, 0.0, tf, dt, uo, vo, sumfact=False)
+        ur, vr = u0.copy(), v0.copy()
+        orc.reference_rk4(mesh, P, G, m, m1, m2, c0, f0, p0, 0.0, tf, dt, ur, vr)
+        assert steps == nsteps + (1 if frac else 0)
+        assert np.abs(ur).max() > 0
+        assert np.array_equal(uo, ur) and np.array_equal(vo, vr)
+    capfd.readouterr()                                   # (the reference prints its progress every 50 steps)
