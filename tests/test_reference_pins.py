@@ -6,10 +6,19 @@ LinearGLLOpt::init / f0 / f1 / rk4 (common/LinearGLL.hpp).  The oracle's restate
 FOR BIT (same flags: -O2 -ffp-contract=off) -- operators, right-hand side and whole RK4 trajectories.  What
 stays restated (third-party arithmetic, absent here): Basix tables, DOLFINx geometry, the FFCx facet kernel.
 The GPU box uses the prebuilt library (it travels with the snapshot)."""
+import importlib.util
+import os
+
 import numpy as np
 import pytest
 
 from oracle import refmesh
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_spec = importlib.util.spec_from_file_location("make_reference_golden",
+                                               os.path.join(HERE, "golden", "make_reference_golden.py"))
+mrg = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(mrg)
 
 CASES = [(2, (3, 2, 2), 0.15), (3, (2, 2, 3), 0.15), (4, (2, 2, 2), 0.15), (4, (3, 1, 2), 0.0), (5, (1, 2, 1), 0.2)]
 
@@ -122,3 +131,50 @@ def test_oracle_rk4_is_the_reference_rk4(wfx, orc, ref, capfd, P, shape, perturb
         assert np.abs(ur).max() > 0
         assert np.array_equal(uo, ur) and np.array_equal(vo, vr)
     capfd.readouterr()                                   # (the reference prints its progress every 50 steps)
+
+
+# ---- golden vectors generated by the reference's own code (tests/golden/reference_*.npz) --------------------
+def _golden(name):
+    return dict(np.load(os.path.join(HERE, "golden", name + ".npz")))
+
+
+@pytest.mark.parametrize("name", list(mrg.CASES))
+def test_reference_code_regenerates_its_golden_vectors(wfx, orc, ref, capfd, name):
+    want, got = _golden(name), mrg.compute_reference(wfx, orc, name)
+    capfd.readouterr()
+    assert sorted(got) == sorted(want)
+    for k in want:
+        assert np.array_equal(np.asarray(got[k]), want[k]), k
+
+
+@pytest.mark.parametrize("name", list(mrg.CASES))
+def test_oracle_reproduces_the_reference_golden_vectors(wfx, orc, name):
+    """Runs wherever the fixtures are, with or without the reference library: bit for bit."""
+    want, got = _golden(name), mrg.compute_oracle(wfx, orc, name)
+    for k in want:
+        assert np.array_equal(np.asarray(got[k]), want[k]), k
+    assert np.abs(want["rk4_from_rest_u"]).max() > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(mrg.CASES))
+def test_cuda_path_matches_the_reference_golden_vectors(wfx, orc, name):
+    """The CUDA path through the C ABI against the stored outputs of the reference's own code (1e-12)."""
+    import torch
+    want = _golden(name)
+    P, mesh, G, detJ, m1, m2, x, u0, v0, dt, tf = mrg.setup(wfx, orc, name)
+    rel = lambda a, b: np.linalg.norm(np.asarray(a) - b) / np.linalg.norm(b)
+    geo = wfx.Geometry(mesh, P)
+    for mode in (wfx.capi.STIFF_AUTO, wfx.capi.STIFF_CELL_STREAM):
+        op = wfx.StiffnessOperator(mesh, P, geometry=geo, mode=mode)
+        y = torch.full((mesh.ndofs,), float("nan"), dtype=torch.float64, device="cuda")
+        op.apply(torch.from_numpy(x).cuda(), y, beta=0)
+        assert rel(y.cpu().numpy(), want["stiffness_of_x"]) < 1e-12
+    assert np.array_equal(wfx.MassOperator(mesh, P, geometry=geo).diagonal(), want["lumped_mass"])
+    for key, (ua, va) in (("rest", (np.zeros(mesh.ndofs), np.zeros(mesh.ndofs))), ("state", (u0, v0))):
+        eqn = wfx.LinearGLLOpt(mesh, None, P, mrg.C0, mrg.F0, mrg.P0)
+        eqn.init()
+        eqn.set_state(ua, va)
+        eqn.rk4(0.0, float(want["rk4_tf"]), float(want["rk4_dt"]))
+        u, v = eqn.get_state()
+        assert rel(u, want[f"rk4_from_{key}_u"]) < 1e-12 and rel(v, want[f"rk4_from_{key}_v"]) < 1e-12
