@@ -1,7 +1,8 @@
 """Generates tests/golden/*.npz.
 
 IMPORTANT: the reference (Excalibur-SLE/wave-fenics) ships no golden vectors for this path and cannot
-be built or imported in this environment, so these fixtures are outputs of THIS
+be built or imported as a whole in this environment (what of it does compile produces
+tests/golden/reference_*.npz, see make_reference_golden.py), so these fixtures are outputs of THIS
 repository's CPU oracle (oracle/wave_oracle.c, strict build: -O2 -ffp-contract=off, one thread), not of
 the reference.  They (1) pin the oracle against drift -- tests/test_golden.py re-runs it and compares
 -- and (2) give the GPU box stored values to check the CUDA path against without running the oracle.
