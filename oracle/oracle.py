@@ -106,14 +106,16 @@ def ref_cuda():
     return L
 
 
-def ref_cpu():
-    """ctypes handle of oracle/_ref/libwfref_cpu.so -- the REFERENCE's own cell kernels skernel and mkernel
+def ref_cpu(fast=False):
+    """ctypes handle of oracle/_ref/libwfref_cpu.so (fast: libwfref_cpu_fast.so, the same code at -Ofast for timing) -- the REFERENCE's own cell kernels skernel and mkernel
     (common/operators.hpp:113-133, 36-40), cut out of the header where it lies under /root/reference and
     compiled by oracle/build_ref.py -- or None when it has not been built.
       wfref_skernel(A[nd] (+=), w[nd], G[nq][3][3], dphi[3][nq][nd], nq, nd)
       wfref_mkernel(A[nq] (=), w[nq], detJ[nq], nq, nd)"""
     from . import build_ref
     path = build_ref.build_cpu()
+    if fast and path:
+        path = build_ref.LIB_CPU_FAST
     if not path or not os.path.exists(path):
         return None
     L = C.CDLL(path)

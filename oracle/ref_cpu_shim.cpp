@@ -113,17 +113,29 @@ template <typename T, typename Alloc = std::allocator<T>>
 class Vector
 {
 public:
-  Vector(std::shared_ptr<const common::IndexMap> map, int bs) : _map(map), _x((std::size_t)map->size_local() * bs, T(0)) {}
-  xtl::span<const T> array() const { return xtl::span<const T>(_x.data(), _x.size()); }
-  xtl::span<T> mutable_array() { return xtl::span<T>(_x.data(), _x.size()); }
+  Vector(std::shared_ptr<const common::IndexMap> map, int bs)
+      : _map(map), _x((std::size_t)map->size_local() * bs, T(0)), _p(_x.data()), _n(_x.size())
+  {
+  }
+  // a view of the caller's array (no copy)
+  Vector(std::shared_ptr<const common::IndexMap> map, int bs, T* external)
+      : _map(map), _p(external), _n((std::size_t)map->size_local() * bs)
+  {
+  }
+  Vector(const Vector&) = delete;
+  Vector& operator=(const Vector&) = delete;
+  xtl::span<const T> array() const { return xtl::span<const T>(_p, _n); }
+  xtl::span<T> mutable_array() { return xtl::span<T>(_p, _n); }
   std::shared_ptr<const common::IndexMap> map() const { return _map; }
-  void set(T v) { std::fill(_x.begin(), _x.end(), v); }
+  void set(T v) { std::fill(_p, _p + _n, v); }
   void scatter_fwd() {}                     // one rank
   void scatter_rev(common::IndexMap::Mode) {} // one rank
 
 private:
   std::shared_ptr<const common::IndexMap> _map;
   std::vector<T> _x;
+  T* _p = nullptr;
+  std::size_t _n = 0;
 };
 } // namespace la
 namespace graph
@@ -301,24 +313,18 @@ void wfref_stiffness_apply(int ncells, int ndofs, int nd, const std::int32_t* do
 {
   using namespace standin;
   auto map = std::make_shared<const common::IndexMap>(ndofs);
-  la::Vector<double> vx(map, 1), vy(map, 1);
-  std::copy(x, x + ndofs, vx.mutable_array().begin());
-  std::copy(y, y + ndofs, vy.mutable_array().begin());
+  la::Vector<double> vx(map, 1, const_cast<double*>(x)), vy(map, 1, y); // views: the operator reads x, adds into y
   reference::StiffnessOperator<double> op(ncells, nd, dofmap, G9, dphi);
   op(vx, vy);
-  std::copy(vy.array().begin(), vy.array().end(), y);
 }
 void wfref_mass_apply(int ncells, int ndofs, int nd, const std::int32_t* dofmap, double* detJ, const int* perm,
                       const double* x, double* y)
 {
   using namespace standin;
   auto map = std::make_shared<const common::IndexMap>(ndofs);
-  la::Vector<double> vx(map, 1), vy(map, 1);
-  std::copy(x, x + ndofs, vx.mutable_array().begin());
-  std::copy(y, y + ndofs, vy.mutable_array().begin());
+  la::Vector<double> vx(map, 1, const_cast<double*>(x)), vy(map, 1, y);
   reference::MassOperatorCPU<double> op(ncells, nd, dofmap, detJ, perm);
   op(vx, vy);
-  std::copy(vy.array().begin(), vy.array().end(), y);
 }
 // the reference's LinearGLLOpt::rk4 from (u, v) at t0; dv/dt at (t, u, v) through its f1
 void wfref_rk4(int ncells, int ndofs, int nd, const std::int32_t* dofmap, double* G9, double* dphi, const double* m,
