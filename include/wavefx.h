@@ -189,7 +189,8 @@ int wfx_stiffness_info(wfx_stiffness* op, int64_t* num_cells, int* num_dofs_per_
                        int* nlaunches);
 /* Which kernel the plan selected: variant -1 simple per-cell kernel, 0 generic brick kernel (staged
  * local dofmap), 1 regular-brick kernel (arithmetic positions), 2 the same with the conflict-free P4
- * layout; affine = 1: structured fast path (6 scalars of G per cell, the per-point array is never
+ * layout, 3 / 4 the streamed-cell kernel in colour / brick-plan order (no shared-memory dof arrays; the
+ * other outputs then describe its plan); affine = 1: structured fast path (6 scalars of G per cell, the per-point array is never
  * read); mixed = 1: regular batches and irregular batches run their own kernel (two launches per
  * colour). */
 int wfx_stiffness_kernel_info(wfx_stiffness* op, int* variant, int* affine, int* mixed,
