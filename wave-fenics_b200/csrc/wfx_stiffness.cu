@@ -1635,7 +1635,25 @@ template <> struct Cfg<8> { static constexpr int SLOT = 64, W = WFX_P7_W, BX = W
 #define WFX_CELL2_MIN_N64 99
 #endif
 #ifndef WFX_CELL2_MIN_N32
-#define WFX_CELL2_MIN_N32 8 // P7 fp32: 0.259 ms (colour order) / 0.294 (brick order) against 0.311 for the brick kernel
+#define WFX_CELL2_MIN_N32 8 // P7 fp32: 0.235 ms (colour order) / 0.294 (brick order) against 0.311 for the brick kernel
+#endif
+// fp32 at P6 / P7: planes of G in the register window and min CTAs per SM of the colour-ordered kernel.  With
+// a two-plane window instead of the whole next cell the P7 kernel fits 80 registers without spills (three
+// 256-thread CTAs, 24 warps per SM) or 64 with 80 B of spills (four CTAs, 32 warps); occupancy then hides the
+// latency and walking one cell per slot is fastest: P7 fp32 0.276 (whole-cell window, two CTAs, two cells per
+// slot) -> 0.242 (three CTAs) -> 0.235 ms (four CTAs) = 0.61 of the HBM peak.  P6 fp32 stays with the brick
+// kernel (0.284 against 0.288 at best).
+#ifndef WFX_C2_P7_GW32
+#define WFX_C2_P7_GW32 2
+#endif
+#ifndef WFX_C2_P7_MINB32
+#define WFX_C2_P7_MINB32 4
+#endif
+#ifndef WFX_C2_P6_GW32
+#define WFX_C2_P6_GW32 7
+#endif
+#ifndef WFX_C2_P6_MINB32
+#define WFX_C2_P6_MINB32 WFX_C2_P6_MINB
 #endif
 template <int N> struct Cfg2;
 template <> struct Cfg2<3> { static constexpr int CPB = 16, MINB = 2, GW = 3; };
@@ -1791,7 +1809,7 @@ struct wfx_stiffness
   // streamed-cell path (shares the colour plan): per-point dofmap with FIRST / LAST flags
   bool cell2 = false;
   bool cell2_brick = false; // cells in the order of a brick plan (one CTA per batch) instead of global colours
-  int cell2_cps = 2; // colour order: cells a slot walks per launch
+  int cell2_cps = 1; // colour order: cells a slot walks per launch
   int axis_perm[3] = {0, 1, 2}; // kernel axis a' is the mesh's tensor axis axis_perm[a'] (see detect_axis_perm)
   DevBuf<uint32_t> d_tdmf;
   DevBuf<unsigned char> d_G6perm; // private copy of G6 in the permuted axis order (empty: identity)
@@ -1873,7 +1891,8 @@ void launch_cell2(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   using C2 = Cfg2<N>;
   using C3 = Cfg3<N>;
   using C = Cell2Slot<N>; // whole warps per slot
-  constexpr int GW = sizeof(T) == 4 ? N : C2::GW;
+  constexpr int GW = sizeof(T) == 4 ? (N == 8 ? WFX_C2_P7_GW32 : (N == 7 ? WFX_C2_P6_GW32 : N)) : C2::GW;
+  constexpr int MINB2 = sizeof(T) == 4 ? (N == 8 ? WFX_C2_P7_MINB32 : (N == 7 ? WFX_C2_P6_MINB32 : C2::MINB)) : C2::MINB;
   DMat<T, N> Dm;
   for (int q = 0; q < N * N; ++q) Dm.d[q] = (T)op->Dhost[q];
   for (int q = 0; q < N; ++q) Dm.w[q] = (T)op->Whost[q];
@@ -1932,7 +1951,7 @@ void launch_cell2(wfx_stiffness* op, const T* x, const T* scale, T* y, int beta,
   {
     const int beg = op->cplan.colour_off[k], ncl = op->cplan.colour_off[k + 1] - beg;
     const int per_cta = C2::CPB * op->cell2_cps;
-    launch(stiff_cell2_kernel<T, N, C::SLOT, C2::CPB, C2::MINB, GW, false>, C::SLOT * C2::CPB,
+    launch(stiff_cell2_kernel<T, N, C::SLOT, C2::CPB, MINB2, GW, false>, C::SLOT * C2::CPB,
            (ncl + per_cta - 1) / per_cta, beg, ncl);
   }
 }
