@@ -38,6 +38,14 @@ def run(ncell=64, P=4):
     astiff = wfx.StiffnessOperator(amesh, P, geometry=ageo)
     astiff.apply(x, y, beta=0)
     del astiff, ageo, amesh
+    # the streamed-cell kernel where WFX_STIFF_AUTO takes it: P7 fp32 (37^3 cells, ~17.6 M dofs)
+    smesh = wfx.create_box_hex(37, 7, (0.1,) * 3, perturb=0.15)
+    sgeo = wfx.Geometry(smesh, 7, np.float32)
+    sstiff = wfx.StiffnessOperator(smesh, 7, dtype=np.float32, geometry=sgeo)   # permute_g_axes_kernel at set-up
+    xs = torch.randn(smesh.ndofs, dtype=torch.float32, device="cuda")
+    ys = torch.empty_like(xs)
+    sstiff.apply(xs, ys, beta=0)                                  # stiff_cell2_kernel, 8 colour launches
+    del sstiff, sgeo, smesh, xs, ys
     # the time loop: stiffness, boundary_kernel, rk_stage_kernel<1..4>, set_source_kernel
     os.environ.setdefault("WFX_WAVE_GRAPH", "0")
     model = wfx.LinearGLLOpt(mesh, None, P, 1500.0, 0.5e6, 60000.0)
@@ -59,8 +67,15 @@ def summarise(path):
         per.setdefault(key, {})[r[ci["Metric Name"]]] = (float(r[ci["Metric Value"]].replace(",", "")), r[ci["Metric Unit"]])
     agg = {}
     for (_, name), m in per.items():
-        short = name.split("(")[0]
-        short = short.split("<")[0] + ("<…AFF>" if "true, true" in name.replace("(bool)1, (bool)1", "true, true") else "")
+        clean = name.replace("void ", "").replace("<unnamed>::", "")
+        short = clean.split("(")[0].split("<")[0]
+        if short == "stiff_brick_kernel":  # template arguments: T, N, SLOT, W, MINB, REG, layout, AFF, IDS
+            targs = clean.split("<", 1)[1].split(">(")[0].replace("LayoutStd<", "LayoutStd[").split(",")
+            aff = len(targs) >= 3 and targs[-2].strip() in ("1", "true", "(bool)1")
+            short += "<" + targs[0].strip() + ", N=" + targs[1].strip() + (", AFF" if aff else "") + ">"
+        elif short in ("stiff_cell2_kernel", "stiff_cell_kernel", "rk_stage_kernel"):
+            targs = clean.split("<", 1)[1].split(">(")[0].split(",")
+            short += "<" + ", ".join(t.strip() for t in targs[:2]) + ">"
         a = agg.setdefault(short, dict(n=0, t=0.0, rd=0.0, wr=0.0, pct=0.0, regs=0, occ=0.0))
         t, tu = m["gpu__time_duration.sum"]
         t *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(tu, 1.0)            # -> us
