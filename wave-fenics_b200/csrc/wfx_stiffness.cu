@@ -19,6 +19,10 @@
 //                           are consecutive launches chained by programmatic dependent launch.
 //                           REG = every batch is a lattice brick: arithmetic shared-memory
 //                           positions, no staged local dofmap.
+//   stiff_cell2_kernel      streamed cells: no dof arrays in shared memory, x gathered and y updated
+//                           in global memory, FIRST / LAST flags in the per-point dofmap (fused scaling,
+//                           no memset), cells in colour order or in the order of a brick plan with a
+//                           round barrier; WFX_STIFF_AUTO takes it where it measured faster (P7 fp32).
 // (A persistent single-launch form of the brick kernel was measured slower and removed:
 //  DESIGN.md section 6.)
 #include "wfx_internal.h"
