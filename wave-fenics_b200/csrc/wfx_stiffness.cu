@@ -1662,7 +1662,13 @@ template <> struct Cfg<8> { static constexpr int SLOT = 64, W = WFX_P7_W, BX = W
 template <int N> struct Cfg2;
 template <> struct Cfg2<3> { static constexpr int CPB = 16, MINB = 2, GW = 3; };
 template <> struct Cfg2<4> { static constexpr int CPB = 16, MINB = 2, GW = 4; };
-template <> struct Cfg2<5> { static constexpr int CPB = 8, MINB = 2, GW = 3; };
+#ifndef WFX_C2_P4_GW
+#define WFX_C2_P4_GW 3
+#endif
+#ifndef WFX_C2_P4_MINB
+#define WFX_C2_P4_MINB 2
+#endif
+template <> struct Cfg2<5> { static constexpr int CPB = 8, MINB = WFX_C2_P4_MINB, GW = WFX_C2_P4_GW; };
 template <> struct Cfg2<6> { static constexpr int CPB = WFX_C2_P5_CPB, MINB = WFX_C2_P5_MINB, GW = WFX_C2_P5_GW; };
 template <> struct Cfg2<7> { static constexpr int CPB = WFX_C2_P6_CPB, MINB = WFX_C2_P6_MINB, GW = WFX_C2_P6_GW; };
 template <> struct Cfg2<8> { static constexpr int CPB = WFX_C2_P7_CPB, MINB = WFX_C2_P7_MINB, GW = WFX_C2_P7_GW; };
