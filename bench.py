@@ -563,8 +563,14 @@ def run_b200(args):
                 # the regular-brick kernel never reads a per-point dofmap (positions are arithmetic; it reads
                 # one int32 per brick DOF instead): the same time against the bytes without the +4 B/point term
                 "frac_no_dofmap": bytes_no_dofmap / (ms * 1e-3) / 1e9 / peak,
-                "limiter": "HBM is the bounding roofline; ncu shows the kernel co-limited by the L1TEX/LSU "
-                           "data pipe and load latency at this occupancy (DESIGN.md section 6)"}
+                "limiter": "HBM is the bounding roofline; the measured DRAM traffic over this step time is "
+                           "dram_traffic_gbs (about 0.8 of the copy bandwidth: ~2400 concurrent 6-KB streams plus "
+                           "scattered 136-byte rows); the rest is the 1.14x traffic overhead and load latency at "
+                           "16 warps per SM (DESIGN.md section 6)"}
+    if traffic:
+        # what DRAM actually moved per step (ncu bytes of one launch x launches) over the measured step time
+        roofline["dram_traffic_gbs"] = traffic * info["nlaunches"] / (ms * 1e-3) / 1e9
+        roofline["dram_traffic_frac"] = roofline["dram_traffic_gbs"] / peak
     if sustained:
         roofline["sustained"] = {"ms_per_step": sustained["ms_per_step"], "steps": sustained["steps"],
                                  "achieved": info["bytes"] / (sustained["ms_per_step"] * 1e-3) / 1e9,
