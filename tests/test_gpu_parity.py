@@ -938,3 +938,50 @@ def test_cuda_rk4_against_the_reference_time_stepper(wfx, orc, torch, capfd, sha
     so, to = orc.rk4(mesh, P, Go, m, m1, m2, c0, f0, p0, 0.0, tf, dt, uo, vo, sumfact=True)
     assert (s, t) == (so, to) and s >= nsteps and np.abs(ur).max() > 0
     assert rel_l2(u, ur) < TOL64 and rel_l2(v, vr) < TOL64
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_rank_without_cells(wfx, torch, dtype):
+    """A rank that owns no cell (only ghost dofs, or nothing): every operator is a no-op of the right kind --
+    y = A x zeroes y, y += A x leaves it, the lumped mass is zero, gather / scatter of nothing succeed."""
+    from wave_fenics_b200.mesh import HexMesh
+    P, nd, ndofs = 4, 125, 7
+    mesh = HexMesh(P=P, shape=(0, 0, 0), x=np.zeros((0, 3)), xdofs=np.zeros((0, 8), dtype=np.int32),
+                   dofmap=np.zeros((0, nd), dtype=np.int32), ndofs=ndofs, size_local=0,
+                   facet_cells=np.zeros(0, dtype=np.int32), facet_local=np.zeros(0, dtype=np.int32),
+                   facet_tags=np.zeros(0, dtype=np.int32), h_min=1.0, lengths=(1.0, 1.0, 1.0), ndofs_global=ndofs)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    geo = wfx.Geometry(mesh, P, dtype)
+    for mode in (wfx.capi.STIFF_AUTO, wfx.capi.STIFF_CELL_STREAM, wfx.capi.STIFF_CELL_COLOUR):
+        op = wfx.StiffnessOperator(mesh, P, dtype=dtype, geometry=geo, mode=mode)
+        x = torch.ones(ndofs, dtype=tdt, device="cuda")
+        y = torch.full_like(x, float("nan"))
+        op.apply(x, y, beta=0)
+        assert (y == 0).all()
+        y.fill_(3.0)
+        op(x, y)
+        assert (y == 3.0).all()
+    mass = wfx.MassOperator(mesh, P, dtype=dtype, geometry=geo)
+    assert (mass.diagonal() == 0).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P", [2, 4, 7])
+def test_single_cell_mesh(wfx, orc, torch, P):
+    """The smallest mesh: one (perturbed) cell; every stiffness kernel, the lumped mass and one RK4 step."""
+    mesh = wfx.create_box_hex((1, 1, 1), P, (L, 0.8 * L, 1.1 * L), perturb=0.0)
+    mesh.x = mesh.x + 0.05 * L * np.random.default_rng(P).uniform(-1, 1, mesh.x.shape)   # a general hexahedron
+    geo = wfx.Geometry(mesh, P)
+    Go, detJ = orc.precompute_geometric_data(mesh, P)
+    x = np.random.default_rng(1).standard_normal(mesh.ndofs)
+    kx = np.zeros(mesh.ndofs)
+    orc.stiffness_apply(mesh, P, Go, x, kx, dense=True)
+    for mode in (wfx.capi.STIFF_AUTO, wfx.capi.STIFF_CELL_STREAM, wfx.capi.STIFF_CELL_COLOUR):
+        op = wfx.StiffnessOperator(mesh, P, geometry=geo, mode=mode)
+        y = torch.full((mesh.ndofs,), float("nan"), dtype=torch.float64, device="cuda")
+        op.apply(dev(torch, x), y, beta=0)
+        assert rel_l2(y.cpu().numpy(), kx) < TOL64
+    m = np.zeros(mesh.ndofs)
+    orc.mass_apply(mesh, P, detJ, np.ones(mesh.ndofs), m)
+    assert np.array_equal(wfx.MassOperator(mesh, P, geometry=geo).diagonal(), m)
