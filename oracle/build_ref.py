@@ -120,6 +120,38 @@ def build_cpu(force=False):
     return LIB_CPU
 
 
+LIB_MESH = os.path.join(OUT, "libwfref_mesh.so")
+
+
+def build_mesh(force=False):
+    """oracle/_ref/libwfref_mesh.so: the reference's partition arithmetic decompose3d /
+    compute_cartesian_indices (demo/gpu_cg/mesh.hpp:37-62), cut out of the header and compiled against the
+    stand-in of oracle/ref_mesh_shim.cpp.  None when neither the sources nor a prebuilt library exist."""
+    hdr = os.path.join(REF, "demo", "gpu_cg", "mesh.hpp")
+    shim = os.path.join(HERE, "ref_mesh_shim.cpp")
+    if not os.path.exists(hdr):
+        return LIB_MESH if os.path.exists(LIB_MESH) else None
+    if not force and os.path.exists(LIB_MESH) and os.path.getmtime(LIB_MESH) >= max(
+            os.path.getmtime(hdr), os.path.getmtime(shim), os.path.getmtime(__file__)):
+        return LIB_MESH
+    os.makedirs(OUT, exist_ok=True)
+    text = open(hdr).read()
+    inc = os.path.join(OUT, "ref_mesh_functions.inc")
+    with open(inc, "w") as fh:
+        fh.write(_cut(text, "decompose3d(int x)", with_template=False))
+        fh.write(_cut(text, "compute_cartesian_indices(", with_template=False))
+    try:
+        cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", OUT, shim, "-o", LIB_MESH]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("building oracle/_ref/libwfref_mesh.so failed")
+    finally:
+        os.remove(inc)
+    return LIB_MESH
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
     print(build_cpu(force="--force" in sys.argv))
+    print(build_mesh(force="--force" in sys.argv))

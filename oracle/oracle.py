@@ -137,6 +137,21 @@ def ref_cpu(fast=False):
     return L
 
 
+def ref_mesh():
+    """ctypes handle of oracle/_ref/libwfref_mesh.so -- the REFERENCE's own decompose3d and
+    compute_cartesian_indices (demo/gpu_cg/mesh.hpp:37-62) -- or None when it has not been built."""
+    from . import build_ref
+    path = build_ref.build_mesh()
+    if not path or not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.wfref_decompose3d.argtypes = [C.c_int, C.POINTER(C.c_int)]
+    L.wfref_decompose3d.restype = None
+    L.wfref_cartesian_indices.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
+    L.wfref_cartesian_indices.restype = None
+    return L
+
+
 def reference_stiffness_apply(mesh, P, G, x, y):
     """y += A x through the REFERENCE's own StiffnessOperator::operator() and skernel
     (common/operators.hpp:182-200, 113-133), compiled into oracle/_ref/libwfref_cpu.so."""

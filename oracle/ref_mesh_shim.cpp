@@ -1,0 +1,78 @@
+// C entry points over the REFERENCE's own partition arithmetic -- decompose3d and
+// compute_cartesian_indices (demo/gpu_cg/mesh.hpp:37-62), which partition.py follows -- for
+// oracle/_ref/libwfref_cpu.so's sibling libwfref_mesh.so.  TEST INFRASTRUCTURE ONLY.  The two functions
+// are cut out of the header where it lies under /root/reference at build time (oracle/build_ref.py,
+// oracle/_ref/ref_mesh_functions.inc, deleted again after the compile); this file supplies the
+// xt::xtensor stand-in they need and contains no reference code.
+#include <cmath>
+#include <cstddef>
+#include <cstdlib>
+#include <functional>
+#include <initializer_list>
+#include <numeric>
+#include <vector>
+
+namespace xt
+{
+template <typename T>
+struct zeros_expr
+{
+  std::vector<std::size_t> shape;
+};
+template <typename T, typename S>
+zeros_expr<T> zeros(std::initializer_list<S> shape)
+{
+  zeros_expr<T> z;
+  for (S s : shape) z.shape.push_back((std::size_t)s);
+  return z;
+}
+// owning row-major array of rank R: [i], (i, j), begin / end -- what the cut functions use
+template <typename T, std::size_t R>
+class xtensor
+{
+public:
+  xtensor() = default;
+  template <typename U>
+  xtensor(const zeros_expr<U>& z) : _shape(z.shape)
+  {
+    std::size_t n = 1;
+    for (std::size_t s : _shape) n *= s;
+    _d.assign(n, T(0));
+  }
+  T& operator[](std::size_t i) { return _d[i]; }
+  const T& operator[](std::size_t i) const { return _d[i]; }
+  T& operator()(std::size_t i, std::size_t j) { return _d[i * _shape[1] + j]; }
+  const T& operator()(std::size_t i, std::size_t j) const { return _d[i * _shape[1] + j]; }
+  typename std::vector<T>::iterator begin() { return _d.begin(); }
+  typename std::vector<T>::iterator end() { return _d.end(); }
+  std::size_t shape(std::size_t i) const { return _shape[i]; }
+
+private:
+  std::vector<std::size_t> _shape;
+  std::vector<T> _d;
+};
+} // namespace xt
+
+namespace reference
+{
+#include "ref_mesh_functions.inc" // decompose3d, compute_cartesian_indices
+} // namespace reference
+
+extern "C" {
+// 2^x ranks -> (2^x0, 2^x1, 2^x2)
+void wfref_decompose3d(int x, int* out)
+{
+  const xt::xtensor<int, 1> n = reference::decompose3d(x);
+  for (int a = 0; a < 3; ++a) out[a] = n[a];
+}
+// rank -> (Ix, Iy, Iz) for all ranks of a procs[0] x procs[1] x procs[2] grid; out [size][3]
+void wfref_cartesian_indices(const int* procs, long long* out)
+{
+  xt::xtensor<int, 1> p = xt::zeros<int>({3});
+  for (int a = 0; a < 3; ++a) p[a] = procs[a];
+  const int size = procs[0] * procs[1] * procs[2];
+  const xt::xtensor<std::size_t, 2> idx = reference::compute_cartesian_indices(p);
+  for (int i = 0; i < size; ++i)
+    for (int a = 0; a < 3; ++a) out[3 * i + a] = (long long)idx(i, a);
+}
+}

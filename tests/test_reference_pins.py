@@ -178,3 +178,22 @@ def test_cuda_path_matches_the_reference_golden_vectors(wfx, orc, name):
         eqn.rk4(0.0, float(want["rk4_tf"]), float(want["rk4_dt"]))
         u, v = eqn.get_state()
         assert rel(u, want[f"rk4_from_{key}_u"]) < 1e-12 and rel(v, want[f"rk4_from_{key}_v"]) < 1e-12
+
+
+# ---- the reference's partition arithmetic (demo/gpu_cg/mesh.hpp:37-62) ------------------------------------
+def test_rank_grid_is_the_reference_decompose3d(wfx, orc):
+    import ctypes as C
+    L = orc.ref_mesh()
+    if L is None:
+        pytest.skip("oracle/_ref/libwfref_mesh.so was not built (needs /root/reference at build time)")
+    from wave_fenics_b200 import partition
+    for x in range(0, 10):                                # 1 .. 512 ranks (powers of two: all the reference handles)
+        out = (C.c_int * 3)()
+        L.wfref_decompose3d(x, out)
+        grid = partition.rank_grid(2 ** x)
+        assert tuple(out) == tuple(grid)
+        idx = (C.c_longlong * (3 * 2 ** x))()
+        L.wfref_cartesian_indices((C.c_int * 3)(*grid), idx)
+        want = np.array(list(idx)).reshape(-1, 3)
+        got = np.array([partition.rank_coords(grid, r) for r in range(2 ** x)])
+        assert np.array_equal(got, want)
