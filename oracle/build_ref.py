@@ -140,6 +140,7 @@ def build_mesh(force=False):
     with open(inc, "w") as fh:
         fh.write(_cut(text, "decompose3d(int x)", with_template=False))
         fh.write(_cut(text, "compute_cartesian_indices(", with_template=False))
+        fh.write(_cut(open(os.path.join(REF, "common", "permute.hpp")).read(), "void reorder_dofmap(", with_template=False))
     try:
         cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", OUT, shim, "-o", LIB_MESH]
         r = subprocess.run(cmd, capture_output=True, text=True)

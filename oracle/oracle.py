@@ -149,6 +149,8 @@ def ref_mesh():
     L.wfref_decompose3d.restype = None
     L.wfref_cartesian_indices.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
     L.wfref_cartesian_indices.restype = None
+    L.wfref_reorder_dofmap.argtypes = [C.c_int, C.c_int, C.c_int, _i32p, _i32p, _i32p]
+    L.wfref_reorder_dofmap.restype = None
     return L
 
 

@@ -1,5 +1,6 @@
 // C entry points over the REFERENCE's own partition arithmetic -- decompose3d and
-// compute_cartesian_indices (demo/gpu_cg/mesh.hpp:37-62), which partition.py follows -- for
+// compute_cartesian_indices (demo/gpu_cg/mesh.hpp:37-62), which partition.py follows -- and its
+// reorder_dofmap (common/permute.hpp:10-28), for
 // oracle/_ref/libwfref_cpu.so's sibling libwfref_mesh.so.  TEST INFRASTRUCTURE ONLY.  The two functions
 // are cut out of the header where it lies under /root/reference at build time (oracle/build_ref.py,
 // oracle/_ref/ref_mesh_functions.inc, deleted again after the compile); this file supplies the
@@ -53,9 +54,38 @@ private:
 };
 } // namespace xt
 
+// stand-in for the Basix calls of reorder_dofmap (common/permute.hpp:10-28): the element only has to hand
+// out the tensor-product permutation, which the caller supplies (it is Basix's arithmetic, absent here)
+#include <tuple>
+namespace basix
+{
+namespace element
+{
+enum class family { P };
+enum class lagrange_variant { gll_warped };
+} // namespace element
+namespace cell
+{
+enum class type { hexahedron };
+}
+inline std::vector<int>& supplied_perm()
+{
+  static std::vector<int> p;
+  return p;
+}
+struct FiniteElement
+{
+  std::vector<std::tuple<std::vector<int>, std::vector<int>>> get_tensor_product_representation() const
+  {
+    return {std::make_tuple(std::vector<int>(), supplied_perm())};
+  }
+};
+inline FiniteElement create_element(element::family, cell::type, int, element::lagrange_variant) { return FiniteElement(); }
+} // namespace basix
+
 namespace reference
 {
-#include "ref_mesh_functions.inc" // decompose3d, compute_cartesian_indices
+#include "ref_mesh_functions.inc" // decompose3d, compute_cartesian_indices, reorder_dofmap
 } // namespace reference
 
 extern "C" {
@@ -64,6 +94,14 @@ void wfref_decompose3d(int x, int* out)
 {
   const xt::xtensor<int, 1> n = reference::decompose3d(x);
   for (int a = 0; a < 3; ++a) out[a] = n[a];
+}
+// out = reorder_dofmap(in) with the given tensor-product permutation (common/permute.hpp:10-28)
+void wfref_reorder_dofmap(int p, int nd, int ncells, const int* perm, const int* in, int* out)
+{
+  basix::supplied_perm().assign(perm, perm + nd);
+  std::vector<int> vin(in, in + (std::size_t)ncells * nd), vout((std::size_t)ncells * nd, -1);
+  reference::reorder_dofmap(vout, vin, p);
+  for (std::size_t i = 0; i < vout.size(); ++i) out[i] = vout[i];
 }
 // rank -> (Ix, Iy, Iz) for all ranks of a procs[0] x procs[1] x procs[2] grid; out [size][3]
 void wfref_cartesian_indices(const int* procs, long long* out)

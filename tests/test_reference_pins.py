@@ -197,3 +197,20 @@ def test_rank_grid_is_the_reference_decompose3d(wfx, orc):
         want = np.array(list(idx)).reshape(-1, 3)
         got = np.array([partition.rank_coords(grid, r) for r in range(2 ** x)])
         assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("P", [1, 2, 4, 7])
+def test_reorder_dofmap_is_the_reference_loop(wfx, orc, P):
+    """reorder_dofmap (common/permute.hpp:10-28) with the tensor-product permutation supplied (Basix's part):
+    the oracle's and the product's host function equal the reference's own loop."""
+    L = orc.ref_mesh()
+    if L is None:
+        pytest.skip("oracle/_ref/libwfref_mesh.so was not built (needs /root/reference at build time)")
+    nd = (P + 1) ** 3
+    rng = np.random.default_rng(P)
+    dm = rng.integers(0, 10 ** 6, size=(11, nd)).astype(np.int32)
+    pm = np.ascontiguousarray(orc.perm(P), dtype=np.int32)
+    out = np.empty_like(dm)
+    L.wfref_reorder_dofmap(P, nd, dm.shape[0], orc._i(pm), orc._i(dm.reshape(-1)), orc._i(out.reshape(-1)))
+    assert np.array_equal(orc.reorder_dofmap(dm, P), out)
+    assert np.array_equal(wfx.capi.reorder_dofmap(dm, P), out)
