@@ -141,14 +141,22 @@ def build_mesh(force=False):
         fh.write(_cut(text, "decompose3d(int x)", with_template=False))
         fh.write(_cut(text, "compute_cartesian_indices(", with_template=False))
         fh.write(_cut(open(os.path.join(REF, "common", "permute.hpp")).read(), "void reorder_dofmap(", with_template=False))
+    # the statements between "// Temporal parameters" and the first print of demo/cpu_planar3d/main.cpp
+    demo = open(os.path.join(REF, "demo", "cpu_planar3d", "main.cpp")).read().split("\n")
+    a = next(i for i, l in enumerate(demo) if "// Temporal parameters" in l)
+    b = next(i for i in range(a, len(demo)) if "if (rank == 0)" in demo[i])
+    inc2 = os.path.join(OUT, "ref_demo_params.inc")
+    with open(inc2, "w") as fh:
+        fh.write("\n".join(demo[a + 1:b]) + "\n")
     try:
-        cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", OUT, shim, "-o", LIB_MESH]
+        cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-I", OUT, shim, "-o", LIB_MESH]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("building oracle/_ref/libwfref_mesh.so failed")
     finally:
         os.remove(inc)
+        os.remove(inc2)
     return LIB_MESH
 
 

@@ -151,6 +151,9 @@ def ref_mesh():
     L.wfref_cartesian_indices.restype = None
     L.wfref_reorder_dofmap.argtypes = [C.c_int, C.c_int, C.c_int, _i32p, _i32p, _i32p]
     L.wfref_reorder_dofmap.restype = None
+    L.wfref_demo_time_parameters.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, _f64p, _f64p,
+                                             C.POINTER(C.c_int)]
+    L.wfref_demo_time_parameters.restype = None
     return L
 
 

@@ -103,6 +103,19 @@ void wfref_reorder_dofmap(int p, int nd, int ncells, const int* perm, const int*
   reference::reorder_dofmap(vout, vin, p);
   for (std::size_t i = 0; i < vout.size(); ++i) out[i] = vout[i];
 }
+// the temporal parameters of the reference demo (demo/cpu_planar3d/main.cpp:59-66: CFL time step snapped to
+// whole steps per period, final time), computed by the demo's own statements from the smallest mesh size
+void wfref_demo_time_parameters(double meshSize, double speedOfSound, double sourceFrequency, double domainLength,
+                                int degreeOfBasis, double* dt, double* tf, int* steps_per_period)
+{
+  double period = 1 / sourceFrequency; // (main.cpp:30)
+  using std::pow;
+#include "ref_demo_params.inc"
+  (void)startTime;
+  *dt = timeStepSize;
+  *tf = finalTime;
+  *steps_per_period = stepPerPeriod;
+}
 // rank -> (Ix, Iy, Iz) for all ranks of a procs[0] x procs[1] x procs[2] grid; out [size][3]
 void wfref_cartesian_indices(const int* procs, long long* out)
 {

@@ -214,3 +214,19 @@ def test_reorder_dofmap_is_the_reference_loop(wfx, orc, P):
     L.wfref_reorder_dofmap(P, nd, dm.shape[0], orc._i(pm), orc._i(dm.reshape(-1)), orc._i(out.reshape(-1)))
     assert np.array_equal(orc.reorder_dofmap(dm, P), out)
     assert np.array_equal(wfx.capi.reorder_dofmap(dm, P), out)
+
+
+def test_time_step_is_the_reference_demos(wfx, orc):
+    """cfl_timestep and the final time of the planar-wave runs against the demo's own statements
+    (demo/cpu_planar3d/main.cpp:59-66), bit for bit."""
+    import ctypes as C
+    L = orc.ref_mesh()
+    if L is None:
+        pytest.skip("oracle/_ref/libwfref_mesh.so was not built (needs /root/reference at build time)")
+    rng = np.random.default_rng(2)
+    for P in (2, 3, 4, 5, 7):
+        for h in list(rng.uniform(1e-4, 5e-2, 6)) + [np.sqrt(3.0) * 0.1 / 16]:
+            dt, tf, spp = C.c_double(), C.c_double(), C.c_int()
+            L.wfref_demo_time_parameters(float(h), 1500.0, 0.5e6, 0.1, P, C.byref(dt), C.byref(tf), C.byref(spp))
+            assert wfx.cfl_timestep(float(h), 1500.0, P, 0.5e6) == dt.value
+            assert 0.1 / 1500.0 + 8.0 / 0.5e6 == tf.value
