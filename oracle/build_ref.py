@@ -141,6 +141,7 @@ def build_mesh(force=False):
         fh.write(_cut(text, "decompose3d(int x)", with_template=False))
         fh.write(_cut(text, "compute_cartesian_indices(", with_template=False))
         fh.write(_cut(open(os.path.join(REF, "common", "permute.hpp")).read(), "void reorder_dofmap(", with_template=False))
+        fh.write(_cut(open(os.path.join(REF, "common", "precompute.hpp")).read(), "void dot(const U& A"))
     # the statements between "// Temporal parameters" and the first print of demo/cpu_planar3d/main.cpp
     demo = open(os.path.join(REF, "demo", "cpu_planar3d", "main.cpp")).read().split("\n")
     a = next(i for i, l in enumerate(demo) if "// Temporal parameters" in l)

@@ -154,6 +154,8 @@ def ref_mesh():
     L.wfref_demo_time_parameters.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, _f64p, _f64p,
                                              C.POINTER(C.c_int)]
     L.wfref_demo_time_parameters.restype = None
+    L.wfref_dot.argtypes = [_f64p, C.c_int, C.c_int, _f64p, C.c_int, C.c_int, _f64p, C.c_int]
+    L.wfref_dot.restype = None
     return L
 
 

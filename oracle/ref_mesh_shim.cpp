@@ -116,6 +116,22 @@ void wfref_demo_time_parameters(double meshSize, double speedOfSound, double sou
   *tf = finalTime;
   *steps_per_period = stepPerPeriod;
 }
+// C (3x3, accumulated into) = op(A) op(B) through the reference's dot (common/precompute.hpp:17-41), the
+// small matrix product of compute_jacobian (transpose: A [nodes][3], B [3][nodes]) and of
+// compute_geometrical_factor (A, B 3x3)
+struct Mat
+{
+  double* d;
+  int r, c;
+  int shape(int i) const { return i == 0 ? r : c; }
+  double& operator()(int i, int j) { return d[i * c + j]; }
+  const double& operator()(int i, int j) const { return d[i * c + j]; }
+};
+void wfref_dot(double* A, int ar, int ac, double* B, int br, int bc, double* C, int transpose)
+{
+  Mat a{A, ar, ac}, b{B, br, bc}, c{C, 3, 3};
+  reference::dot(a, b, c, transpose != 0);
+}
 // rank -> (Ix, Iy, Iz) for all ranks of a procs[0] x procs[1] x procs[2] grid; out [size][3]
 void wfref_cartesian_indices(const int* procs, long long* out)
 {

@@ -230,3 +230,38 @@ def test_time_step_is_the_reference_demos(wfx, orc):
             L.wfref_demo_time_parameters(float(h), 1500.0, 0.5e6, 0.1, P, C.byref(dt), C.byref(tf), C.byref(spp))
             assert wfx.cfl_timestep(float(h), 1500.0, P, 0.5e6) == dt.value
             assert 0.1 / 1500.0 + 8.0 / 0.5e6 == tf.value
+
+
+def test_general_point_jacobian_and_factor_use_the_reference_dot(wfx, orc):
+    """compute_jacobian and compute_geometrical_factor (common/precompute.hpp:49-96, 148-176) are the reference's
+    small matrix product `dot` (:17-41) around DOLFINx's det / inv: with the oracle's inverse supplied, its J and G
+    equal the reference's own `dot` bit for bit (row a9)."""
+    L = orc.ref_mesh()
+    if L is None:
+        pytest.skip("oracle/_ref/libwfref_mesh.so was not built (needs /root/reference at build time)")
+    mesh = wfx.create_box_hex((2, 2, 1), 2, (1.0, 0.7, 1.3), perturb=0.2)
+    pts = np.random.default_rng(4).uniform(0, 1, size=(5, 3))
+    wts = np.random.default_rng(5).uniform(0.1, 1, size=5)
+    d = orc.jacobian_data(mesh, pts, wts)
+    for c in range(mesh.ncells):
+        for q in range(5):
+            K = np.ascontiguousarray(d["K"][c, q])
+            KT = np.ascontiguousarray(K.T)
+            G = np.zeros((3, 3))
+            L.wfref_dot(orc._f(K.reshape(-1)), 3, 3, orc._f(KT.reshape(-1)), 3, 3, orc._f(G.reshape(-1)), 0)
+            assert np.array_equal(G * (d["detJ"][c, q] * wts[q]), d["G"][c, q])
+    # the Jacobian: dot(coords [8][3], dphi [3][8], J, transpose = true); dphi from J itself is not available, so
+    # check the transpose branch on random operands against the same sum written out in the oracle's order
+    rng = np.random.default_rng(6)
+    A, B = rng.standard_normal((8, 3)), rng.standard_normal((3, 8))
+    Cm = np.zeros((3, 3))
+    L.wfref_dot(orc._f(np.ascontiguousarray(A).reshape(-1)), 8, 3, orc._f(np.ascontiguousarray(B).reshape(-1)), 3, 8,
+                orc._f(Cm.reshape(-1)), 1)
+    want = np.zeros((3, 3))
+    for i in range(3):
+        for j in range(3):
+            s_ = 0.0
+            for k in range(8):
+                s_ += A[k, i] * B[j, k]
+            want[i, j] = s_
+    assert np.array_equal(Cm, want)
