@@ -15,8 +15,10 @@
  *   time and compiled against container stand-ins (oracle/build_ref.py,
  *   oracle/ref_cpu_shim.cpp -> oracle/_ref/libwfref_cpu.so); the restatements below
  *   reproduce them BIT FOR BIT -- operators, right-hand side, whole RK4 trajectories
- *   (tests/test_reference_pins.py).  Likewise gather / scatter / transform1 against
- *   the reference's CUDA kernels (oracle/_ref/libwfref_cuda.so).
+ *   (tests/test_reference_pins.py).  Likewise reorder_dofmap's loop, precompute.hpp's
+ *   dot, the demo's CFL time step and the partition arithmetic decompose3d /
+ *   compute_cartesian_indices (oracle/_ref/libwfref_mesh.so), and gather / scatter /
+ *   transform1 against the reference's CUDA kernels (oracle/_ref/libwfref_cuda.so).
  *  UNPINNED (third-party arithmetic the reference calls, absent here): the Basix /
  *   DOLFINx pieces -- GLL quadrature, gll_warped Lagrange tabulation, tensor-product
  *   permutation, cmap tabulation, math::det / math::inv inside
